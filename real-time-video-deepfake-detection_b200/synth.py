@@ -1,0 +1,193 @@
+"""Synthetic inputs for tests and benchmarks (host-side data generation only).
+
+There is no network in the build or GPU image, the reference's checkpoint
+``weights/best_model.pth`` is absent from the snapshot (.MISSING_LARGE_BLOBS)
+and no dataset ships, so every measurement runs on:
+
+  * synthetic BGR uint8 frames of five families that hit
+    distinct branches of the forensic score tables;
+  * synthetic face boxes (faces are inputs -- face detection is out of scope);
+  * a fixed-seed random-init ``net.*`` state_dict in the reference checkpoint's
+    layout whose BatchNorm running statistics are calibrated on a small batch
+    so activations stay O(1) through all 16 MBConv blocks and logits spread
+    over a few units (an uncalibrated random net saturates the sigmoid and
+    makes probability parity vacuous -- SURVEY.md "hard part 4").
+
+Nothing here runs on the per-frame path.
+"""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import arch
+
+FAMILIES = ("uniform", "pink", "blur", "flat", "gradient")
+
+
+# --------------------------------------------------------------------------
+# frames / boxes
+# --------------------------------------------------------------------------
+def _pink(rng, h, w):
+    fy = np.fft.fftfreq(h)[:, None]
+    fx = np.fft.fftfreq(w)[None, :]
+    f = np.sqrt(fx * fx + fy * fy)
+    f[0, 0] = 1.0
+    chans = []
+    for _ in range(3):
+        spec = np.fft.fft2(rng.standard_normal((h, w))) / f ** 0.6
+        spec[0, 0] = 0
+        x = np.real(np.fft.ifft2(spec))
+        x = x / (x.std() + 1e-9) * 45.0 + 120.0 + rng.normal(0, 3, (h, w))
+        chans.append(x)
+    return np.clip(np.stack(chans, -1), 0, 255).astype(np.uint8)
+
+
+def make_frame(family, h, w, rng):
+    """One BGR uint8 frame of the given family."""
+    import cv2
+    if family == "uniform":
+        return rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    if family == "pink":
+        return _pink(rng, h, w)
+    if family == "blur":
+        x = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        return cv2.GaussianBlur(x, (31, 31), 8)
+    if family == "flat":
+        return np.full((h, w, 3), 128, np.uint8)
+    if family == "gradient":
+        img = np.zeros((h, w, 3), np.uint8)
+        img[:, :, :] = (np.arange(h)[:, None, None] * 255 // h).astype(np.uint8)
+        cv2.rectangle(img, (w // 5, h // 5), (w * 4 // 5, h * 4 // 5), (255, 0, 0), 3)
+        cv2.circle(img, (w // 2, h // 2), min(h, w) // 4, (0, 255, 0), 3)
+        return img
+    raise ValueError(family)
+
+
+def make_sequence(family, h, w, n, seed=1234, jitter=2.0):
+    """n frames of one stream: base frame + per-frame N(0, jitter) noise."""
+    rng = np.random.RandomState(seed)
+    base = make_frame(family, h, w, rng).astype(np.float32)
+    out = []
+    for _ in range(n):
+        out.append(np.clip(base + rng.normal(0, jitter, base.shape), 0, 255).astype(np.uint8))
+    return out
+
+
+def make_boxes(n, h, w, rng, lo=96, hi=400):
+    """(n,4) int32 boxes x,y,w,h fully inside an h x w frame."""
+    boxes = np.zeros((n, 4), np.int32)
+    for i in range(n):
+        bw = int(rng.randint(lo, min(hi, w) + 1))
+        bh = int(rng.randint(lo, min(hi, h) + 1))
+        boxes[i] = (rng.randint(0, w - bw + 1), rng.randint(0, h - bh + 1), bw, bh)
+    return boxes
+
+
+# --------------------------------------------------------------------------
+# random-init, BN-calibrated state_dict in the reference checkpoint layout
+# --------------------------------------------------------------------------
+def _calib_batch(gen, n=16):
+    lo = torch.rand(n, 3, 28, 28, generator=gen, dtype=torch.float64)
+    x = F.interpolate(lo, size=(224, 224), mode="bilinear", align_corners=False)
+    x = (x + 0.08 * torch.randn(n, 3, 224, 224, generator=gen, dtype=torch.float64)).clamp(0, 1)
+    mean = torch.tensor([0.485, 0.456, 0.406], dtype=torch.float64).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], dtype=torch.float64).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+def _conv_same(x, w, stride, groups=1):
+    k = w.shape[-1]
+    lo_h, hi_h = arch.same_pad(x.shape[2], k, stride)
+    lo_w, hi_w = arch.same_pad(x.shape[3], k, stride)
+    return F.conv2d(F.pad(x, (lo_w, hi_w, lo_h, hi_h)), w, None, stride=stride, groups=groups)
+
+
+def make_state_dict(seed=1234, logit_gain=1.5, cache=True):
+    """Fixed-seed random weights + calibrated BN statistics (float32 tensors,
+    374 entries, lukemelas names under ``net.``).  Calibration runs a 16-image
+    synthetic batch through each layer in float64 as the layer is created and
+    sets that layer's running_mean/var to the batch statistics."""
+    path = f"/tmp/dfd_synth_state_dict_seed{seed}_g{logit_gain}.pt"
+    if cache and os.path.exists(path):
+        return torch.load(path, map_location="cpu", weights_only=True)
+    gen = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    dd = torch.float64
+
+    def randn(*shape, std=1.0):
+        return torch.randn(*shape, generator=gen, dtype=dd) * std
+
+    def rand(*shape, lo=0.0, hi=1.0):
+        return torch.rand(*shape, generator=gen, dtype=dd) * (hi - lo) + lo
+
+    def bn_calibrated(prefix, y, gamma_lo=0.8, gamma_hi=1.2, beta_std=0.2, eps=arch.BN_EPS):
+        dims = (0, 2, 3) if y.dim() == 4 else (0,)
+        c = y.shape[1]
+        m = y.mean(dims)
+        v = y.var(dims, unbiased=False) + 1e-6
+        g = rand(c, lo=gamma_lo, hi=gamma_hi)
+        b = randn(c, std=beta_std)
+        sd[prefix + ".weight"], sd[prefix + ".bias"] = g, b
+        sd[prefix + ".running_mean"], sd[prefix + ".running_var"] = m, v
+        sd[prefix + ".num_batches_tracked"] = torch.tensor(1, dtype=torch.int64)
+        shape = (1, c, 1, 1) if y.dim() == 4 else (1, c)
+        return (y - m.view(shape)) / torch.sqrt(v.view(shape) + eps) * g.view(shape) + b.view(shape)
+
+    def swish(t):
+        return t * torch.sigmoid(t)
+
+    x = _calib_batch(gen)
+    w = randn(32, 3, 3, 3, std=(2.0 / 27) ** 0.5)
+    sd["net._conv_stem.weight"] = w
+    x = swish(bn_calibrated("net._bn0", _conv_same(x, w, 2)))
+    for i, b in enumerate(arch.BLOCKS):
+        p = f"net._blocks.{i}."
+        inp = x
+        if b.cexp != b.cin:
+            w = randn(b.cexp, b.cin, 1, 1, std=(2.0 / b.cin) ** 0.5)
+            sd[p + "_expand_conv.weight"] = w
+            x = swish(bn_calibrated(p + "_bn0", F.conv2d(x, w)))
+        w = randn(b.cexp, 1, b.k, b.k, std=(2.0 / (b.k * b.k)) ** 0.5)
+        sd[p + "_depthwise_conv.weight"] = w
+        x = swish(bn_calibrated(p + "_bn1", _conv_same(x, w, b.s, groups=b.cexp)))
+        wr = randn(b.se, b.cexp, 1, 1, std=(1.0 / b.cexp) ** 0.5)
+        br = randn(b.se, std=0.1)
+        we = randn(b.cexp, b.se, 1, 1, std=(1.0 / b.se) ** 0.5)
+        be = randn(b.cexp, std=0.5) + 1.0
+        sd[p + "_se_reduce.weight"], sd[p + "_se_reduce.bias"] = wr, br
+        sd[p + "_se_expand.weight"], sd[p + "_se_expand.bias"] = we, be
+        sq = swish(F.conv2d(x.mean((2, 3), keepdim=True), wr, br))
+        x = x * torch.sigmoid(F.conv2d(sq, we, be))
+        w = randn(b.cout, b.cexp, 1, 1, std=(1.0 / b.cexp) ** 0.5)
+        sd[p + "_project_conv.weight"] = w
+        skip = b.s == 1 and b.cin == b.cout
+        x = bn_calibrated(p + "_bn2", F.conv2d(x, w),
+                          gamma_lo=0.4 if skip else 0.8, gamma_hi=0.7 if skip else 1.2, beta_std=0.1)
+        if skip:
+            x = x + inp
+    w = randn(1280, 320, 1, 1, std=(2.0 / 320) ** 0.5)
+    sd["net._conv_head.weight"] = w
+    x = swish(bn_calibrated("net._bn1", F.conv2d(x, w)))
+    f = x.mean((2, 3))
+    w, bb = randn(512, 1280, std=(2.0 / 1280) ** 0.5), randn(512, std=0.05)
+    sd["net._fc.1.weight"], sd["net._fc.1.bias"] = w, bb
+    f = F.relu(bn_calibrated("net._fc.2", F.linear(f, w, bb), eps=arch.FC_BN_EPS))
+    w, bb = randn(256, 512, std=(2.0 / 512) ** 0.5), randn(256, std=0.05)
+    sd["net._fc.5.weight"], sd["net._fc.5.bias"] = w, bb
+    f = F.relu(bn_calibrated("net._fc.6", F.linear(f, w, bb), eps=arch.FC_BN_EPS))
+    w = randn(1, 256, std=(1.0 / 256) ** 0.5)
+    z = F.linear(f, w)
+    w = w * (logit_gain / float(z.std() + 1e-9))
+    sd["net._fc.9.weight"] = w
+    sd["net._fc.9.bias"] = -F.linear(f, w).mean().reshape(1)
+    out = OrderedDict()
+    for k, shape in arch.state_dict_spec():       # canonical order + dtype
+        t = sd[k]
+        out[k] = t.to(torch.int64) if k.endswith("num_batches_tracked") else t.to(torch.float32).contiguous()
+        assert tuple(out[k].shape) == tuple(shape), (k, out[k].shape, shape)
+    if cache:
+        torch.save(out, path)
+    return out
