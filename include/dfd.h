@@ -1,0 +1,167 @@
+/* libdfd -- C-ABI of the B200-native per-frame deepfake-detection hot path.
+ *
+ * The reference (KrishTanna28/Real-Time-Video-Deepfake-Detection) is pure
+ * Python and has no FFI; this header is the boundary a maintainer binds with
+ * ctypes to replace, one for one, the Python call sites
+ * cited on each entry.  All bulk pointers are DEVICE pointers unless marked
+ * HOST; the caller owns every buffer passed in or out; the context owns the
+ * weights, the per-stream state and its workspaces.  Every entry returns 0 on
+ * success or a negative dfd_status and never throws; dfd_last_error() returns
+ * the message.  Calls are asynchronous on the supplied CUDA stream
+ * (cudaStream_t passed as void*; NULL = legacy default stream).  A context is
+ * bound to one GPU and is not thread-safe (one host thread per context, like
+ * the reference's effectively serial detector).  There is no CPU fallback.
+ */
+#ifndef DFD_H
+#define DFD_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFD_ABI_VERSION 1
+#define DFD_TILE 256          /* forensic analysis size, frame_analysis.py:28 */
+#define DFD_N_RAW 16          /* raw statistics per frame, order = oracle/forensics.py RAW_NAMES */
+#define DFD_N_SIGNALS 6       /* frequency, noise, ela, edge, color, temporal */
+#define DFD_CROP 224          /* classifier input size, deepfake_detection.py:383 */
+
+typedef enum {
+    DFD_OK = 0,
+    DFD_ERR_INVALID = -1,     /* bad argument */
+    DFD_ERR_CUDA = -2,        /* CUDA runtime/driver error */
+    DFD_ERR_NO_WEIGHTS = -3,  /* classifier called before dfd_load_weights */
+    DFD_ERR_CAPACITY = -4,    /* batch / stream id / crop size beyond the configured capacity */
+    DFD_ERR_ARCH = -5         /* device is not sm_100 */
+} dfd_status;
+
+typedef enum { DFD_F32 = 0, DFD_BF16 = 1 } dfd_dtype;
+typedef enum { DFD_UNCERTAIN = 0, DFD_REAL = 1, DFD_FAKE = 2 } dfd_verdict;
+/* vote input policy: reference code feeds the face probability alone when a
+ * face exists (deepfake_detection.py:620-626, backend_server.py:167-171); the
+ * README's 70/30 blend is opt-in. */
+typedef enum { DFD_BLEND_REFERENCE = 0, DFD_BLEND_README = 1 } dfd_blend_mode;
+
+typedef struct dfd_ctx dfd_ctx;
+
+typedef struct {
+    int32_t device;               /* CUDA ordinal */
+    int32_t max_streams;          /* per-stream state slots (stream ids 0..max_streams-1) */
+    int32_t max_batch;            /* max frames and max face boxes per call */
+    int32_t max_crop;             /* max face-box side in pixels */
+    int32_t window_size;          /* TemporalTracker(window_size=60)        deepfake_detection.py:99 */
+    int32_t voting_window;        /* TemporalTracker(voting_window=10) */
+    double detection_threshold;   /* DeepfakeDetector(detection_threshold)  deepfake_detection.py:300 */
+    double face_weight;           /* 0.70, used only with DFD_BLEND_README */
+    double forensic_weight;       /* 0.30 */
+    int32_t blend_mode;           /* dfd_blend_mode */
+    int32_t reserved;
+} dfd_config;
+
+/* One frame's forensic result; replaces the dict returned by
+ * FrameForensicAnalyzer.analyze / analyze_fast (frame_analysis.py:58-126). */
+typedef struct {
+    double raw[DFD_N_RAW];        /* NaN where the statistic was not computed */
+    double scores[DFD_N_SIGNALS]; /* NaN for signals skipped by analyze_fast */
+    double fake_probability;
+    int32_t frame_number;         /* analyzer.frame_count after this frame */
+    int32_t full;                 /* 1 = analyze, 0 = analyze_fast */
+} dfd_forensic_result;
+
+/* One stream's vote record; replaces TemporalTracker.update + get_confidence_level +
+ * get_voting_stats + get_temporal_average + get_stability_score
+ * (deepfake_detection.py:120-268).  32-byte aligned, gathered across GPUs as is. */
+typedef struct {
+    int32_t stream_id;
+    int32_t verdict;              /* dfd_verdict */
+    int32_t fake_count, real_count;
+    int32_t history_len;          /* len(score_history) */
+    int32_t frame_count;          /* detector.frame_count of the stream */
+    double vote_input;            /* NaN = nothing fed this frame */
+    double temporal_average;
+    double stability_score;
+    double face_probability;      /* NaN if no face */
+    double forensic_probability;
+} dfd_vote_record;
+
+void dfd_default_config(dfd_config* cfg);
+int dfd_abi_version(void);
+int dfd_create(const dfd_config* cfg, dfd_ctx** out);
+void dfd_destroy(dfd_ctx* ctx);
+const char* dfd_last_error(dfd_ctx* ctx);   /* ctx may be NULL for dfd_create failures */
+
+/* Classifier weights.  HOST blob of float32: BN-folded parameters in the order
+ * produced by dfd_b200.weights.pack_state_dict() from the reference
+ * checkpoint's `net.*` state_dict (model.py:36-61, deepfake_detection.py:44-51).
+ * n_floats must equal dfd_weights_blob_floats(). */
+size_t dfd_weights_blob_floats(void);
+int dfd_load_weights(dfd_ctx* ctx, const float* blob_host, size_t n_floats);
+
+/* FrameForensicAnalyzer.analyze / analyze_fast for a batch of frames, one per
+ * stream (frame_analysis.py:58-126; cadence chosen by the caller as in
+ * deepfake_detection.py:504-515).  frames: n images of H x W BGR u8, image i at
+ * frames + i*frame_stride, rows row_pitch bytes apart.  stream_ids[n], full[n]
+ * (1 = analyze, 0 = analyze_fast) are device arrays.  A stream id may appear at
+ * most once per call. */
+int dfd_forensics_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride,
+                        int row_pitch, const int32_t* stream_ids, const uint8_t* full,
+                        dfd_forensic_result* results, void* stream);
+
+/* preprocess_face_quality + _single_prediction preprocessing (deepfake_detection.py:357-389)
+ * for m face boxes: crop -> LAB CLAHE -> RGB -> PIL-bilinear 160^2 -> bilinear 224^2 -> /255 ->
+ * ImageNet normalise.  boxes[m*4] = x,y,w,h (device int32); frame_idx[m] selects the frame of each
+ * box.  out: m x 224 x 224 x 3 (NHWC) of dtype. */
+int dfd_face_prep_batch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
+                        int row_pitch, const int32_t* boxes, const int32_t* frame_idx, int m, void* out_nhwc,
+                        int dtype, void* stream);
+
+/* DeepfakeEfficientNet.forward (model.py:63-72): in m x 224 x 224 x 3 NHWC -> logits[m] (float32). */
+int dfd_effnet_forward(dfd_ctx* ctx, const void* in_nhwc, int m, int dtype, float* logits, void* stream);
+
+/* sigmoid + apply_heuristics (deepfake_detection.py:398,489-502): prob[i] = clip(sigmoid(logit) + 0.10*(w<80||h<80)). */
+int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, void* stream);
+
+/* TemporalTracker.update for n streams (deepfake_detection.py:120-196).  vote_input[i] NaN = update(None). */
+int dfd_vote_update(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, int n,
+                    dfd_vote_record* records, void* stream);
+
+/* The whole per-frame path for a batch: forensics + face prep + classifier + probability + vote input
+ * selection + vote (backend_server.py:148-174).  One frame per stream; box_frame[m] maps each box to its
+ * frame (only the first box of a frame feeds the vote, like faces[0]); full[n] as above.
+ * records[n] (device) receives one record per frame, in frame order. */
+int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride, int row_pitch,
+                      const int32_t* stream_ids, const uint8_t* full, const int32_t* boxes, const int32_t* box_frame,
+                      int m, int dtype, dfd_forensic_result* forensic_out /* may be NULL */,
+                      double* face_prob_out /* m, may be NULL */, dfd_vote_record* records, void* stream);
+
+/* DeepfakeDetector.reset / FrameForensicAnalyzer.reset / TemporalTracker.reset
+ * (deepfake_detection.py:344-355, 270-289; frame_analysis.py:391-395).  stream_id < 0 resets all. */
+int dfd_reset_stream(dfd_ctx* ctx, int stream_id, void* stream);
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t dfd_launch_count(dfd_ctx* ctx);
+
+/* ---- diagnostics used by the parity tests (stage outputs) ------------------------------------------ */
+/* tile (n x 256 x 256 x 3 BGR u8) and gray (n x 256 x 256 u8) of the last dfd_forensics_batch call. */
+int dfd_dbg_tiles(dfd_ctx* ctx, uint8_t* tile_out, uint8_t* gray_out, int n, void* stream);
+/* JPEG Q90 round trip of n tiles (256 x 256 x 3 BGR u8) -> same shape. */
+int dfd_dbg_jpeg_roundtrip(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n, void* stream);
+/* Canny(50,150) edge map (0/255) of n gray tiles (256 x 256). */
+int dfd_dbg_canny(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, void* stream);
+/* After dfd_face_prep_batch: the 160 x 160 x 3 RGB u8 image of box i. */
+int dfd_dbg_face160(dfd_ctx* ctx, int i, uint8_t* out_dev, void* stream);
+/* After dfd_face_prep_batch: the CLAHE'd crop of box i as w*h*3 BGR u8 (tight). */
+int dfd_dbg_face_clahe(dfd_ctx* ctx, const uint8_t* frames, int H, int W, size_t frame_stride, int row_pitch,
+                       const int32_t* boxes, const int32_t* frame_idx, int i, uint8_t* out_dev, void* stream);
+/* Activation tap: dfd_dbg_set_tap(name) before dfd_effnet_forward records that layer's output
+ * (name = "stem", "b<i>.expand", "b<i>.dw", "b<i>.out", "features"; NULL/"" = off);
+ * dfd_dbg_activation then copies min(n_floats, size) float32 values (NHWC, converted from bf16 if
+ * needed) and returns the element count or a negative status. */
+int dfd_dbg_set_tap(dfd_ctx* ctx, const char* name);
+int64_t dfd_dbg_activation(dfd_ctx* ctx, const char* name, float* out_dev, int64_t n_floats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFD_H */

@@ -1,0 +1,229 @@
+// C-ABI of libdfd.so (include/dfd.h): context, workspaces, entry points.
+#include "dfd_internal.cuh"
+#include <math.h>
+#include <string.h>
+
+int dfd_forensics_init(dfd_ctx* ctx);
+int dfd_dbg_jpeg_launch(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n, cudaStream_t st);
+int dfd_dbg_canny_launch(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, cudaStream_t st);
+int dfd_dbg_clahe_launch(dfd_ctx* ctx, const uint8_t* frames, size_t frame_stride, int row_pitch, const int32_t* boxes,
+                         const int32_t* frame_idx, int i, uint8_t* out, cudaStream_t st);
+void dfd_gemm_free(dfd_ctx* ctx);
+
+static thread_local std::string g_create_err;
+
+int dfd_ensure(dfd_ctx* ctx, DfdBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return DFD_OK;
+    if (b.p) { DFD_CUDA(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+    DFD_CUDA(cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return DFD_OK;
+}
+
+extern "C" {
+
+void dfd_default_config(dfd_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->device = 0; c->max_streams = 256; c->max_batch = 256; c->max_crop = 1024;
+    c->window_size = 60; c->voting_window = 10; c->detection_threshold = 0.5;
+    c->face_weight = 0.70; c->forensic_weight = 0.30; c->blend_mode = DFD_BLEND_REFERENCE;
+}
+
+int dfd_abi_version(void) { return DFD_ABI_VERSION; }
+
+const char* dfd_last_error(dfd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+static int create_impl(dfd_ctx* ctx) {
+    const dfd_config& c = ctx->cfg;
+    DFD_REQUIRE(c.max_streams > 0 && c.max_batch > 0 && c.max_crop >= 8, DFD_ERR_INVALID, "create: bad capacities");
+    DFD_REQUIRE(c.max_crop <= 31 * 160 && c.max_crop * 3 <= 48 * 1024, DFD_ERR_INVALID, "create: max_crop too large");
+    DFD_REQUIRE(c.window_size >= 10 && c.window_size <= DFD_MAX_SCORES, DFD_ERR_INVALID, "create: window_size must be 10..128");
+    DFD_REQUIRE(c.voting_window >= 1 && c.voting_window <= DFD_MAX_VOTES, DFD_ERR_INVALID, "create: voting_window must be 1..64");
+    DFD_CUDA(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    DFD_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    DFD_REQUIRE(prop.major == 10, DFD_ERR_ARCH, "create: libdfd is built for sm_100a (B200) only");
+    ctx->sm_count = prop.multiProcessorCount;
+    // tables
+    DfdColorTables* T = new DfdColorTables;
+    dfd_build_color_tables(T);
+    DFD_CUDA(cudaMalloc(&ctx->d_tables, sizeof(DfdColorTables)));
+    DFD_CUDA(cudaMemcpy(ctx->d_tables, T, sizeof(DfdColorTables), cudaMemcpyHostToDevice));
+    delete T;
+    float2 tw[128];
+    for (int j = 0; j < 128; j++) {
+        double a = -2.0 * M_PI * (double)j / 256.0;
+        tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    DFD_CUDA(cudaMalloc(&ctx->d_twiddle, sizeof(tw)));
+    DFD_CUDA(cudaMemcpy(ctx->d_twiddle, tw, sizeof(tw), cudaMemcpyHostToDevice));
+    // per-stream state
+    DFD_CUDA(cudaMalloc(&ctx->d_state, sizeof(DfdStreamState) * c.max_streams));
+    DFD_CUDA(cudaMemset(ctx->d_state, 0, sizeof(DfdStreamState) * c.max_streams));
+    DFD_CUDA(cudaMalloc(&ctx->d_prev_gray, (size_t)c.max_streams * 65536));
+    DFD_CUDA(cudaMemset(ctx->d_prev_gray, 0, (size_t)c.max_streams * 65536));
+    const size_t nb = c.max_batch;
+    DFD_CUDA(cudaMalloc(&ctx->d_tile, nb * 65536 * 3));
+    DFD_CUDA(cudaMalloc(&ctx->d_gray, nb * 65536));
+    DFD_CUDA(cudaMalloc(&ctx->d_fft, nb * 129 * 256 * sizeof(float2)));
+    DFD_CUDA(cudaMalloc(&ctx->d_part, nb * sizeof(DfdFramePartials)));
+    DFD_CUDA(cudaMemset(ctx->d_part, 0, nb * sizeof(DfdFramePartials)));
+    DFD_CUDA(cudaMalloc(&ctx->d_fres, nb * sizeof(dfd_forensic_result)));
+    DFD_CUDA(cudaMalloc(&ctx->d_luts, nb * 64 * 256));
+    DFD_CUDA(cudaMalloc(&ctx->d_pil, nb * 2 * 160 * (2 + 64) * sizeof(int)));
+    DFD_CUDA(cudaMalloc(&ctx->d_hpass, nb * (size_t)c.max_crop * 480));
+    DFD_CUDA(cudaMalloc(&ctx->d_face160, nb * 160 * 480));
+    DFD_CUDA(cudaMalloc(&ctx->d_pool, nb * 1152 * sizeof(float)));
+    DFD_CUDA(cudaMalloc(&ctx->d_sescale, nb * 1152 * sizeof(float)));
+    DFD_CUDA(cudaMalloc(&ctx->d_feat, nb * 1280 * sizeof(float)));
+    DFD_CUDA(cudaMalloc(&ctx->d_logits, nb * sizeof(float)));
+    DFD_CUDA(cudaMalloc(&ctx->d_faceprob, nb * sizeof(double)));
+    DFD_CUDA(cudaMalloc(&ctx->d_voteinput, nb * sizeof(double)));
+    int rc = dfd_forensics_init(ctx);
+    if (rc) return rc;
+    return DFD_OK;
+}
+
+int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
+    if (!cfg || !out) { g_create_err = "create: null argument"; return DFD_ERR_INVALID; }
+    dfd_ctx* ctx = new dfd_ctx;
+    ctx->cfg = *cfg;
+    int rc = create_impl(ctx);
+    if (rc) { g_create_err = ctx->err; dfd_destroy(ctx); *out = nullptr; return rc; }
+    *out = ctx;
+    return DFD_OK;
+}
+
+void dfd_destroy(dfd_ctx* ctx) {
+    if (!ctx) return;
+    void* ptrs[] = {ctx->d_tables, ctx->d_twiddle, ctx->d_state, ctx->d_prev_gray, ctx->d_tile, ctx->d_gray, ctx->d_fft,
+                    ctx->d_part, ctx->d_fres, ctx->d_luts, ctx->d_pil, ctx->d_hpass, ctx->d_face160, ctx->d_wf32,
+                    ctx->d_wbf16, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
+                    ctx->d_sescale, ctx->d_feat, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    dfd_gemm_free(ctx);
+    delete ctx;
+}
+
+size_t dfd_weights_blob_floats(void) { return dfd_effnet_blob_floats(); }
+
+int dfd_load_weights(dfd_ctx* ctx, const float* blob_host, size_t n_floats) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(blob_host != nullptr, DFD_ERR_INVALID, "load_weights: null blob");
+    return dfd_effnet_upload(ctx, blob_host, n_floats);
+}
+
+int dfd_forensics_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride, int row_pitch,
+                        const int32_t* stream_ids, const uint8_t* full, dfd_forensic_result* results, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(frames && stream_ids && full && results, DFD_ERR_INVALID, "forensics_batch: null pointer");
+    return dfd_forensics_launch(ctx, frames, n, H, W, frame_stride, row_pitch, stream_ids, full, results, (cudaStream_t)stream);
+}
+
+int dfd_face_prep_batch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride, int row_pitch,
+                        const int32_t* boxes, const int32_t* frame_idx, int m, void* out_nhwc, int dtype, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(frames && boxes && frame_idx && out_nhwc, DFD_ERR_INVALID, "face_prep_batch: null pointer");
+    return dfd_faceprep_launch(ctx, frames, n_frames, H, W, frame_stride, row_pitch, boxes, frame_idx, m, out_nhwc, dtype,
+                               (cudaStream_t)stream);
+}
+
+int dfd_effnet_forward(dfd_ctx* ctx, const void* in_nhwc, int m, int dtype, float* logits, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(in_nhwc && logits, DFD_ERR_INVALID, "effnet_forward: null pointer");
+    return dfd_effnet_launch(ctx, in_nhwc, m, dtype, logits, (cudaStream_t)stream);
+}
+
+int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(logits && boxes && prob && m > 0, DFD_ERR_INVALID, "face_probability: bad argument");
+    return dfd_faceprob_launch(ctx, logits, boxes, m, prob, (cudaStream_t)stream);
+}
+
+int dfd_vote_update(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, int n, dfd_vote_record* records,
+                    void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(stream_ids && vote_input && records && n > 0, DFD_ERR_INVALID, "vote_update: bad argument");
+    return dfd_vote_launch(ctx, stream_ids, vote_input, n, records, (cudaStream_t)stream);
+}
+
+int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride, int row_pitch,
+                      const int32_t* stream_ids, const uint8_t* full, const int32_t* boxes, const int32_t* box_frame, int m,
+                      int dtype, dfd_forensic_result* forensic_out, double* face_prob_out, dfd_vote_record* records,
+                      void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(frames && stream_ids && full && records, DFD_ERR_INVALID, "analyze_batch: null pointer");
+    DFD_REQUIRE(m == 0 || (boxes && box_frame), DFD_ERR_INVALID, "analyze_batch: boxes missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    dfd_forensic_result* fres = forensic_out ? forensic_out : ctx->d_fres;
+    int rc = dfd_forensics_launch(ctx, frames, n, H, W, frame_stride, row_pitch, stream_ids, full, fres, st);
+    if (rc) return rc;
+    double* fprob = face_prob_out ? face_prob_out : ctx->d_faceprob;
+    if (m > 0) {
+        size_t esz = dtype == DFD_BF16 ? 2 : 4;
+        if ((rc = dfd_ensure(ctx, ctx->face_in, (size_t)m * 224 * 224 * 3 * esz))) return rc;
+        if ((rc = dfd_faceprep_launch(ctx, frames, n, H, W, frame_stride, row_pitch, boxes, box_frame, m, ctx->face_in.p, dtype, st))) return rc;
+        if ((rc = dfd_effnet_launch(ctx, ctx->face_in.p, m, dtype, ctx->d_logits, st))) return rc;
+        if ((rc = dfd_faceprob_launch(ctx, ctx->d_logits, boxes, m, fprob, st))) return rc;
+    }
+    return dfd_select_vote_launch(ctx, n, m, box_frame, fprob, fres, stream_ids, records, st);
+}
+
+int dfd_reset_stream(dfd_ctx* ctx, int stream_id, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(stream_id < ctx->cfg.max_streams, DFD_ERR_CAPACITY, "reset_stream: id beyond max_streams");
+    return dfd_reset_launch(ctx, stream_id, (cudaStream_t)stream);
+}
+
+int64_t dfd_launch_count(dfd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- diagnostics ---------------------------------------------------------------------------------
+int dfd_dbg_tiles(dfd_ctx* ctx, uint8_t* tile_out, uint8_t* gray_out, int n, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(n > 0 && n <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "dbg_tiles: bad n");
+    if (tile_out) DFD_CUDA(cudaMemcpyAsync(tile_out, ctx->d_tile, (size_t)n * 65536 * 3, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (gray_out) DFD_CUDA(cudaMemcpyAsync(gray_out, ctx->d_gray, (size_t)n * 65536, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DFD_OK;
+}
+
+int dfd_dbg_jpeg_roundtrip(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    return dfd_dbg_jpeg_launch(ctx, tiles, out, n, (cudaStream_t)stream);
+}
+
+int dfd_dbg_canny(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    return dfd_dbg_canny_launch(ctx, gray, edges, n, (cudaStream_t)stream);
+}
+
+int dfd_dbg_face160(dfd_ctx* ctx, int i, uint8_t* out_dev, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(i >= 0 && i < ctx->cfg.max_batch, DFD_ERR_CAPACITY, "dbg_face160: bad index");
+    DFD_CUDA(cudaMemcpyAsync(out_dev, ctx->d_face160 + (size_t)i * 160 * 480, 160 * 480, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DFD_OK;
+}
+
+int dfd_dbg_face_clahe(dfd_ctx* ctx, const uint8_t* frames, int H, int W, size_t frame_stride, int row_pitch,
+                       const int32_t* boxes, const int32_t* frame_idx, int i, uint8_t* out_dev, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    return dfd_dbg_clahe_launch(ctx, frames, frame_stride, row_pitch, boxes, frame_idx, i, out_dev, (cudaStream_t)stream);
+}
+
+int dfd_dbg_set_tap(dfd_ctx* ctx, const char* name) {
+    if (!ctx) return DFD_ERR_INVALID;
+    ctx->tap_name = name ? name : "";
+    ctx->tap_elems = 0;
+    return DFD_OK;
+}
+
+int64_t dfd_dbg_activation(dfd_ctx* ctx, const char* name, float* out_dev, int64_t n_floats, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(name && ctx->tap_name == name && ctx->tap_elems > 0, DFD_ERR_INVALID,
+                "dbg_activation: call dfd_dbg_set_tap(name) before the forward pass");
+    int64_t n = n_floats < ctx->tap_elems ? n_floats : ctx->tap_elems;
+    if (out_dev && n > 0)
+        DFD_CUDA(cudaMemcpyAsync(out_dev, ctx->tap.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return ctx->tap_elems;
+}
+
+}  // extern "C"

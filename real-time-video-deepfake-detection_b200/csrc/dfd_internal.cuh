@@ -1,0 +1,139 @@
+// Internal context shared by the translation units of libdfd.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/dfd.h"
+#include "px_color.h"
+
+#define DFD_MAX_VOTES 64
+#define DFD_MAX_SCORES 128
+#define DFD_RING 30                 // FrameForensicAnalyzer.temporal_diffs deque(maxlen=30)
+#define DFD_NBLK 64                 // 8x8 blocks of 32x32 on the 256^2 tile
+#define DFD_FFT_GROUPS 17           // 129 half-spectrum columns in groups of 8
+
+// Per-stream state (device).  Replaces the Python objects' fields:
+//   FrameForensicAnalyzer.{prev_frame_gray, temporal_diffs, frame_count}  frame_analysis.py:35-37
+//   TemporalTracker.{score_history, frame_classifications, current_verdict} deepfake_detection.py:111-118
+//   DeepfakeDetector.frame_count                                           deepfake_detection.py:324
+struct DfdStreamState {
+    int32_t has_prev;
+    int32_t analyzer_frames;
+    int32_t ring_n, ring_head;
+    float ring[DFD_RING];
+    int32_t score_n, score_head;
+    int32_t vote_n, vote_head;
+    int32_t verdict;
+    int32_t detector_frames;
+    uint8_t votes[DFD_MAX_VOTES];
+    double scores[DFD_MAX_SCORES];
+};
+
+// Per-frame partial statistics written by the tile kernels and reduced by the finalize kernel.
+struct DfdFramePartials {
+    long long noise_sx[DFD_NBLK], noise_sxx[DFD_NBLK];      // x = 256*gray - 256*blur (exact integers)
+    long long lap_s[DFD_NBLK], lap_ss[DFD_NBLK];
+    unsigned long long sat_s[DFD_NBLK], sat_ss[DFD_NBLK], val_s[DFD_NBLK], val_ss[DFD_NBLK];
+    unsigned int hue_bits[DFD_NBLK][6];
+    int tdiff[DFD_NBLK];
+    int ela_sum[DFD_NBLK];
+    int canny_count;
+    int pad;
+    double fft[DFD_FFT_GROUPS][8];   // low_sum, mid_sum, mid_sumsq, high_sum, n_low, n_mid, n_high, -
+};
+
+struct DfdBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct dfd_ctx {
+    dfd_config cfg;
+    int sm_count = 0;
+    std::string err;
+    int64_t launches = 0;
+    // tables + state
+    DfdColorTables* d_tables = nullptr;
+    float2* d_twiddle = nullptr;          // 128 twiddles of the 256-point FFT
+    DfdStreamState* d_state = nullptr;
+    uint8_t* d_prev_gray = nullptr;       // [max_streams][256*256]
+    // forensic workspaces (max_batch)
+    uint8_t* d_tile = nullptr;            // [n][256][256][3]
+    uint8_t* d_gray = nullptr;            // [n][256][256]
+    float2* d_fft = nullptr;              // [n][129][256]
+    DfdFramePartials* d_part = nullptr;   // [n]
+    dfd_forensic_result* d_fres = nullptr;  // [n] internal results for analyze_batch
+    // face-prep workspaces
+    uint8_t* d_luts = nullptr;            // [m][64][256]
+    int* d_pil = nullptr;                 // [m][2][160][2+KMAX]
+    uint8_t* d_hpass = nullptr;           // [m][max_crop][160][3]
+    uint8_t* d_face160 = nullptr;         // [m][160][160][3]
+    // classifier
+    bool has_weights = false;
+    float* d_wf32 = nullptr;              // packed folded fp32 parameters
+    size_t w_floats = 0;
+    __nv_bfloat16* d_wbf16 = nullptr;     // bf16 copies of the GEMM weights (same offsets)
+    DfdBuf act[3];                        // activation ping-pong + expanded buffer
+    DfdBuf face_in;                       // prepared crops for analyze_batch
+    float* d_pool = nullptr;              // [m][1152] SE squeeze sums
+    float* d_sescale = nullptr;           // [m][1152]
+    float* d_feat = nullptr;              // [m][1280]
+    float* d_logits = nullptr;            // [m]
+    double* d_faceprob = nullptr;         // [m]
+    double* d_voteinput = nullptr;        // [n]
+    // diagnostics
+    std::string tap_name;
+    DfdBuf tap;
+    int64_t tap_elems = 0;
+    void* tmaps = nullptr;                // host-side cache of TMA descriptors (effnet_bf16.cu)
+};
+
+#define DFD_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            return DFD_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define DFD_LAUNCH_CHECK()                                                                  \
+    do {                                                                                    \
+        ctx->launches++;                                                                    \
+        cudaError_t e_ = cudaPeekAtLastError();                                             \
+        if (e_ != cudaSuccess) {                                                            \
+            ctx->err = std::string("kernel launch at ") + __FILE__ + ":" + std::to_string(__LINE__) + ": " + \
+                       cudaGetErrorString(e_);                                              \
+            return DFD_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define DFD_REQUIRE(cond, code, msg)                                                        \
+    do {                                                                                    \
+        if (!(cond)) { ctx->err = msg; return code; }                                       \
+    } while (0)
+
+int dfd_ensure(dfd_ctx* ctx, DfdBuf& b, size_t bytes);
+
+// forensics.cu
+int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride, int row_pitch,
+                         const int32_t* stream_ids, const uint8_t* full, dfd_forensic_result* results, cudaStream_t st);
+// faceprep.cu
+int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
+                        int row_pitch, const int32_t* boxes, const int32_t* frame_idx, int m, void* out, int dtype,
+                        cudaStream_t st);
+// effnet.cu
+int dfd_effnet_launch(dfd_ctx* ctx, const void* in, int m, int dtype, float* logits, cudaStream_t st);
+int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n);
+size_t dfd_effnet_blob_floats();
+// vote.cu
+int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, cudaStream_t st);
+int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, int n, dfd_vote_record* rec,
+                    cudaStream_t st);
+int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame, const double* face_prob,
+                           const dfd_forensic_result* fres, const int32_t* stream_ids, dfd_vote_record* rec,
+                           cudaStream_t st);
+int dfd_reset_launch(dfd_ctx* ctx, int stream_id, cudaStream_t st);

@@ -1,0 +1,451 @@
+// EfficientNet-B0 forward (reference model.py:63-72 -> lukemelas EfficientNet + custom _fc) on NHWC
+// activations.  This translation unit holds the launch plan and the CUDA-core kernels:
+//
+//   k_stem      dense 3x3 s2 conv 3->32, TF-SAME pad (0,1), folded BN, swish
+//   k_pw        1x1 conv as an fp32-FMA tiled GEMM with fused bias / swish / SE-scale / residual
+//               (fp32 accuracy mode; bf16 mode uses the tcgen05 GEMM in gemm_tcgen05.cu instead)
+//   k_dw        depthwise kxk stride s conv + folded BN + swish with the SE squeeze (per image,
+//               per channel sums) fused in: register accumulation -> smem -> one atomic per channel
+//   k_se        SE excite: mean -> reduce FC -> swish -> expand FC -> sigmoid  (one CTA per image)
+//   k_scale     x * se (bf16 mode only; fp32 mode applies the scale while loading A in k_pw)
+//   k_pool      global average pool of the head output
+//   k_fc        custom classifier 1280->512->256->1 (BN1d folded, ReLU)  (one CTA per image)
+//
+// Activations are float (fp32 mode: true fp32 FMA everywhere, parity 1e-4) or bf16 (storage only;
+// all accumulation in fp32).
+#include "dfd_internal.cuh"
+#include "effnet_plan.h"
+#include <string.h>
+
+int dfd_gemm_bf16(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
+                  const __nv_bfloat16* residual, __nv_bfloat16* C, int M, int N, int K, int act, cudaStream_t st);
+bool dfd_gemm_bf16_enabled();
+
+template <typename T> __device__ __forceinline__ float ld1(const T* p);
+template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st1(T* p, float v);
+template <> __device__ __forceinline__ void st1<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_stem(const T* __restrict__ in, const float* __restrict__ W,
+                                              const float* __restrict__ bias, T* __restrict__ out, int total) {
+    __shared__ float sw[27 * 32];
+    __shared__ float sb[32];
+    for (int i = threadIdx.x; i < 27 * 32; i += 128) sw[i] = W[i];
+    if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    int o = blockIdx.x * 128 + threadIdx.x;
+    if (o >= total) return;
+    int ox = o % 112, oy = (o / 112) % 112, b = o / (112 * 112);
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) acc[c] = sb[c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+        int iy = 2 * oy + ky;
+        if (iy >= 224) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            int ix = 2 * ox + kx;
+            if (ix >= 224) continue;
+            const T* p = in + (((size_t)b * 224 + iy) * 224 + ix) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ci++) {
+                float v = ld1<T>(p + ci);
+                const float* w = sw + ((ky * 3 + kx) * 3 + ci) * 32;
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[c] = fmaf(v, w[c], acc[c]);
+            }
+        }
+    }
+    T* q = out + (size_t)o * 32;
+#pragma unroll
+    for (int c = 0; c < 32; c++) st1<T>(q + c, swishf(acc[c]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// C[M,N] = act(A[M,K] (* se[img][k]) . W[N,K]^T + bias[n]) (+ residual[M,N]); 64x64x16 tiles, 4x4 per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) k_pw(const T* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                                            const float* __restrict__ se, int hw, const T* __restrict__ residual,
+                                            T* __restrict__ C, int M, int N, int K, int act) {
+    __shared__ float sa[16][64 + 4];
+    __shared__ float sb[16][64 + 4];
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+            int r = e >> 4, kk = e & 15;
+            int m = m0 + r, k = k0 + kk;
+            float v = 0.f;
+            if (m < M && k < K) {
+                v = ld1<T>(A + (size_t)m * K + k);
+                if (se) v *= se[(size_t)(m / hw) * K + k];
+            }
+            sa[kk][r] = v;
+            int n = n0 + r;
+            sb[kk][r] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = sa[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = sb[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + bias[n];
+            if (act) v = swishf(v);
+            if (residual) v += ld1<T>(residual + (size_t)m * N + n);
+            st1<T>(C + (size_t)m * N + n, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise conv.  Block = CG channel-groups x PS pixel lanes; each thread owns VEC channels and walks
+// the pixels of its tile, so the SE squeeze accumulates in registers.
+template <typename T, int VEC> struct VecIO;
+template <> struct VecIO<float, 4> {
+    static __device__ __forceinline__ void load(const float* p, float* v) { float4 t = *(const float4*)p; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void store(float* p, const float* v) { *(float4*)p = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct VecIO<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+        uint4 t = *(const uint4*)p;
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&t;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+        uint4 t;
+        __nv_bfloat162* h = (__nv_bfloat162*)&t;
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *(uint4*)p = t;
+    }
+};
+
+template <typename T, int VEC, int KS>
+__global__ void __launch_bounds__(320) k_dw(const T* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+                                            T* __restrict__ out, float* __restrict__ pool, int C, int hin, int hout,
+                                            int stride, int pad, int pix_per_block) {
+    extern __shared__ float spool[];                      // [PS][C]
+    const int CG = C / VEC;
+    const int PS = blockDim.x / CG;
+    const int cg = threadIdx.x % CG, ps = threadIdx.x / CG;
+    const int b = blockIdx.y;
+    const int npix = hout * hout;
+    const int p0 = blockIdx.x * pix_per_block;
+    float psum[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) psum[v] = 0.f;
+    if (ps < PS) {
+        const int c0 = cg * VEC;
+        float bv[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) bv[v] = bias[c0 + v];
+        const int pend = min(p0 + pix_per_block, npix);
+        for (int p = p0 + ps; p < pend; p += PS) {
+            int oy = p / hout, ox = p % hout;
+            float acc[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] = bv[v];
+#pragma unroll
+            for (int ky = 0; ky < KS; ky++) {
+                int iy = oy * stride + ky - pad;
+                if (iy < 0 || iy >= hin) continue;
+#pragma unroll
+                for (int kx = 0; kx < KS; kx++) {
+                    int ix = ox * stride + kx - pad;
+                    if (ix < 0 || ix >= hin) continue;
+                    float xv[VEC], wv[VEC];
+                    VecIO<T, VEC>::load(in + (((size_t)b * hin + iy) * hin + ix) * C + c0, xv);
+                    const float* wp = W + (size_t)(ky * KS + kx) * C + c0;
+#pragma unroll
+                    for (int v = 0; v < VEC; v += 4) { float4 t = __ldg((const float4*)(wp + v)); wv[v] = t.x; wv[v + 1] = t.y; wv[v + 2] = t.z; wv[v + 3] = t.w; }
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) acc[v] = fmaf(xv[v], wv[v], acc[v]);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; v++) { acc[v] = swishf(acc[v]); psum[v] += acc[v]; }
+            VecIO<T, VEC>::store(out + ((size_t)b * npix + p) * C + c0, acc);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; v++) spool[ps * C + c0 + v] = psum[v];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int q = 0; q < PS; q++) s += spool[q * C + c];
+        atomicAdd(pool + (size_t)b * C + c, s);
+    }
+}
+
+// SE excite; also clears the pool for the next block.
+__global__ void __launch_bounds__(256) k_se(float* __restrict__ pool, const float* __restrict__ Wr, const float* __restrict__ br,
+                                            const float* __restrict__ Wx, const float* __restrict__ bx,
+                                            float* __restrict__ scale, int C, int se, float inv_hw) {
+    __shared__ float s[1152];
+    __shared__ float r[64];
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += 256) { s[c] = pool[(size_t)b * C + c] * inv_hw; pool[(size_t)b * C + c] = 0.f; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < se; j += 8) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a = fmaf(Wr[(size_t)j * C + c], s[c], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) r[j] = swishf(a + br[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = bx[c];
+        for (int j = 0; j < se; j++) a = fmaf(Wx[(size_t)c * se + j], r[j], a);
+        scale[(size_t)b * C + c] = sigmoidf(a);
+    }
+}
+
+// x *= se[img][c]   (bf16 mode: produces the A operand of the project GEMM)
+__global__ void __launch_bounds__(256) k_scale(__nv_bfloat16* __restrict__ x, const float* __restrict__ se, int C, int hw,
+                                               size_t total_vec) {
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total_vec) return;
+    size_t e = i * 8;
+    int c = (int)(e % C);
+    size_t img = e / ((size_t)C * hw);
+    float v[8];
+    VecIO<__nv_bfloat16, 8>::load(x + e, v);
+    const float* s = se + img * C + c;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] *= s[k];
+    VecIO<__nv_bfloat16, 8>::store(x + e, v);
+}
+
+template <typename T>
+__global__ void k_pool(const T* __restrict__ x, float* __restrict__ feat, int hw, int C) {
+    int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int p = 0; p < hw; p++) s += ld1<T>(x + ((size_t)b * hw + p) * C + c);
+    feat[(size_t)b * C + c] = s / (float)hw;
+}
+
+__global__ void __launch_bounds__(512) k_fc(const float* __restrict__ feat, const float* __restrict__ W1, const float* __restrict__ b1,
+                                            const float* __restrict__ W2, const float* __restrict__ b2,
+                                            const float* __restrict__ W3, const float* __restrict__ b3, float* __restrict__ logits) {
+    __shared__ float f[1280];
+    __shared__ float h1[512];
+    __shared__ float h2[256];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 1280; i += 512) f[i] = feat[(size_t)b * 1280 + i];
+    __syncthreads();
+    for (int j = warp; j < 512; j += 16) {
+        float a = 0.f;
+        for (int c = lane; c < 1280; c += 32) a = fmaf(W1[(size_t)j * 1280 + c], f[c], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) h1[j] = fmaxf(a + b1[j], 0.f);
+    }
+    __syncthreads();
+    for (int j = warp; j < 256; j += 16) {
+        float a = 0.f;
+        for (int c = lane; c < 512; c += 32) a = fmaf(W2[(size_t)j * 512 + c], h1[c], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) h2[j] = fmaxf(a + b2[j], 0.f);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float a = 0.f;
+        for (int c = lane; c < 256; c += 32) a = fmaf(W3[c], h2[c], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) logits[b] = a + b3[0];
+    }
+}
+
+template <typename T>
+__global__ void k_to_f32(const T* __restrict__ x, float* __restrict__ o, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = ld1<T>(x + i);
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t dfd_effnet_blob_floats() { return eff_offsets().total; }
+
+int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n) {
+    EffOffsets o = eff_offsets();
+    DFD_REQUIRE(n == o.total, DFD_ERR_INVALID, "load_weights: blob size does not match dfd_weights_blob_floats()");
+    if (!ctx->d_wf32) {
+        DFD_CUDA(cudaMalloc(&ctx->d_wf32, o.total * sizeof(float)));
+        DFD_CUDA(cudaMalloc(&ctx->d_wbf16, o.total * sizeof(__nv_bfloat16)));
+    }
+    DFD_CUDA(cudaMemcpy(ctx->d_wf32, blob, o.total * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<__nv_bfloat16> h(o.total);
+    for (size_t i = 0; i < o.total; i++) h[i] = __float2bfloat16_rn(blob[i]);
+    DFD_CUDA(cudaMemcpy(ctx->d_wbf16, h.data(), o.total * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    ctx->w_floats = o.total;
+    ctx->has_weights = true;
+    return DFD_OK;
+}
+
+template <typename T>
+static int tap(dfd_ctx* ctx, const char* name, const T* x, size_t n, cudaStream_t st) {
+    if (ctx->tap_name.empty() || ctx->tap_name != name) return DFD_OK;
+    int rc = dfd_ensure(ctx, ctx->tap, n * sizeof(float));
+    if (rc) return rc;
+    k_to_f32<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (float*)ctx->tap.p, n);
+    DFD_LAUNCH_CHECK();
+    ctx->tap_elems = (int64_t)n;
+    return DFD_OK;
+}
+
+template <typename T, int VEC>
+static int launch_dw(dfd_ctx* ctx, const EffBlock& b, const T* in, const float* W, const float* bias, T* out, int m,
+                     cudaStream_t st) {
+    const int CG = b.cexp / VEC;
+    int threads = CG >= 256 ? CG : (256 / CG) * CG;
+    if (threads > 1024) threads = CG;               // CG <= 288
+    const int PS = threads / CG;
+    const int npix = b.hout * b.hout;
+    // enough CTAs to fill the chip: aim for >= 4 waves but at least 8 pixels per thread-lane
+    int ppb = PS * 8;
+    if (ppb > npix) ppb = npix;
+    const int gx = (npix + ppb - 1) / ppb;
+    size_t smem = (size_t)PS * b.cexp * sizeof(float);
+#define DW_CASE(KS)                                                                                         \
+    k_dw<T, VEC, KS><<<dim3(gx, m), threads, smem, st>>>(in, W, bias, out, ctx->d_pool, b.cexp, b.hin, b.hout, \
+                                                         b.s, b.pad, ppb)
+    if (b.k == 3) DW_CASE(3); else DW_CASE(5);
+#undef DW_CASE
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+template <typename T>
+static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream_t st) {
+    const EffOffsets o = eff_offsets();
+    const float* Wf = ctx->d_wf32;
+    constexpr bool BF = sizeof(T) == 2;
+    constexpr int VEC = BF ? 8 : 4;
+    const bool tc = BF && dfd_gemm_bf16_enabled();
+    // activation buffers: x (block input / output ping-pong in act[0], act[1]) and e (expanded, act[2])
+    const size_t max_io = (size_t)m * 112 * 112 * 32;          // stem out
+    const size_t max_e = (size_t)m * (112 * 112 * 96 + 56 * 56 * 96);   // block 1: expand out + depthwise out
+    int rc;
+    if ((rc = dfd_ensure(ctx, ctx->act[0], max_io * sizeof(T)))) return rc;
+    if ((rc = dfd_ensure(ctx, ctx->act[1], max_io * sizeof(T)))) return rc;
+    if ((rc = dfd_ensure(ctx, ctx->act[2], max_e * sizeof(T)))) return rc;
+    T* x = (T*)ctx->act[0].p;
+    T* y = (T*)ctx->act[1].p;
+    T* e = (T*)ctx->act[2].p;
+    DFD_CUDA(cudaMemsetAsync(ctx->d_pool, 0, (size_t)m * 1152 * sizeof(float), st));
+
+    {
+        int total = m * 112 * 112;
+        k_stem<T><<<(total + 127) / 128, 128, 0, st>>>(in, Wf + o.stem_w, Wf + o.stem_b, x, total);
+        DFD_LAUNCH_CHECK();
+        if ((rc = tap<T>(ctx, "stem", x, (size_t)total * 32, st))) return rc;
+    }
+    auto pw = [&](const T* A, size_t w_off, size_t b_off, const float* se, int hw, const T* res, T* C, int M, int N, int K,
+                  int act) -> int {
+        if (tc) {
+            return dfd_gemm_bf16(ctx, (const __nv_bfloat16*)A, ctx->d_wbf16 + w_off, Wf + b_off, (const __nv_bfloat16*)res,
+                                 (__nv_bfloat16*)C, M, N, K, act, st);
+        }
+        k_pw<T><<<dim3((M + 63) / 64, (N + 63) / 64), 256, 0, st>>>(A, Wf + w_off, Wf + b_off, se, hw, res, C, M, N, K, act);
+        DFD_LAUNCH_CHECK();
+        return DFD_OK;
+    };
+    char nm[32];
+    for (int i = 0; i < 16; i++) {
+        const EffBlock& b = EFF_BLOCKS[i];
+        const EffBlockOff& f = o.blk[i];
+        const int Min = m * b.hin * b.hin, Mout = m * b.hout * b.hout;
+        const T* dw_in = x;
+        T* dw_out;
+        if (b.cexp != b.cin) {
+            if ((rc = pw(x, f.we, f.be, nullptr, 0, nullptr, e, Min, b.cexp, b.cin, 1))) return rc;
+            snprintf(nm, sizeof nm, "b%d.expand", i);
+            if ((rc = tap<T>(ctx, nm, e, (size_t)Min * b.cexp, st))) return rc;
+            dw_in = e;
+        }
+        // depthwise output: behind the expand output inside e (sized for block 1), or y for block 0
+        if (b.cexp != b.cin) {
+            dw_out = e + (size_t)Min * b.cexp;
+            size_t need = ((size_t)Min + Mout) * b.cexp * sizeof(T);
+            if (need > ctx->act[2].bytes) { ctx->err = "internal: expanded buffer too small"; return DFD_ERR_CAPACITY; }
+        } else dw_out = y;
+        if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, st))) return rc;
+        snprintf(nm, sizeof nm, "b%d.dw", i);
+        if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
+        k_se<<<m, 256, 0, st>>>(ctx->d_pool, Wf + f.wr, Wf + f.br, Wf + f.wx, Wf + f.bx, ctx->d_sescale, b.cexp, b.se,
+                                1.0f / (float)(b.hout * b.hout));
+        DFD_LAUNCH_CHECK();
+        const bool skip = b.s == 1 && b.cin == b.cout;
+        T* outp = (dw_out == y) ? x : y;       // block 0 wrote dw into y; its project output goes to x (input is dead, no skip)
+        const float* se_arg = ctx->d_sescale;
+        if (tc) {
+            size_t tv = (size_t)Mout * b.cexp / 8;
+            k_scale<<<(unsigned)((tv + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)dw_out, ctx->d_sescale, b.cexp, b.hout * b.hout, tv);
+            DFD_LAUNCH_CHECK();
+            se_arg = nullptr;
+        }
+        if ((rc = pw(dw_out, f.wp, f.bp, se_arg, b.hout * b.hout, skip ? x : nullptr, outp, Mout, b.cout, b.cexp, 0))) return rc;
+        snprintf(nm, sizeof nm, "b%d.out", i);
+        if ((rc = tap<T>(ctx, nm, outp, (size_t)Mout * b.cout, st))) return rc;
+        if (outp == y) { T* t = x; x = y; y = t; }
+    }
+    // head 1x1 320->1280 + swish, global average pool, classifier
+    {
+        const int M = m * 49;
+        if ((rc = pw(x, o.head_w, o.head_b, nullptr, 0, nullptr, e, M, 1280, 320, 1))) return rc;
+        k_pool<T><<<dim3(1280 / 128, m), 128, 0, st>>>(e, ctx->d_feat, 49, 1280);
+        DFD_LAUNCH_CHECK();
+        if (!ctx->tap_name.empty() && ctx->tap_name == "features") {
+            if ((rc = tap<float>(ctx, "features", ctx->d_feat, (size_t)m * 1280, st))) return rc;
+        }
+        k_fc<<<m, 512, 0, st>>>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, Wf + o.fc2_w, Wf + o.fc2_b, Wf + o.fc3_w, Wf + o.fc3_b,
+                                logits);
+        DFD_LAUNCH_CHECK();
+    }
+    return DFD_OK;
+}
+
+int dfd_effnet_launch(dfd_ctx* ctx, const void* in, int m, int dtype, float* logits, cudaStream_t st) {
+    DFD_REQUIRE(ctx->has_weights, DFD_ERR_NO_WEIGHTS, "effnet_forward: call dfd_load_weights first");
+    DFD_REQUIRE(m > 0 && m <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "effnet_forward: batch exceeds max_batch");
+    if (dtype == DFD_F32) return forward_t<float>(ctx, (const float*)in, m, logits, st);
+    if (dtype == DFD_BF16) return forward_t<__nv_bfloat16>(ctx, (const __nv_bfloat16*)in, m, logits, st);
+    ctx->err = "effnet_forward: bad dtype";
+    return DFD_ERR_INVALID;
+}

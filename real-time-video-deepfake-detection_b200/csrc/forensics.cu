@@ -1,0 +1,549 @@
+// Six frame-forensic signals as batched sm_100a kernels.
+//
+// Replaces FrameForensicAnalyzer.analyze / analyze_fast (reference
+// frame_analysis.py:58-126) for a batch of frames, one per stream:
+//
+//   k_resize256   cv2.resize(frame,(256,256),INTER_LINEAR) + BGR2GRAY          :71,111,136
+//   k_tile_stats  noise residual (:188-202), Laplacian sums (:292), HSV sums (:318-341),
+//                 temporal |gray - prev| (:356-366), per 32x32 block, exact integers
+//   k_canny       cv2.Canny(gray,50,150) edge count (:288-289): NMS + bit-packed hysteresis in smem
+//   k_ela         JPEG Q90 4:2:0 round trip + absdiff + gray block sums (:234-253), all in smem
+//   k_fft_rows / k_fft_cols   np.fft.fft2 -> fftshift -> log1p|.| band sums (:139-152,168-170)
+//   k_finalize    thresholds, weighted sum, per-stream temporal ring update (:154-180,204-225,...)
+//
+// The integer stages are bit-exact with cv2 (same px_*.h functions that tests/hostcheck checks on
+// the CPU); float statistics agree to ~1e-6 relative (double accumulation vs NumPy float32 pairwise).
+#include "dfd_internal.cuh"
+#include "px_resize.h"
+#include "px_jpeg.h"
+#include "px_canny.h"
+#include "px_numpy.h"
+
+#define T 256
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize256(const uint8_t* __restrict__ frames, int H, int W, size_t fstride,
+                                                   int pitch, uint8_t* __restrict__ tile, uint8_t* __restrict__ gray) {
+    const int n = blockIdx.y, y = blockIdx.x, x = threadIdx.x;
+    int sy0, sy1, b0, b1, sx0, sx1, a0, a1;
+    dfd_cvresize_coef(y, H, T, 0, &sy0, &sy1, &b0, &b1);
+    dfd_cvresize_coef(x, W, T, 1, &sx0, &sx1, &a0, &a1);
+    const uint8_t* f = frames + (size_t)n * fstride;
+    const uint8_t* r0 = f + (size_t)sy0 * pitch;
+    const uint8_t* r1 = f + (size_t)sy1 * pitch;
+    int px[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        px[c] = dfd_cvresize_px(__ldg(r0 + sx0 * 3 + c), __ldg(r0 + sx1 * 3 + c), __ldg(r1 + sx0 * 3 + c),
+                                __ldg(r1 + sx1 * 3 + c), a0, a1, b0, b1);
+    size_t o = ((size_t)n * T + y) * T + x;
+    tile[o * 3 + 0] = (uint8_t)px[0];
+    tile[o * 3 + 1] = (uint8_t)px[1];
+    tile[o * 3 + 2] = (uint8_t)px[2];
+    gray[o] = (uint8_t)dfd_bgr2gray(px[0], px[1], px[2]);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ V warp_sum(V v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block = 256 threads (8 warps); every thread calls; result valid in thread 0
+template <typename V>
+__device__ __forceinline__ V block_sum_256(V v, V* sh /* [8] */) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    V r = 0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 8; i++) r += sh[i];
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ tile, const uint8_t* __restrict__ gray,
+                                                    const int32_t* __restrict__ stream_ids,
+                                                    const uint8_t* __restrict__ full, const DfdColorTables* __restrict__ tab,
+                                                    const DfdStreamState* __restrict__ state, uint8_t* __restrict__ prev_gray,
+                                                    DfdFramePartials* __restrict__ part) {
+    const int n = blockIdx.y, blk = blockIdx.x;
+    const int by = blk >> 3, bx = blk & 7;
+    const bool is_full = full[n] != 0;
+    const int sid = stream_ids[n];
+    __shared__ uint8_t sg[36][36];
+    __shared__ long long shll[8];
+    __shared__ unsigned int shue[6];
+    const uint8_t* g = gray + (size_t)n * T * T;
+    for (int i = threadIdx.x; i < 36 * 36; i += 256) {
+        int ly = i / 36, lx = i % 36;
+        int gy = dfd_reflect101(by * 32 + ly - 2, T), gx = dfd_reflect101(bx * 32 + lx - 2, T);
+        sg[ly][lx] = g[gy * T + gx];
+    }
+    if (threadIdx.x < 6) shue[threadIdx.x] = 0;
+    __syncthreads();
+    uint8_t* prev = prev_gray + (size_t)sid * T * T;
+    long long nsx = 0, nsxx = 0, ls = 0, lss = 0, ss = 0, sss = 0, vs = 0, vss = 0, td = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int p = threadIdx.x + k * 256;
+        int ly = p >> 5, lx = p & 31;
+        int gy = by * 32 + ly, gx = bx * 32 + lx;
+        int c = sg[ly + 2][lx + 2];
+        int lap = sg[ly + 1][lx + 2] + sg[ly + 3][lx + 2] + sg[ly + 2][lx + 1] + sg[ly + 2][lx + 3] - 4 * c;
+        ls += lap; lss += lap * lap;
+        size_t gi = (size_t)gy * T + gx;
+        int pv = prev[gi];
+        td += dfd_absi(c - pv);
+        prev[gi] = (uint8_t)c;
+        if (is_full) {
+            const int kk[5] = {1, 4, 6, 4, 1};
+            int acc = 0;
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                int row = 0;
+#pragma unroll
+                for (int i = 0; i < 5; i++) row += kk[i] * sg[ly + j][lx + i];
+                acc += kk[j] * row;
+            }
+            long long x = 256 * c - acc;
+            nsx += x; nsxx += x * x;
+            const uint8_t* t3 = tile + ((size_t)n * T * T + gi) * 3;
+            int h, s, v;
+            dfd_bgr2hsv(tab, t3[0], t3[1], t3[2], &h, &s, &v);
+            ss += s; sss += s * s; vs += v; vss += v * v;
+            atomicOr(&shue[h >> 5], 1u << (h & 31));
+        }
+    }
+    DfdFramePartials* P = part + n;
+    long long r;
+    r = block_sum_256(ls, shll);  if (threadIdx.x == 0) P->lap_s[blk] = r;
+    r = block_sum_256(lss, shll); if (threadIdx.x == 0) P->lap_ss[blk] = r;
+    r = block_sum_256(td, shll);  if (threadIdx.x == 0) P->tdiff[blk] = (int)r;
+    if (is_full) {
+        r = block_sum_256(nsx, shll);  if (threadIdx.x == 0) P->noise_sx[blk] = r;
+        r = block_sum_256(nsxx, shll); if (threadIdx.x == 0) P->noise_sxx[blk] = r;
+        r = block_sum_256(ss, shll);   if (threadIdx.x == 0) P->sat_s[blk] = (unsigned long long)r;
+        r = block_sum_256(sss, shll);  if (threadIdx.x == 0) P->sat_ss[blk] = (unsigned long long)r;
+        r = block_sum_256(vs, shll);   if (threadIdx.x == 0) P->val_s[blk] = (unsigned long long)r;
+        r = block_sum_256(vss, shll);  if (threadIdx.x == 0) P->val_ss[blk] = (unsigned long long)r;
+        __syncthreads();
+        if (threadIdx.x < 6) P->hue_bits[blk][threadIdx.x] = shue[threadIdx.x];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Canny: one CTA per frame.  smem: gray 64 KB + candidate bits 8 KB + strong bits 8 KB.
+__device__ __forceinline__ int sob_mag(const uint8_t* g, int x, int y, int* dxo, int* dyo) {
+    int dx, dy;
+    dfd_sobel3(g, T, T, x, y, &dx, &dy);
+    if (dxo) { *dxo = dx; *dyo = dy; }
+    return dfd_absi(dx) + dfd_absi(dy);
+}
+
+struct MagAt {
+    const uint8_t* g;
+    __device__ __forceinline__ int operator()(int x, int y) const {
+        if (x < 0 || y < 0 || x >= T || y >= T) return 0;
+        return sob_mag(g, x, y, nullptr, nullptr);
+    }
+};
+
+__global__ void __launch_bounds__(1024) k_canny(const uint8_t* __restrict__ gray, int* __restrict__ count_out,
+                                                size_t count_stride_bytes, uint8_t* __restrict__ edges_out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* sg = smem;
+    uint32_t* W = (uint32_t*)(smem + T * T);
+    uint32_t* S = W + 2048;
+    const int n = blockIdx.x;
+    const uint4* src = (const uint4*)(gray + (size_t)n * T * T);
+    for (int i = threadIdx.x; i < T * T / 16; i += 1024) ((uint4*)sg)[i] = src[i];
+    __syncthreads();
+    MagAt mag{sg};
+    for (int it = 0; it < 64; it++) {
+        int p = it * 1024 + threadIdx.x;
+        int y = p >> 8, x = p & 255;
+        int dx, dy;
+        int m = sob_mag(sg, x, y, &dx, &dy);
+        int st = dfd_canny_nms(dx, dy, m, x, y, mag);
+        uint32_t wb = __ballot_sync(0xffffffffu, st >= 1);
+        uint32_t sb = __ballot_sync(0xffffffffu, st == 2);
+        if ((threadIdx.x & 31) == 0) { W[p >> 5] = wb; S[p >> 5] = sb; }
+    }
+    __syncthreads();
+    // hysteresis: S <- W & dilate3x3(S) until stable (monotone, in place)
+    while (true) {
+        int changed = 0;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            int w = threadIdx.x + k * 1024;
+            int r = w >> 3, c = w & 7;
+            uint32_t cand = W[w], cur = S[w];
+            if (cand == cur) continue;
+            uint32_t dil = 0;
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++) {
+                int rr = r + dr;
+                if (rr < 0 || rr >= T) continue;
+                uint32_t mid = S[rr * 8 + c];
+                uint32_t lft = c > 0 ? S[rr * 8 + c - 1] : 0u;
+                uint32_t rgt = c < 7 ? S[rr * 8 + c + 1] : 0u;
+                dil |= mid | (mid << 1) | (mid >> 1) | (lft >> 31) | (rgt << 31);
+            }
+            uint32_t nw = cand & dil;
+            // run the in-word horizontal propagation to a fixed point
+            uint32_t prevv;
+            do { prevv = nw; nw |= cand & ((nw << 1) | (nw >> 1)); } while (nw != prevv);
+            nw |= cur;
+            if (nw != cur) { S[w] = nw; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    int cnt = __popc(S[threadIdx.x]) + __popc(S[threadIdx.x + 1024]);
+    cnt = warp_sum(cnt);
+    __shared__ int sc[32];
+    if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int i = 0; i < 32; i++) tot += sc[i];
+        if (count_out) *(int*)((char*)count_out + (size_t)n * count_stride_bytes) = tot;
+    }
+    if (edges_out) {
+        for (int p = threadIdx.x; p < T * T; p += 1024)
+            edges_out[(size_t)n * T * T + p] = (S[p >> 5] >> (p & 31)) & 1 ? 255 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ELA: JPEG Q90 4:2:0 round trip in shared memory; one CTA (512 threads) per frame.
+__global__ void __launch_bounds__(512) k_ela(const uint8_t* __restrict__ tile, const uint8_t* __restrict__ full,
+                                             DfdFramePartials* __restrict__ part, uint8_t* __restrict__ recon_out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* Y = smem;                  // 256 x 256
+    uint8_t* Cb = smem + T * T;         // 128 x 128
+    uint8_t* Cr = Cb + 128 * 128;
+    __shared__ int sums[DFD_NBLK];
+    const int n = blockIdx.x;
+    if (full && !full[n]) return;
+    const uint8_t* src = tile + (size_t)n * T * T * 3;
+    if (threadIdx.x < DFD_NBLK) sums[threadIdx.x] = 0;
+    for (int q = threadIdx.x; q < 128 * 128; q += 512) {
+        int qy = q >> 7, qx = q & 127;
+        int cb = 0, cr = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                int y = 2 * qy + j, x = 2 * qx + i;
+                const uint8_t* p = src + (y * T + x) * 3;
+                int b = p[0], g = p[1], r = p[2];
+                Y[y * T + x] = (uint8_t)dfd_jpeg_y(r, g, b);
+                cb += dfd_jpeg_cb(r, g, b);
+                cr += dfd_jpeg_cr(r, g, b);
+            }
+        int bias = (qx & 1) ? 2 : 1;
+        Cb[q] = (uint8_t)((cb + bias) >> 2);
+        Cr[q] = (uint8_t)((cr + bias) >> 2);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 1536; b += 512) {
+        uint8_t* plane; int pw, bi, chroma;
+        if (b < 1024) { plane = Y; pw = T; bi = b; chroma = 0; }
+        else if (b < 1280) { plane = Cb; pw = 128; bi = b - 1024; chroma = 1; }
+        else { plane = Cr; pw = 128; bi = b - 1280; chroma = 1; }
+        int nbx = pw >> 3;
+        uint8_t* base = plane + ((bi / nbx) * 8) * pw + (bi % nbx) * 8;
+        int blk[64];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint2 v = *(const uint2*)(base + r * pw);
+            blk[r * 8 + 0] = v.x & 255; blk[r * 8 + 1] = (v.x >> 8) & 255; blk[r * 8 + 2] = (v.x >> 16) & 255; blk[r * 8 + 3] = v.x >> 24;
+            blk[r * 8 + 4] = v.y & 255; blk[r * 8 + 5] = (v.y >> 8) & 255; blk[r * 8 + 6] = (v.y >> 16) & 255; blk[r * 8 + 7] = v.y >> 24;
+        }
+        dfd_jpeg_block_roundtrip(blk, chroma);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint2 v;
+            v.x = blk[r * 8 + 0] | (blk[r * 8 + 1] << 8) | (blk[r * 8 + 2] << 16) | (blk[r * 8 + 3] << 24);
+            v.y = blk[r * 8 + 4] | (blk[r * 8 + 5] << 8) | (blk[r * 8 + 6] << 16) | (blk[r * 8 + 7] << 24);
+            *(uint2*)(base + r * pw) = v;
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < T * T; p += 512) {
+        int y = p >> 8, x = p & 255;
+        int r, g, b;
+        dfd_jpeg_ycc2rgb(Y[p], dfd_jpeg_fancy_up(Cb, 128, 128, x, y), dfd_jpeg_fancy_up(Cr, 128, 128, x, y), &r, &g, &b);
+        const uint8_t* o = src + p * 3;
+        int d = dfd_bgr2gray(dfd_absi(o[0] - b), dfd_absi(o[1] - g), dfd_absi(o[2] - r));
+        if (recon_out) {
+            uint8_t* ro = recon_out + ((size_t)n * T * T + p) * 3;
+            ro[0] = (uint8_t)b; ro[1] = (uint8_t)g; ro[2] = (uint8_t)r;
+        }
+        d = warp_sum(d);                                   // a warp covers 32 consecutive x of one row
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sums[(y >> 5) * 8 + (x >> 5)], d);
+    }
+    __syncthreads();
+    if (part && threadIdx.x < DFD_NBLK) part[n].ela_sum[threadIdx.x] = sums[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// 256-point radix-2 DIT FFT on shared memory; 128 threads cooperate on one transform.
+__device__ __forceinline__ int bitrev8(int v) { return (int)(__brev((unsigned)v) >> 24); }
+
+__device__ __forceinline__ void fft256(float2* s, const float2* __restrict__ tw, int t, int barrier_id, int nthreads) {
+#pragma unroll
+    for (int st = 1; st <= 8; st++) {
+        int half = 1 << (st - 1);
+        int grp = t >> (st - 1), idx = t & (half - 1);
+        int i0 = (grp << st) + idx, i1 = i0 + half;
+        float2 w = tw[idx << (8 - st)];
+        float2 a = s[i0], b = s[i1];
+        float2 wb = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+        s[i0] = make_float2(a.x + wb.x, a.y + wb.y);
+        s[i1] = make_float2(a.x - wb.x, a.y - wb.y);
+        __syncthreads();
+    }
+}
+
+// rows: CTA = 8 row-pairs (16 rows); grid (16, n).  Output half-spectrum, transposed: fft[n][k][row].
+__global__ void __launch_bounds__(1024) k_fft_rows(const uint8_t* __restrict__ gray, const float2* __restrict__ tw,
+                                                   float2* __restrict__ out) {
+    __shared__ float2 s[8][256];
+    const int n = blockIdx.y, grp = blockIdx.x;
+    const int f = threadIdx.x >> 7, t = threadIdx.x & 127;
+    const int row0 = grp * 16 + 2 * f;
+    const uint8_t* g = gray + (size_t)n * T * T;
+    for (int j = t; j < 256; j += 128)
+        s[f][bitrev8(j)] = make_float2((float)g[row0 * T + j], (float)g[(row0 + 1) * T + j]);
+    __syncthreads();
+    fft256(s[f], tw, t, 0, 0);
+    float2* o = out + (size_t)n * 129 * 256;
+    for (int k = t; k <= 128; k += 128) {
+        float2 zk = s[f][k], zn = s[f][(256 - k) & 255];
+        // F1 = (Zk + conj(Zn))/2 ; F2 = (Zk - conj(Zn))/(2i)
+        float2 f1 = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        float2 f2 = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+        o[(size_t)k * 256 + row0] = f1;
+        o[(size_t)k * 256 + row0 + 1] = f2;
+    }
+}
+
+// columns: CTA = 8 half-spectrum columns; grid (17, n).
+__global__ void __launch_bounds__(1024) k_fft_cols(const float2* __restrict__ in, const float2* __restrict__ tw,
+                                                   DfdFramePartials* __restrict__ part) {
+    __shared__ float2 s[8][256];
+    __shared__ double red[32][7];
+    const int n = blockIdx.y, grp = blockIdx.x;
+    const int f = threadIdx.x >> 7, t = threadIdx.x & 127;
+    const int k = grp * 8 + f;
+    const bool active = k <= 128;
+    if (active) {
+        const float2* c = in + ((size_t)n * 129 + k) * 256;
+        for (int j = t; j < 256; j += 128) s[f][bitrev8(j)] = c[j];
+    }
+    __syncthreads();
+    fft256(s[f], tw, t, 0, 0);      // inactive columns transform garbage; results unused
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+        const int fv = k < 128 ? k : -128;
+        const double wgt = (k == 0 || k == 128) ? 1.0 : 2.0;
+        for (int u = t; u < 256; u += 128) {
+            int fu = u < 128 ? u : u - 256;
+            int d2 = fu * fu + fv * fv;
+            float2 z = s[f][u];
+            double m = (double)log1pf(hypotf(z.x, z.y));
+            if (d2 <= 32 * 32) { acc[0] += wgt * m; acc[4] += wgt; }
+            else if (d2 <= 64 * 64) { acc[1] += wgt * m; acc[2] += wgt * m * m; acc[5] += wgt; }
+            else if (d2 <= 128 * 128) { acc[3] += wgt * m; acc[6] += wgt; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) acc[i] = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 7; i++) red[threadIdx.x >> 5][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double r = 0;
+        for (int w = 0; w < 32; w++) r += red[w][threadIdx.x];
+        part[n].fft[grp][threadIdx.x] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Score tables + state update; one thread per frame.
+__device__ double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+
+__global__ void k_finalize(int n, const int32_t* __restrict__ stream_ids, const uint8_t* __restrict__ full,
+                           const DfdFramePartials* __restrict__ part, DfdStreamState* __restrict__ state,
+                           dfd_forensic_result* __restrict__ results) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DfdFramePartials& P = part[i];
+    DfdStreamState& S = state[stream_ids[i]];
+    dfd_forensic_result R;
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    for (int k = 0; k < DFD_N_RAW; k++) R.raw[k] = NaN;
+    for (int k = 0; k < DFD_N_SIGNALS; k++) R.scores[k] = NaN;
+    const bool is_full = full[i] != 0;
+    S.analyzer_frames += 1;                                     // frame_analysis.py:68,110
+    R.frame_number = S.analyzer_frames;
+    R.full = is_full ? 1 : 0;
+
+    // ---- frequency (frame_analysis.py:150-180) ----
+    {
+        double a[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int g = 0; g < DFD_FFT_GROUPS; g++)
+            for (int k = 0; k < 7; k++) a[k] += P.fft[g][k];
+        float low = (float)(a[0] / a[4]), mid = (float)(a[1] / a[5]), high = (float)(a[3] / a[6]);
+        float total = __fadd_rn(__fadd_rn(__fadd_rn(low, mid), high), 1e-10f);
+        float hr = __fdiv_rn(high, total), mr = __fdiv_rn(mid, total);
+        double mmean = a[1] / a[5];
+        double var = a[2] / a[5] - mmean * mmean;
+        float mstd = (float)sqrt(var > 0 ? var : 0.0);
+        float mcv = __fdiv_rn(mstd, __fadd_rn(mid, 1e-10f));
+        R.raw[0] = hr; R.raw[1] = mr; R.raw[2] = mcv;
+        double s = 0.0;
+        if (hr < 0.18f) s += 0.4; else if (hr < 0.22f) s += 0.2;
+        if (mcv > 0.6f) s += 0.25; else if (mcv > 0.45f) s += 0.1;
+        if (mr > 0.45f && hr < 0.2f) s += 0.15;
+        R.scores[0] = clip01(s);
+    }
+    float tmp[DFD_NBLK], tmp2[DFD_NBLK];
+    if (is_full) {
+        // ---- noise (:194-225) ----
+        for (int b = 0; b < DFD_NBLK; b++) {
+            double sx = (double)P.noise_sx[b], sxx = (double)P.noise_sxx[b];
+            double var = (sxx - sx * sx / 1024.0) / 1024.0;
+            tmp[b] = (float)(sqrt(var > 0 ? var : 0.0) / 256.0);
+        }
+        float mean_noise = dfd_np_mean_f32(tmp, DFD_NBLK);
+        float ncv = __fdiv_rn(dfd_np_std_f32(tmp, DFD_NBLK, tmp2), __fadd_rn(mean_noise, 1e-10f));
+        R.raw[3] = ncv; R.raw[4] = mean_noise;
+        double s = 0.0;
+        if (ncv > 0.7f) s += 0.5; else if (ncv > 0.5f) s += 0.25;
+        if (mean_noise < 1.0f) s += 0.3; else if (mean_noise < 2.0f) s += 0.1;
+        R.scores[1] = clip01(s);
+        // ---- ELA (:245-276) ----
+        for (int b = 0; b < DFD_NBLK; b++) tmp[b] = __fdiv_rn((float)P.ela_sum[b], 1024.0f);
+        float emean = dfd_np_mean_f32(tmp, DFD_NBLK);
+        float ecv = __fdiv_rn(dfd_np_std_f32(tmp, DFD_NBLK, tmp2), __fadd_rn(emean, 1e-10f));
+        R.raw[5] = ecv; R.raw[6] = emean;
+        s = 0.0;
+        if (ecv > 0.9f) s += 0.5; else if (ecv > 0.6f) s += 0.2;
+        if (emean > 15.0f) s += 0.2; else if (emean > 10.0f) s += 0.1;
+        R.scores[2] = clip01(s);
+    }
+    // ---- edges (:288-309) ----
+    {
+        double density = (double)P.canny_count / 65536.0;
+        long long ls = 0, lss = 0;
+        for (int b = 0; b < DFD_NBLK; b++) { ls += P.lap_s[b]; lss += P.lap_ss[b]; }
+        double mean = (double)ls / 65536.0;
+        double var = (double)lss / 65536.0 - mean * mean;
+        R.raw[7] = density; R.raw[8] = var;
+        double s = 0.0;
+        if (density < 0.02) s += 0.35; else if (density < 0.04) s += 0.15;
+        if (var < 50.0) s += 0.3; else if (var < 100.0) s += 0.1;
+        R.scores[3] = clip01(s);
+    }
+    if (is_full) {
+        // ---- colour (:318-347) ----
+        unsigned long long ss = 0, sss = 0, vs = 0, vss = 0;
+        unsigned int hb[6] = {0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < DFD_NBLK; b++) {
+            ss += P.sat_s[b]; sss += P.sat_ss[b]; vs += P.val_s[b]; vss += P.val_ss[b];
+            for (int k = 0; k < 6; k++) hb[k] |= P.hue_bits[b][k];
+        }
+        double sm = (double)ss / 65536.0, vm = (double)vs / 65536.0;
+        double svar = (double)sss / 65536.0 - sm * sm, vvar = (double)vss / 65536.0 - vm * vm;
+        float sstd = (float)sqrt(svar > 0 ? svar : 0.0), vstd = (float)sqrt(vvar > 0 ? vvar : 0.0);
+        int hues = 0;
+        for (int k = 0; k < 6; k++) hues += __popc(hb[k]);
+        R.raw[9] = sstd; R.raw[10] = vstd; R.raw[11] = hues;
+        double s = 0.0;
+        if (sstd < 15.0f) s += 0.3; else if (sstd < 25.0f) s += 0.1;
+        if (vstd < 15.0f) s += 0.25; else if (vstd < 25.0f) s += 0.1;
+        if (hues < 30) s += 0.25; else if (hues < 50) s += 0.1;
+        R.scores[4] = clip01(s);
+    }
+    // ---- temporal (:356-389) ----
+    {
+        double s = 0.0;
+        if (!S.has_prev) {
+            S.has_prev = 1;
+            R.raw[14] = 0;
+        } else {
+            int td = 0;
+            for (int b = 0; b < DFD_NBLK; b++) td += P.tdiff[b];
+            float mean_diff = __fdiv_rn((float)td, 65536.0f);       // exact: integer sum < 2^24
+            if (S.ring_n < DFD_RING) { S.ring[(S.ring_head + S.ring_n) % DFD_RING] = mean_diff; S.ring_n++; }
+            else { S.ring[S.ring_head] = mean_diff; S.ring_head = (S.ring_head + 1) % DFD_RING; }
+            R.raw[13] = mean_diff; R.raw[14] = S.ring_n;
+            if (S.ring_n >= 5) {
+                for (int k = 0; k < S.ring_n; k++) tmp[k] = S.ring[(S.ring_head + k) % DFD_RING];
+                float md = dfd_np_mean_f32(tmp, S.ring_n);
+                float cv = __fdiv_rn(dfd_np_std_f32(tmp, S.ring_n, tmp2), __fadd_rn(md, 1e-10f));
+                R.raw[12] = cv;
+                if (cv > 1.5f) s += 0.4; else if (cv > 1.0f) s += 0.2;
+                if (mean_diff < 0.3f && S.analyzer_frames > 10) s += 0.3;
+                else if (mean_diff < 0.8f && S.analyzer_frames > 10) s += 0.1;
+            }
+        }
+        R.scores[5] = clip01(s);
+    }
+    // ---- weighted sum in the reference's dict order, Python float arithmetic (:94,119) ----
+    double c = 0.0;
+    if (is_full) {
+        c = c + R.scores[0] * 0.25; c = c + R.scores[1] * 0.20; c = c + R.scores[2] * 0.20;
+        c = c + R.scores[3] * 0.15; c = c + R.scores[4] * 0.10; c = c + R.scores[5] * 0.10;
+    } else {
+        c = c + R.scores[0] * 0.45; c = c + R.scores[5] * 0.25; c = c + R.scores[3] * 0.30;
+    }
+    R.fake_probability = clip01(c);
+    results[i] = R;
+}
+
+// ---------------------------------------------------------------------------------------------
+int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride, int row_pitch,
+                         const int32_t* stream_ids, const uint8_t* full, dfd_forensic_result* results, cudaStream_t st) {
+    DFD_REQUIRE(n > 0 && n <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "forensics: batch exceeds max_batch");
+    DFD_REQUIRE(H >= 1 && W >= 1 && row_pitch >= 3 * W, DFD_ERR_INVALID, "forensics: bad frame geometry");
+    k_resize256<<<dim3(T, n), 256, 0, st>>>(frames, H, W, frame_stride, row_pitch, ctx->d_tile, ctx->d_gray);
+    DFD_LAUNCH_CHECK();
+    k_tile_stats<<<dim3(DFD_NBLK, n), 256, 0, st>>>(ctx->d_tile, ctx->d_gray, stream_ids, full, ctx->d_tables, ctx->d_state,
+                                                     ctx->d_prev_gray, ctx->d_part);
+    DFD_LAUNCH_CHECK();
+    k_canny<<<n, 1024, T * T + 2 * 2048 * 4, st>>>(ctx->d_gray, &ctx->d_part[0].canny_count, sizeof(DfdFramePartials), nullptr);
+    DFD_LAUNCH_CHECK();
+    k_ela<<<n, 512, T * T + 2 * 128 * 128, st>>>(ctx->d_tile, full, ctx->d_part, nullptr);
+    DFD_LAUNCH_CHECK();
+    k_fft_rows<<<dim3(16, n), 1024, 0, st>>>(ctx->d_gray, ctx->d_twiddle, ctx->d_fft);
+    DFD_LAUNCH_CHECK();
+    k_fft_cols<<<dim3(DFD_FFT_GROUPS, n), 1024, 0, st>>>(ctx->d_fft, ctx->d_twiddle, ctx->d_part);
+    DFD_LAUNCH_CHECK();
+    k_finalize<<<(n + 63) / 64, 64, 0, st>>>(n, stream_ids, full, ctx->d_part, ctx->d_state, results);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_forensics_init(dfd_ctx* ctx) {
+    DFD_CUDA(cudaFuncSetAttribute(k_canny, cudaFuncAttributeMaxDynamicSharedMemorySize, T * T + 2 * 2048 * 4));
+    DFD_CUDA(cudaFuncSetAttribute(k_ela, cudaFuncAttributeMaxDynamicSharedMemorySize, T * T + 2 * 128 * 128));
+    return DFD_OK;
+}
+
+int dfd_dbg_jpeg_launch(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n, cudaStream_t st) {
+    k_ela<<<n, 512, T * T + 2 * 128 * 128, st>>>(tiles, nullptr, nullptr, out);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_dbg_canny_launch(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, cudaStream_t st) {
+    k_canny<<<n, 1024, T * T + 2 * 2048 * 4, st>>>(gray, nullptr, 0, edges);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}

@@ -73,7 +73,6 @@ DFD_HD void dfd_lab2bgr(const DfdColorTables* T, int L, int a, int b, int* ob, i
 }
 
 // ---- host-side table construction ------------------------------------------
-#if !defined(__CUDA_ARCH__)
 #include <cmath>
 static inline int dfd_cvround_d(double v) { return (int)std::nearbyint(v); }   // FE_TONEAREST: half-to-even
 static inline int dfd_cvround_f(float v) { return (int)std::nearbyintf(v); }
@@ -150,4 +149,3 @@ static inline void dfd_build_color_tables(DfdColorTables* T, int cbrt_mode = 0, 
         T->inv_gamma[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
     }
 }
-#endif

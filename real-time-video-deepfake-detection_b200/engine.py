@@ -1,0 +1,220 @@
+"""Host-side engine: owns one libdfd context on one GPU and moves torch tensors
+across the C-ABI.  PyTorch is used for device memory, streams and (in
+sharding.py) torch.distributed only -- every kernel on the path is libdfd's.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, weights as _weights
+
+FORENSIC_DTYPE = np.dtype([("raw", "<f8", (_lib.N_RAW,)), ("scores", "<f8", (_lib.N_SIGNALS,)),
+                           ("fake_probability", "<f8"), ("frame_number", "<i4"), ("full", "<i4")])
+RECORD_DTYPE = np.dtype([("stream_id", "<i4"), ("verdict", "<i4"), ("fake_count", "<i4"), ("real_count", "<i4"),
+                         ("history_len", "<i4"), ("frame_count", "<i4"), ("vote_input", "<f8"),
+                         ("temporal_average", "<f8"), ("stability_score", "<f8"), ("face_probability", "<f8"),
+                         ("forensic_probability", "<f8")])
+assert FORENSIC_DTYPE.itemsize == _lib.FORENSIC_BYTES and RECORD_DTYPE.itemsize == _lib.RECORD_BYTES
+
+DTYPES = {"fp32": (_lib.F32, torch.float32), "bf16": (_lib.BF16, torch.bfloat16)}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One context per GPU.  All tensor arguments are CUDA tensors on ``device``."""
+
+    def __init__(self, device=0, max_streams=256, max_batch=256, max_crop=1024, window_size=60, voting_window=10,
+                 detection_threshold=0.5, face_weight=0.70, forensic_weight=0.30, blend_mode="reference"):
+        if not torch.cuda.is_available():
+            raise _lib.DfdError("no CUDA device visible: the B200 path has no CPU fallback")
+        self.lib = _lib.load()
+        if isinstance(device, torch.device):
+            device = device.index or 0
+        self.device = torch.device("cuda", int(device))
+        cfg = _lib.Config()
+        self.lib.dfd_default_config(C.byref(cfg))
+        cfg.device, cfg.max_streams, cfg.max_batch, cfg.max_crop = int(device), max_streams, max_batch, max_crop
+        cfg.window_size, cfg.voting_window = window_size, voting_window
+        cfg.detection_threshold, cfg.face_weight, cfg.forensic_weight = detection_threshold, face_weight, forensic_weight
+        cfg.blend_mode = {"reference": 0, "readme": 1}[blend_mode]
+        self.cfg = cfg
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)          # make torch's primary context current first
+            h = C.c_void_p()
+            rc = self.lib.dfd_create(C.byref(cfg), C.byref(h))
+            if rc != 0:
+                raise _lib.DfdError(f"dfd_create failed ({rc}): {self.lib.dfd_last_error(None).decode()}")
+        self.h = h
+        self.has_weights = False
+
+    # -- plumbing -----------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dfd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise _lib.DfdError(f"{what} failed ({rc}): {self.lib.dfd_last_error(self.h).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, a, dtype):
+        if torch.is_tensor(a):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    @property
+    def launches(self):
+        return int(self.lib.dfd_launch_count(self.h))
+
+    # -- weights --------------------------------------------------------------------
+    def load_state_dict(self, state_dict):
+        sd = _weights.extract_state_dict(state_dict)
+        blob = np.ascontiguousarray(_weights.pack_state_dict(sd), np.float32)
+        assert blob.size == self.lib.dfd_weights_blob_floats()
+        self._check(self.lib.dfd_load_weights(self.h, blob.ctypes.data_as(C.c_void_p), blob.size), "dfd_load_weights")
+        self.has_weights = True
+        return _weights.check_keys(sd)
+
+    # -- forensics ------------------------------------------------------------------
+    def forensics_batch(self, frames, stream_ids, full):
+        """frames: (n,H,W,3) uint8 CUDA tensor (BGR).  Returns a (n,) uint8-backed CUDA tensor of
+        dfd_forensic_result records; use ``forensic_to_numpy``."""
+        n, H, W, _ = frames.shape
+        assert frames.dtype == torch.uint8 and frames.is_cuda and frames.stride(3) == 1 and frames.stride(2) == 3
+        sid = self._dev(stream_ids, torch.int32)
+        fl = self._dev(full, torch.uint8)
+        out = torch.empty(n * _lib.FORENSIC_BYTES, dtype=torch.uint8, device=self.device)
+        rc = self.lib.dfd_forensics_batch(self.h, _ptr(frames), n, H, W, frames.stride(0), frames.stride(1), _ptr(sid),
+                                          _ptr(fl), _ptr(out), self._stream())
+        self._check(rc, "dfd_forensics_batch")
+        return out
+
+    @staticmethod
+    def forensic_to_numpy(buf):
+        return buf.cpu().numpy().view(FORENSIC_DTYPE)
+
+    @staticmethod
+    def records_to_numpy(buf):
+        return buf.cpu().numpy().view(RECORD_DTYPE)
+
+    # -- face path --------------------------------------------------------------------
+    def face_prep_batch(self, frames, boxes, frame_idx, dtype="fp32"):
+        n, H, W, _ = frames.shape
+        code, tdt = DTYPES[dtype]
+        bx = self._dev(boxes, torch.int32)
+        fi = self._dev(frame_idx, torch.int32)
+        m = bx.shape[0]
+        out = torch.empty((m, 224, 224, 3), dtype=tdt, device=self.device)
+        rc = self.lib.dfd_face_prep_batch(self.h, _ptr(frames), n, H, W, frames.stride(0), frames.stride(1), _ptr(bx),
+                                          _ptr(fi), m, _ptr(out), code, self._stream())
+        self._check(rc, "dfd_face_prep_batch")
+        return out
+
+    def effnet_forward(self, x_nhwc):
+        """x: (m,224,224,3) float32 or bfloat16 CUDA tensor, NHWC.  Returns logits (m,) float32."""
+        code = _lib.F32 if x_nhwc.dtype == torch.float32 else _lib.BF16
+        assert x_nhwc.is_contiguous() and x_nhwc.shape[1:] == (224, 224, 3)
+        m = x_nhwc.shape[0]
+        logits = torch.empty(m, dtype=torch.float32, device=self.device)
+        self._check(self.lib.dfd_effnet_forward(self.h, _ptr(x_nhwc), m, code, _ptr(logits), self._stream()),
+                    "dfd_effnet_forward")
+        return logits
+
+    def face_probability(self, logits, boxes):
+        bx = self._dev(boxes, torch.int32)
+        m = logits.shape[0]
+        prob = torch.empty(m, dtype=torch.float64, device=self.device)
+        self._check(self.lib.dfd_face_probability(self.h, _ptr(logits), _ptr(bx), m, _ptr(prob), self._stream()),
+                    "dfd_face_probability")
+        return prob
+
+    # -- vote -------------------------------------------------------------------------
+    def vote_update(self, stream_ids, vote_input):
+        sid = self._dev(stream_ids, torch.int32)
+        vi = self._dev(vote_input, torch.float64)
+        n = sid.shape[0]
+        rec = torch.empty(n * _lib.RECORD_BYTES, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.dfd_vote_update(self.h, _ptr(sid), _ptr(vi), n, _ptr(rec), self._stream()), "dfd_vote_update")
+        return rec
+
+    def analyze_batch(self, frames, stream_ids, full, boxes, box_frame, dtype="bf16", want_forensic=False,
+                      records_out=None):
+        """Whole per-frame path for one frame per stream (see dfd_analyze_batch)."""
+        n, H, W, _ = frames.shape
+        code, _t = DTYPES[dtype]
+        sid = self._dev(stream_ids, torch.int32)
+        fl = self._dev(full, torch.uint8)
+        m = 0 if boxes is None else int(boxes.shape[0])
+        bx = self._dev(boxes, torch.int32) if m else None
+        bf = self._dev(box_frame, torch.int32) if m else None
+        rec = records_out if records_out is not None else torch.empty(n * _lib.RECORD_BYTES, dtype=torch.uint8,
+                                                                      device=self.device)
+        fres = torch.empty(n * _lib.FORENSIC_BYTES, dtype=torch.uint8, device=self.device) if want_forensic else None
+        fprob = torch.empty(max(m, 1), dtype=torch.float64, device=self.device)
+        rc = self.lib.dfd_analyze_batch(self.h, _ptr(frames), n, H, W, frames.stride(0), frames.stride(1), _ptr(sid),
+                                        _ptr(fl), _ptr(bx), _ptr(bf), m, code, _ptr(fres), _ptr(fprob), _ptr(rec),
+                                        self._stream())
+        self._check(rc, "dfd_analyze_batch")
+        return rec, fres, fprob[:m]
+
+    def reset(self, stream_id=-1):
+        self._check(self.lib.dfd_reset_stream(self.h, int(stream_id), self._stream()), "dfd_reset_stream")
+
+    # -- diagnostics ------------------------------------------------------------------
+    def dbg_tiles(self, n):
+        tile = torch.empty((n, 256, 256, 3), dtype=torch.uint8, device=self.device)
+        gray = torch.empty((n, 256, 256), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.dfd_dbg_tiles(self.h, _ptr(tile), _ptr(gray), n, self._stream()), "dfd_dbg_tiles")
+        return tile, gray
+
+    def dbg_jpeg_roundtrip(self, tiles):
+        out = torch.empty_like(tiles)
+        self._check(self.lib.dfd_dbg_jpeg_roundtrip(self.h, _ptr(tiles), _ptr(out), tiles.shape[0], self._stream()),
+                    "dfd_dbg_jpeg_roundtrip")
+        return out
+
+    def dbg_canny(self, gray):
+        out = torch.empty_like(gray)
+        self._check(self.lib.dfd_dbg_canny(self.h, _ptr(gray), _ptr(out), gray.shape[0], self._stream()), "dfd_dbg_canny")
+        return out
+
+    def dbg_face160(self, i):
+        out = torch.empty((160, 160, 3), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.dfd_dbg_face160(self.h, i, _ptr(out), self._stream()), "dfd_dbg_face160")
+        return out
+
+    def dbg_face_clahe(self, frames, boxes, frame_idx, i):
+        n, H, W, _ = frames.shape
+        bx = self._dev(boxes, torch.int32)
+        fi = self._dev(frame_idx, torch.int32)
+        w, h = int(bx[i, 2]), int(bx[i, 3])
+        out = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        rc = self.lib.dfd_dbg_face_clahe(self.h, _ptr(frames), H, W, frames.stride(0), frames.stride(1), _ptr(bx), _ptr(fi),
+                                         i, _ptr(out), self._stream())
+        self._check(rc, "dfd_dbg_face_clahe")
+        return out
+
+    def set_tap(self, name):
+        self._check(self.lib.dfd_dbg_set_tap(self.h, (name or "").encode()), "dfd_dbg_set_tap")
+
+    def activation(self, name):
+        n = self.lib.dfd_dbg_activation(self.h, name.encode(), None, 0, self._stream())
+        if n < 0:
+            self._check(int(n), "dfd_dbg_activation")
+        out = torch.empty(int(n), dtype=torch.float32, device=self.device)
+        self.lib.dfd_dbg_activation(self.h, name.encode(), _ptr(out), n, self._stream())
+        return out
