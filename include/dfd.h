@@ -71,13 +71,15 @@ typedef struct {
 
 /* One stream's vote record; replaces TemporalTracker.update + get_confidence_level +
  * get_voting_stats + get_temporal_average + get_stability_score
- * (deepfake_detection.py:120-268).  32-byte aligned, gathered across GPUs as is. */
+ * (deepfake_detection.py:120-268).  72 bytes, gathered across GPUs as is. */
 typedef struct {
     int32_t stream_id;
     int32_t verdict;              /* dfd_verdict */
     int32_t fake_count, real_count;
     int32_t history_len;          /* len(score_history) */
     int32_t frame_count;          /* detector.frame_count of the stream */
+    int32_t last_vote;            /* this frame's classification: 1 FAKE, 0 REAL, -1 none (update(None)) */
+    int32_t reserved;
     double vote_input;            /* NaN = nothing fed this frame */
     double temporal_average;
     double stability_score;
@@ -122,8 +124,11 @@ int dfd_effnet_forward(dfd_ctx* ctx, const void* in_nhwc, int m, int dtype, floa
 /* sigmoid + apply_heuristics (deepfake_detection.py:398,489-502): prob[i] = clip(sigmoid(logit) + 0.10*(w<80||h<80)). */
 int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, void* stream);
 
-/* TemporalTracker.update for n streams (deepfake_detection.py:120-196).  vote_input[i] NaN = update(None). */
-int dfd_vote_update(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, int n,
+/* TemporalTracker.update for n streams (deepfake_detection.py:120-196).  vote_input[i] NaN = update(None).
+ * np_flags (nullable, device u8[n]): 1 where the reference's value would be a numpy scalar (the face
+ * probability returned by np.clip, deepfake_detection.py:502) rather than a Python float; it selects how
+ * Python's sum() rounds temporal_average / stability_score (compensated vs plain) and nothing else. */
+int dfd_vote_update(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
                     dfd_vote_record* records, void* stream);
 
 /* The whole per-frame path for a batch: forensics + face prep + classifier + probability + vote input
@@ -139,6 +144,11 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
  * (deepfake_detection.py:344-355, 270-289; frame_analysis.py:391-395).  stream_id < 0 resets all. */
 int dfd_reset_stream(dfd_ctx* ctx, int stream_id, void* stream);
 
+/* Per-stream tracker parameters (TemporalTracker(window_size, voting_window, detection_threshold),
+ * deepfake_detection.py:99); streams start with the context defaults.  Resets the stream's vote state. */
+int dfd_configure_stream(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double detection_threshold,
+                         void* stream);
+
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t dfd_launch_count(dfd_ctx* ctx);
 
@@ -149,6 +159,9 @@ int dfd_dbg_tiles(dfd_ctx* ctx, uint8_t* tile_out, uint8_t* gray_out, int n, voi
 int dfd_dbg_jpeg_roundtrip(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n, void* stream);
 /* Canny(50,150) edge map (0/255) of n gray tiles (256 x 256). */
 int dfd_dbg_canny(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, void* stream);
+/* tcgen05 GEMM self-test: C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual) on random bf16 data against a
+ * CUDA-core reference; writes max |err| to *max_err_host (HOST double) and returns 0 if the kernel ran. */
+int dfd_gemm_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int with_residual, double* max_err_host, void* stream);
 /* After dfd_face_prep_batch: the 160 x 160 x 3 RGB u8 image of box i. */
 int dfd_dbg_face160(dfd_ctx* ctx, int i, uint8_t* out_dev, void* stream);
 /* After dfd_face_prep_batch: the CLAHE'd crop of box i as w*h*3 BGR u8 (tight). */

@@ -25,13 +25,14 @@ class ForensicResult(C.Structure):
 
 class VoteRecord(C.Structure):
     _fields_ = [("stream_id", C.c_int32), ("verdict", C.c_int32), ("fake_count", C.c_int32), ("real_count", C.c_int32),
-                ("history_len", C.c_int32), ("frame_count", C.c_int32), ("vote_input", C.c_double),
+                ("history_len", C.c_int32), ("frame_count", C.c_int32), ("last_vote", C.c_int32), ("reserved", C.c_int32),
+                ("vote_input", C.c_double),
                 ("temporal_average", C.c_double), ("stability_score", C.c_double), ("face_probability", C.c_double),
                 ("forensic_probability", C.c_double)]
 
 
 FORENSIC_BYTES = C.sizeof(ForensicResult)     # 192
-RECORD_BYTES = C.sizeof(VoteRecord)           # 64
+RECORD_BYTES = C.sizeof(VoteRecord)           # 72
 
 # name -> (restype, argtypes); every symbol include/dfd.h declares
 _P, _I, _S = C.c_void_p, C.c_int, C.c_size_t
@@ -47,9 +48,10 @@ SYMBOLS = {
     "dfd_face_prep_batch": (_I, [_P, _P, _I, _I, _I, _S, _I, _P, _P, _I, _P, _I, _P]),
     "dfd_effnet_forward": (_I, [_P, _P, _I, _I, _P, _P]),
     "dfd_face_probability": (_I, [_P, _P, _P, _I, _P, _P]),
-    "dfd_vote_update": (_I, [_P, _P, _P, _I, _P, _P]),
+    "dfd_vote_update": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "dfd_analyze_batch": (_I, [_P, _P, _I, _I, _I, _S, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "dfd_reset_stream": (_I, [_P, _I, _P]),
+    "dfd_configure_stream": (_I, [_P, _I, _I, _I, C.c_double, _P]),
     "dfd_launch_count": (C.c_int64, [_P]),
     "dfd_dbg_tiles": (_I, [_P, _P, _P, _I, _P]),
     "dfd_dbg_jpeg_roundtrip": (_I, [_P, _P, _P, _I, _P]),
@@ -58,7 +60,7 @@ SYMBOLS = {
     "dfd_dbg_face_clahe": (_I, [_P, _P, _I, _I, _S, _I, _P, _P, _I, _P, _P]),
     "dfd_dbg_set_tap": (_I, [_P, C.c_char_p]),
     "dfd_dbg_activation": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),
-    "dfd_gemm_selftest": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "dfd_gemm_selftest": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(C.c_double), _P]),
 }
 
 _lib = None

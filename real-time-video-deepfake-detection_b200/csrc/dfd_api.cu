@@ -81,6 +81,8 @@ static int create_impl(dfd_ctx* ctx) {
     DFD_CUDA(cudaMalloc(&ctx->d_voteinput, nb * sizeof(double)));
     int rc = dfd_forensics_init(ctx);
     if (rc) return rc;
+    if ((rc = dfd_configure_launch(ctx, -1, c.window_size, c.voting_window, c.detection_threshold, 0))) return rc;
+    DFD_CUDA(cudaDeviceSynchronize());
     return DFD_OK;
 }
 
@@ -140,11 +142,11 @@ int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes
     return dfd_faceprob_launch(ctx, logits, boxes, m, prob, (cudaStream_t)stream);
 }
 
-int dfd_vote_update(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, int n, dfd_vote_record* records,
-                    void* stream) {
+int dfd_vote_update(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
+                    dfd_vote_record* records, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
     DFD_REQUIRE(stream_ids && vote_input && records && n > 0, DFD_ERR_INVALID, "vote_update: bad argument");
-    return dfd_vote_launch(ctx, stream_ids, vote_input, n, records, (cudaStream_t)stream);
+    return dfd_vote_launch(ctx, stream_ids, vote_input, np_flags, n, records, (cudaStream_t)stream);
 }
 
 int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride, int row_pitch,
@@ -173,6 +175,15 @@ int dfd_reset_stream(dfd_ctx* ctx, int stream_id, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
     DFD_REQUIRE(stream_id < ctx->cfg.max_streams, DFD_ERR_CAPACITY, "reset_stream: id beyond max_streams");
     return dfd_reset_launch(ctx, stream_id, (cudaStream_t)stream);
+}
+
+int dfd_configure_stream(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double detection_threshold,
+                         void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(stream_id < ctx->cfg.max_streams, DFD_ERR_CAPACITY, "configure_stream: id beyond max_streams");
+    DFD_REQUIRE(window_size >= 10 && window_size <= DFD_MAX_SCORES, DFD_ERR_INVALID, "configure_stream: window_size must be 10..128");
+    DFD_REQUIRE(voting_window >= 1 && voting_window <= DFD_MAX_VOTES, DFD_ERR_INVALID, "configure_stream: voting_window must be 1..64");
+    return dfd_configure_launch(ctx, stream_id, window_size, voting_window, detection_threshold, (cudaStream_t)stream);
 }
 
 int64_t dfd_launch_count(dfd_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -28,7 +28,10 @@ struct DfdStreamState {
     int32_t vote_n, vote_head;
     int32_t verdict;
     int32_t detector_frames;
+    int32_t window_size, voting_window;     // per-stream TemporalTracker parameters
+    double threshold;
     uint8_t votes[DFD_MAX_VOTES];
+    uint8_t score_is_np[DFD_MAX_SCORES];    // 1 = the score was a numpy scalar in the reference (see vote.cu py_sum)
     double scores[DFD_MAX_SCORES];
 };
 
@@ -131,9 +134,10 @@ int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n);
 size_t dfd_effnet_blob_floats();
 // vote.cu
 int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, cudaStream_t st);
-int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, int n, dfd_vote_record* rec,
-                    cudaStream_t st);
+int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
+                    dfd_vote_record* rec, cudaStream_t st);
 int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame, const double* face_prob,
                            const dfd_forensic_result* fres, const int32_t* stream_ids, dfd_vote_record* rec,
                            cudaStream_t st);
 int dfd_reset_launch(dfd_ctx* ctx, int stream_id, cudaStream_t st);
+int dfd_configure_launch(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double thr, cudaStream_t st);

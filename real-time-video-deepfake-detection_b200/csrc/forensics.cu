@@ -497,12 +497,10 @@ __global__ void k_finalize(int n, const int32_t* __restrict__ stream_ids, const 
     }
     // ---- weighted sum in the reference's dict order, Python float arithmetic (:94,119) ----
     double c = 0.0;
-    if (is_full) {
-        c = c + R.scores[0] * 0.25; c = c + R.scores[1] * 0.20; c = c + R.scores[2] * 0.20;
-        c = c + R.scores[3] * 0.15; c = c + R.scores[4] * 0.10; c = c + R.scores[5] * 0.10;
-    } else {
-        c = c + R.scores[0] * 0.45; c = c + R.scores[5] * 0.25; c = c + R.scores[3] * 0.30;
-    }
+#define ACC(si, w) c = __dadd_rn(c, __dmul_rn(R.scores[si], w))      /* no FMA: Python rounds the product */
+    if (is_full) { ACC(0, 0.25); ACC(1, 0.20); ACC(2, 0.20); ACC(3, 0.15); ACC(4, 0.10); ACC(5, 0.10); }
+    else { ACC(0, 0.45); ACC(5, 0.25); ACC(3, 0.30); }
+#undef ACC
     R.fake_probability = clip01(c);
     results[i] = R;
 }

@@ -7,15 +7,53 @@
 #include "dfd_internal.cuh"
 
 struct VoteCfg {
-    int window_size, voting_window, blend_mode;
-    double threshold, face_w, forensic_w;
+    int blend_mode;
+    double face_w, forensic_w;
 };
 
-__device__ void tracker_update(DfdStreamState& S, const VoteCfg& c, double p, dfd_vote_record& r) {
+struct TrackerParams { int window_size, voting_window; double threshold; };
+
+// Python's builtin sum() over the score deque, bit for bit (CPython >= 3.12, Python/bltinmodule.c):
+// the running total starts as int 0; while the items are exact Python floats the total is a
+// Neumaier-compensated (hi, lo) pair; the first item that is not an exact float (np.float64, which is
+// what np.clip returns in apply_heuristics, deepfake_detection.py:502) collapses the pair and every
+// later addition is a plain double add.  is_np[k] != 0 marks such items.
+struct ScoreRing {
+    const double* v; const uint8_t* is_np; int head, n, cap;
+    __device__ double val(int k) const { return v[(head + k) % cap]; }
+    __device__ bool np(int k) const { return is_np[(head + k) % cap] != 0; }
+};
+
+template <class Item>
+__device__ double py_sum(int n, Item item, bool any_np_forces_plain, const ScoreRing& R) {
+    if (n == 0) return 0.0;
+    double hi = item(0), lo = 0.0;
+    int k = 1;
+    bool exact = any_np_forces_plain ? false : !R.np(0);
+    if (exact) {
+        for (; k < n; k++) {
+            if (R.np(k)) break;
+            double x = item(k);
+            double t = __dadd_rn(hi, x);
+            if (fabs(hi) >= fabs(x)) lo = __dadd_rn(lo, __dadd_rn(__dsub_rn(hi, t), x));
+            else lo = __dadd_rn(lo, __dadd_rn(__dsub_rn(x, t), hi));
+            hi = t;
+        }
+        if (lo != 0.0 && isfinite(lo)) hi = __dadd_rn(hi, lo);
+    }
+    for (; k < n; k++) hi = __dadd_rn(hi, item(k));
+    return hi;
+}
+
+__device__ void tracker_update(DfdStreamState& S, const VoteCfg&, double p, int p_is_np, dfd_vote_record& r) {
+    TrackerParams c{S.window_size, S.voting_window, S.threshold};
+    r.last_vote = -1; r.reserved = 0;
     if (p == p) {                                   // update(None) is ignored (:123-124)
-        if (S.score_n < c.window_size) { S.scores[(S.score_head + S.score_n) % c.window_size] = p; S.score_n++; }
-        else { S.scores[S.score_head] = p; S.score_head = (S.score_head + 1) % c.window_size; }
+        int slot = S.score_n < c.window_size ? (S.score_head + S.score_n) % c.window_size : S.score_head;
+        S.scores[slot] = p; S.score_is_np[slot] = (uint8_t)(p_is_np != 0);
+        if (S.score_n < c.window_size) S.score_n++; else S.score_head = (S.score_head + 1) % c.window_size;
         uint8_t cls = p > c.threshold ? 1 : 0;      // strict > (:135)
+        r.last_vote = cls;
         if (S.vote_n < c.voting_window) { S.votes[(S.vote_head + S.vote_n) % c.voting_window] = cls; S.vote_n++; }
         else { S.votes[S.vote_head] = cls; S.vote_head = (S.vote_head + 1) % c.voting_window; }
         int fake = 0;
@@ -31,16 +69,16 @@ __device__ void tracker_update(DfdStreamState& S, const VoteCfg& c, double p, df
     r.history_len = S.score_n;
     r.frame_count = S.detector_frames;
     r.vote_input = p;
-    double sum = 0.0;                               // sum(deque)/len (:198-202)
-    for (int k = 0; k < S.score_n; k++) sum = __dadd_rn(sum, S.scores[(S.score_head + k) % c.window_size]);
+    ScoreRing R{S.scores, S.score_is_np, S.score_head, S.score_n, c.window_size};
+    bool any_np = false;
+    for (int k = 0; k < S.score_n; k++) any_np |= R.np(k);
+    double sum = py_sum(S.score_n, [&](int k) { return R.val(k); }, false, R);            // sum(deque)/len (:198-202)
     r.temporal_average = S.score_n ? __ddiv_rn(sum, (double)S.score_n) : 0.0;
     if (S.score_n < 10) r.stability_score = 0.0;    // :214-221
     else {
-        double mean = r.temporal_average, v = 0.0;
-        for (int k = 0; k < S.score_n; k++) {
-            double d = __dsub_rn(S.scores[(S.score_head + k) % c.window_size], mean);
-            v = __dadd_rn(v, __dmul_rn(d, d));
-        }
+        const double mean = r.temporal_average;
+        // (x - mean) ** 2 items are np.float64 as soon as the mean is (any np score) -> plain summation
+        double v = py_sum(S.score_n, [&](int k) { double d = __dsub_rn(R.val(k), mean); return __dmul_rn(d, d); }, any_np, R);
         v = __ddiv_rn(v, (double)S.score_n);
         double m4 = __dmul_rn(v, 4.0);
         r.stability_score = __dsub_rn(1.0, m4 < 1.0 ? m4 : 1.0);
@@ -48,14 +86,15 @@ __device__ void tracker_update(DfdStreamState& S, const VoteCfg& c, double p, df
 }
 
 __global__ void k_vote(int n, const int32_t* __restrict__ stream_ids, const double* __restrict__ vote_input,
-                       DfdStreamState* __restrict__ state, VoteCfg cfg, dfd_vote_record* __restrict__ rec) {
+                       const uint8_t* __restrict__ np_flags, DfdStreamState* __restrict__ state, VoteCfg cfg,
+                       dfd_vote_record* __restrict__ rec) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     dfd_vote_record r;
     r.stream_id = stream_ids[i];
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
     r.face_probability = NaN; r.forensic_probability = NaN;
-    tracker_update(state[r.stream_id], cfg, vote_input[i], r);
+    tracker_update(state[r.stream_id], cfg, vote_input[i], np_flags ? np_flags[i] : 0, r);
     rec[i] = r;
 }
 
@@ -79,7 +118,7 @@ __global__ void k_select_vote(int n, int m, const int32_t* __restrict__ box_fram
     S.detector_frames += 1;                                          // backend_server.py:156
     r.face_probability = fp;
     r.forensic_probability = forensic;
-    tracker_update(S, cfg, p, r);
+    tracker_update(S, cfg, p, (fp == fp) ? 1 : 0, r);   // face prob is np.float64 (np.clip), forensic prob a Python float
     rec[i] = r;
 }
 
@@ -97,19 +136,24 @@ __global__ void k_faceprob(int m, const float* __restrict__ logits, const int32_
     prob[i] = p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p);
 }
 
-__global__ void k_reset(DfdStreamState* state, int first, int count) {
+// what: bit 0 = forensic analyzer state, bit 1 = tracker + detector.frame_count; cfg != 0 also sets parameters
+__global__ void k_reset(DfdStreamState* state, int first, int count, int what, int set_cfg, int window_size,
+                        int voting_window, double thr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     DfdStreamState& S = state[first + i];
-    S.has_prev = 0; S.analyzer_frames = 0; S.ring_n = 0; S.ring_head = 0;
-    S.score_n = 0; S.score_head = 0; S.vote_n = 0; S.vote_head = 0;
-    S.verdict = DFD_UNCERTAIN; S.detector_frames = 0;
+    if (what & 1) { S.has_prev = 0; S.analyzer_frames = 0; S.ring_n = 0; S.ring_head = 0; }
+    if (what & 2) {
+        S.score_n = 0; S.score_head = 0; S.vote_n = 0; S.vote_head = 0;
+        S.verdict = DFD_UNCERTAIN; S.detector_frames = 0;
+    }
+    if (set_cfg) { S.window_size = window_size; S.voting_window = voting_window; S.threshold = thr; }
 }
 
 static VoteCfg make_cfg(const dfd_ctx* ctx) {
     VoteCfg c;
-    c.window_size = ctx->cfg.window_size; c.voting_window = ctx->cfg.voting_window; c.blend_mode = ctx->cfg.blend_mode;
-    c.threshold = ctx->cfg.detection_threshold; c.face_w = ctx->cfg.face_weight; c.forensic_w = ctx->cfg.forensic_weight;
+    c.blend_mode = ctx->cfg.blend_mode;
+    c.face_w = ctx->cfg.face_weight; c.forensic_w = ctx->cfg.forensic_weight;
     return c;
 }
 
@@ -119,9 +163,9 @@ int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes,
     return DFD_OK;
 }
 
-int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, int n, dfd_vote_record* rec,
-                    cudaStream_t st) {
-    k_vote<<<(n + 63) / 64, 64, 0, st>>>(n, stream_ids, vote_input, ctx->d_state, make_cfg(ctx), rec);
+int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
+                    dfd_vote_record* rec, cudaStream_t st) {
+    k_vote<<<(n + 63) / 64, 64, 0, st>>>(n, stream_ids, vote_input, np_flags, ctx->d_state, make_cfg(ctx), rec);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
@@ -136,7 +180,14 @@ int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame,
 
 int dfd_reset_launch(dfd_ctx* ctx, int stream_id, cudaStream_t st) {
     int first = stream_id < 0 ? 0 : stream_id, count = stream_id < 0 ? ctx->cfg.max_streams : 1;
-    k_reset<<<(count + 127) / 128, 128, 0, st>>>(ctx->d_state, first, count);
+    k_reset<<<(count + 127) / 128, 128, 0, st>>>(ctx->d_state, first, count, 3, 0, 0, 0, 0.0);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_configure_launch(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double thr, cudaStream_t st) {
+    int first = stream_id < 0 ? 0 : stream_id, count = stream_id < 0 ? ctx->cfg.max_streams : 1;
+    k_reset<<<(count + 127) / 128, 128, 0, st>>>(ctx->d_state, first, count, 2, 1, window_size, voting_window, thr);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

@@ -12,7 +12,8 @@ from . import _lib, weights as _weights
 FORENSIC_DTYPE = np.dtype([("raw", "<f8", (_lib.N_RAW,)), ("scores", "<f8", (_lib.N_SIGNALS,)),
                            ("fake_probability", "<f8"), ("frame_number", "<i4"), ("full", "<i4")])
 RECORD_DTYPE = np.dtype([("stream_id", "<i4"), ("verdict", "<i4"), ("fake_count", "<i4"), ("real_count", "<i4"),
-                         ("history_len", "<i4"), ("frame_count", "<i4"), ("vote_input", "<f8"),
+                         ("history_len", "<i4"), ("frame_count", "<i4"), ("last_vote", "<i4"), ("reserved", "<i4"),
+                         ("vote_input", "<f8"),
                          ("temporal_average", "<f8"), ("stability_score", "<f8"), ("face_probability", "<f8"),
                          ("forensic_probability", "<f8")])
 assert FORENSIC_DTYPE.itemsize == _lib.FORENSIC_BYTES and RECORD_DTYPE.itemsize == _lib.RECORD_BYTES
@@ -143,13 +144,21 @@ class Engine:
         return prob
 
     # -- vote -------------------------------------------------------------------------
-    def vote_update(self, stream_ids, vote_input):
+    def vote_update(self, stream_ids, vote_input, np_flags=None):
         sid = self._dev(stream_ids, torch.int32)
         vi = self._dev(vote_input, torch.float64)
+        fl = self._dev(np_flags, torch.uint8) if np_flags is not None else None
         n = sid.shape[0]
         rec = torch.empty(n * _lib.RECORD_BYTES, dtype=torch.uint8, device=self.device)
-        self._check(self.lib.dfd_vote_update(self.h, _ptr(sid), _ptr(vi), n, _ptr(rec), self._stream()), "dfd_vote_update")
+        self._check(self.lib.dfd_vote_update(self.h, _ptr(sid), _ptr(vi), _ptr(fl), n, _ptr(rec), self._stream()),
+                    "dfd_vote_update")
         return rec
+
+    def gemm_selftest(self, M, N, K, act=1, with_residual=0):
+        err = C.c_double(-1.0)
+        self._check(self.lib.dfd_gemm_selftest(self.h, M, N, K, act, with_residual, C.byref(err), self._stream()),
+                    "dfd_gemm_selftest")
+        return err.value
 
     def analyze_batch(self, frames, stream_ids, full, boxes, box_frame, dtype="bf16", want_forensic=False,
                       records_out=None):
@@ -170,6 +179,10 @@ class Engine:
                                         self._stream())
         self._check(rc, "dfd_analyze_batch")
         return rec, fres, fprob[:m]
+
+    def configure_stream(self, stream_id, window_size=60, voting_window=10, detection_threshold=0.5):
+        self._check(self.lib.dfd_configure_stream(self.h, int(stream_id), int(window_size), int(voting_window),
+                                                  float(detection_threshold), self._stream()), "dfd_configure_stream")
 
     def reset(self, stream_id=-1):
         self._check(self.lib.dfd_reset_stream(self.h, int(stream_id), self._stream()), "dfd_reset_stream")
