@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/s end to end at 720p (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A step = one pass of the whole per-frame hot path (six forensic signals, face-crop preparation,
+EfficientNet-B0 bf16, sigmoid + heuristics, vote-input selection, 10-frame vote) over one 1280x720
+frame from each of S=256 streams on every GPU (weak scaling), one synthetic face box per frame,
+plus -- for N>1 -- the NCCL gather of the per-stream verdict records.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import dfd_b200  # noqa: E402
+from dfd_b200 import synth  # noqa: E402
+
+H, W = 720, 1280
+STREAMS = 256          # frames per step per GPU
+METRIC = "frames_per_sec_end_to_end_720p"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def make_inputs(n_streams, n_sets, seed):
+    """n_sets x n_streams synthetic 720p BGR frames in pinned host memory + one face box per frame."""
+    rng = np.random.RandomState(seed)
+    bases = []
+    for fam in synth.FAMILIES:
+        for _ in range(2):
+            bases.append(synth.make_frame(fam, H, W, rng))
+    frames = torch.empty((n_sets, n_streams, H, W, 3), dtype=torch.uint8)
+    if torch.cuda.is_available():
+        frames = frames.pin_memory()
+    fn = frames.numpy()
+    for s in range(n_streams):
+        b = np.roll(bases[s % len(bases)], ((s * 7) % 64, (s * 13) % 64), axis=(0, 1))
+        fn[0, s] = b
+        for k in range(1, n_sets):   # next frame of the stream: small temporal jitter
+            jit = rng.randint(-2, 3, size=(H, W, 1)).astype(np.int16)
+            fn[k, s] = np.clip(b.astype(np.int16) + jit, 0, 255).astype(np.uint8)
+    boxes = np.stack([synth.make_boxes(n_streams, H, W, rng, lo=96, hi=400) for _ in range(n_sets)])
+    return frames, boxes
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_pipeline(frames, boxes, sd, n_threads):
+    """The reference's CPU path (oracle port) over frames[t][s]: returns frames processed."""
+    import cv2
+    from oracle import effnet as oeff, faceprep as ofp, forensics as ofor, tracker as otr
+    torch.set_num_threads(n_threads)
+    cv2.setNumThreads(n_threads)
+    n_sets, n_streams = frames.shape[0], frames.shape[1]
+    analyzers = [ofor.OracleForensicAnalyzer() for _ in range(n_streams)]
+    trackers = [otr.OracleTemporalTracker(detection_threshold=0.55) for _ in range(n_streams)]
+    done = 0
+    for t in range(n_sets):
+        for s in range(n_streams):
+            f = frames[t, s]
+            r = analyzers[s].analyze(f) if t % 3 == 0 else analyzers[s].analyze_fast(f)
+            x = ofp.prepare(f, boxes[t, s])
+            p = float(torch.sigmoid(oeff.forward(x, sd)).item())
+            p = float(ofp.heuristics(p, boxes[t, s][3], boxes[t, s][2]))
+            trackers[s].update(p)
+            done += 1
+    return done
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference's
+    third-party CNN package is not installable here), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 8                                      # frames per step
+    sd = synth.make_state_dict()
+    frames, boxes = make_inputs(sample, 3, seed=1234)
+    fn = frames.numpy()
+    for _ in range(args.warmup):
+        cpu_pipeline(fn[:1], boxes[:1], sd, cores)
+    t0 = time.perf_counter()
+    n = 0
+    for k in range(args.steps):
+        n += cpu_pipeline(fn[k % 3:k % 3 + 1], boxes[k % 3:k % 3 + 1], sd, cores)
+    dt = time.perf_counter() - t0
+    v = n / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"720p full per-frame path on CPU, {sample} frames/step, 1 face/frame, fp32 bs=1"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} frames/step x {args.steps} steps of the bench workload"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from dfd_b200 import roofline
+    from dfd_b200.engine import Engine, RECORD_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    S = args.streams
+    K, Wm = args.steps, max(args.warmup, 3)
+    n_sets = 3
+
+    sd = synth.make_state_dict()
+    eng = Engine(device=local, max_streams=S, max_batch=S, max_crop=512, detection_threshold=0.55)
+    eng.load_state_dict(sd)
+    host_frames, boxes = make_inputs(S, n_sets, seed=1234 + rank)
+    dev_frames = host_frames.to(dev)                              # resident inputs for `value`
+    dev_boxes = [torch.from_numpy(boxes[k]).to(dev) for k in range(n_sets)]
+    sids = torch.arange(S, dtype=torch.int32, device=dev)
+    box_frame = torch.arange(S, dtype=torch.int32, device=dev)
+    full_flags = [torch.full((S,), int(k == 0), dtype=torch.uint8, device=dev) for k in range(3)]
+    rec = torch.empty(S * RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * S * RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev) if world > 1 else None
+    rec_host = torch.empty(S * RECORD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # L2 flush buffer (> 126 MB)
+
+    def step(i, frames_dev):
+        eng.analyze_batch(frames_dev, sids, full_flags[i % 3], dev_boxes[i % n_sets], box_frame, dtype=args.dtype,
+                          records_out=rec)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec)              # NCCL verdict gather (config 4)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ----
+    for i in range(Wm):
+        step(i, dev_frames[i % n_sets])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        step(Wm + i, dev_frames[(Wm + i) % n_sets])               # 707 MB of frames per step >> 126 MB L2
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * S * K / (ms / 1e3)
+
+    # ---- end to end through the public call: pinned host frames -> H2D -> path -> D2H records ----
+    copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    stage = [torch.empty_like(dev_frames[0]) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def e2e_loop(n, base):
+        for i in range(n):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(consumed[b])
+                stage[b].copy_(host_frames[(base + i) % n_sets], non_blocking=True)
+                copied[b].record(copy_stream)
+            with torch.cuda.stream(comp_stream):
+                comp_stream.wait_event(copied[b])
+                step(base + i, stage[b])
+                consumed[b].record(comp_stream)
+                rec_host.copy_(rec, non_blocking=True)
+        comp_stream.synchronize()
+
+    e2e_loop(3, 0)
+    barrier()
+    with torch.cuda.stream(copy_stream):
+        e0.record(copy_stream)
+    e2e_loop(K, 3)
+    with torch.cuda.stream(comp_stream):
+        e1.record(comp_stream)
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * K / (float(ms_e2e.item()) / 1e3)
+    h2d = S * H * W * 3
+    d2h = S * RECORD_DTYPE.itemsize
+
+    # ---- per-kernel device times (3 extra steps, one event after every launch) -> roofline ----
+    roof, kernels = None, []
+    if rank == 0:
+        torch.cuda.synchronize()
+        eng.profile_start()
+        for i in range(3):
+            flush.zero_()
+            eng.analyze_batch(dev_frames[i % n_sets], sids, full_flags[i % 3], dev_boxes[i % n_sets], box_frame,
+                              dtype=args.dtype, records_out=rec)
+        prof = eng.profile_stop()
+        hbm, tf, how = peaks()
+        area = float(np.mean(boxes[:, :, 2] * boxes[:, :, 3]))
+        total_ms = sum(p[2] for p in prof)
+        esz = 2 if args.dtype == "bf16" else 4
+        for name, cnt, tms in prof:
+            by = roofline.kernel_bytes(name, S, H, W, S, area, esz)
+            per = tms / cnt
+            kernels.append({"kernel": name, "launches": cnt, "ms_per_launch": round(per, 4),
+                            "share": round(tms / total_ms, 4),
+                            "gbs": round(by / per / 1e6, 1) if by else None})
+        kernels.sort(key=lambda k: -k["share"])
+        top = next(k for k in kernels if k["gbs"] is not None)
+        by = roofline.kernel_bytes(top["kernel"], S, H, W, S, area, esz)
+        roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": round(top["gbs"] / hbm, 4), "traffic": None, "peak_source": how,
+                "algorithmic_bytes_per_launch": by, "share_of_step": top["share"]}
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "bench_kernels.json"), "w") as f:
+                json.dump({"dtype": args.dtype, "streams": S, "kernels": kernels, "peak_gbs": hbm}, f, indent=1)
+        except OSError:
+            pass
+
+    # ---- CPU baseline (rank 0, N=1): the oracle port on a bounded sample of the same workload ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = 48
+        fn = host_frames.numpy()[:, :n_sample // 3]
+        t0 = time.perf_counter()
+        n = cpu_pipeline(fn, boxes[:, :n_sample // 3], sd, cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} frames (3 consecutive frames of {n_sample // 3} streams) of the bench workload, fp32 bs=1"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"720p full per-frame path (6 forensic signals + face prep + EfficientNet-B0 "
+                                   f"{args.dtype} + vote), {S} streams/GPU, 1 face box/frame, full/fast/fast cadence",
+                       "frames_per_step_per_gpu": S, "frame": "1280x720 BGR u8", "l2": "inputs larger than L2 "
+                       "(707 MB of frames per step, 3 rotating sets)", "weights": "fixed-seed random init (synth.make_state_dict)",
+                       "collective": "nccl all_gather of 72-B verdict records" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(ms_e2e.item()) / K, "note": "pinned host frames, H2D double-buffered on a copy stream"},
+            "gpu_launches": int(launches), "crops_per_sec": value, "clocks": clocks, "roofline": roof,
+            "cpu_baseline": cpu, "top_kernels": kernels[:6],
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,11 @@ int dfd_configure_stream(dfd_ctx* ctx, int stream_id, int window_size, int votin
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t dfd_launch_count(dfd_ctx* ctx);
 
+/* Per-kernel device timing for bench.py's roofline: between start and stop an event is recorded after
+ * every launch; stop writes "kernel:label,launches,total_ms" lines into buf (HOST). */
+int dfd_profile_start(dfd_ctx* ctx, void* stream);
+int dfd_profile_stop(dfd_ctx* ctx, char* buf_host, size_t buf_bytes, void* stream);
+
 /* ---- diagnostics used by the parity tests (stage outputs) ------------------------------------------ */
 /* tile (n x 256 x 256 x 3 BGR u8) and gray (n x 256 x 256 u8) of the last dfd_forensics_batch call. */
 int dfd_dbg_tiles(dfd_ctx* ctx, uint8_t* tile_out, uint8_t* gray_out, int n, void* stream);

@@ -53,6 +53,8 @@ SYMBOLS = {
     "dfd_reset_stream": (_I, [_P, _I, _P]),
     "dfd_configure_stream": (_I, [_P, _I, _I, _I, C.c_double, _P]),
     "dfd_launch_count": (C.c_int64, [_P]),
+    "dfd_profile_start": (_I, [_P, _P]),
+    "dfd_profile_stop": (_I, [_P, C.c_char_p, _S, _P]),
     "dfd_dbg_tiles": (_I, [_P, _P, _P, _I, _P]),
     "dfd_dbg_jpeg_roundtrip": (_I, [_P, _P, _P, _I, _P]),
     "dfd_dbg_canny": (_I, [_P, _P, _P, _I, _P]),

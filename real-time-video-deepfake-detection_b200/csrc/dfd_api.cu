@@ -20,7 +20,59 @@ int dfd_ensure(dfd_ctx* ctx, DfdBuf& b, size_t bytes) {
     return DFD_OK;
 }
 
+void dfd_prof_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st) {
+    if (ctx->prof_used >= ctx->prof_events.size()) return;
+    cudaEventRecord(ctx->prof_events[ctx->prof_used], st);
+    ctx->prof_labels[ctx->prof_used] = std::string(kernel) + (ctx->label[0] ? std::string(":") + ctx->label : std::string());
+    ctx->prof_used++;
+}
+
 extern "C" {
+
+int dfd_profile_start(dfd_ctx* ctx, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    const size_t cap = 8192;
+    if (ctx->prof_events.empty()) {
+        ctx->prof_events.resize(cap);
+        ctx->prof_labels.resize(cap);
+        for (size_t i = 0; i < cap; i++) DFD_CUDA(cudaEventCreate(&ctx->prof_events[i]));
+    }
+    ctx->prof_used = 0;
+    ctx->label = "";
+    ctx->profiling = true;
+    dfd_prof_mark(ctx, "begin", (cudaStream_t)stream);
+    return DFD_OK;
+}
+
+// Stops profiling and writes "kernel:label,launches,total_ms" lines (sorted by first appearance) into buf.
+int dfd_profile_stop(dfd_ctx* ctx, char* buf, size_t buf_bytes, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    ctx->profiling = false;
+    DFD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    std::vector<std::string> order;
+    std::vector<double> ms;
+    std::vector<int> cnt;
+    for (size_t i = 1; i < ctx->prof_used; i++) {
+        float t = 0.f;
+        DFD_CUDA(cudaEventElapsedTime(&t, ctx->prof_events[i - 1], ctx->prof_events[i]));
+        size_t k = 0;
+        for (; k < order.size(); k++) if (order[k] == ctx->prof_labels[i]) break;
+        if (k == order.size()) { order.push_back(ctx->prof_labels[i]); ms.push_back(0); cnt.push_back(0); }
+        ms[k] += t; cnt[k]++;
+    }
+    std::string out;
+    for (size_t k = 0; k < order.size(); k++) {
+        char line[256];
+        snprintf(line, sizeof line, "%s,%d,%.6f\n", order[k].c_str(), cnt[k], ms[k]);
+        out += line;
+    }
+    if (buf && buf_bytes) {
+        size_t n = out.size() < buf_bytes - 1 ? out.size() : buf_bytes - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return DFD_OK;
+}
 
 void dfd_default_config(dfd_config* c) {
     memset(c, 0, sizeof(*c));

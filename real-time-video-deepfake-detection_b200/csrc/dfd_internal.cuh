@@ -92,7 +92,15 @@ struct dfd_ctx {
     DfdBuf tap;
     int64_t tap_elems = 0;
     void* tmaps = nullptr;                // host-side cache of TMA descriptors (effnet_bf16.cu)
+    // per-launch profiling (bench.py roofline): an event after every launch, labelled
+    bool profiling = false;
+    const char* label = "";               // set by the launch code before each kernel
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<std::string> prof_labels;
+    size_t prof_used = 0;
 };
+
+void dfd_prof_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st);
 
 #define DFD_CUDA(call)                                                                      \
     do {                                                                                    \
@@ -103,9 +111,10 @@ struct dfd_ctx {
         }                                                                                   \
     } while (0)
 
-#define DFD_LAUNCH_CHECK()                                                                  \
+#define DFD_LAUNCH_CHECK(kname, st_)                                                        \
     do {                                                                                    \
         ctx->launches++;                                                                    \
+        if (ctx->profiling) dfd_prof_mark(ctx, kname, st_);                                 \
         cudaError_t e_ = cudaPeekAtLastError();                                             \
         if (e_ != cudaSuccess) {                                                            \
             ctx->err = std::string("kernel launch at ") + __FILE__ + ":" + std::to_string(__LINE__) + ": " + \

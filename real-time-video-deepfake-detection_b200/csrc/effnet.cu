@@ -324,7 +324,7 @@ static int tap(dfd_ctx* ctx, const char* name, const T* x, size_t n, cudaStream_
     int rc = dfd_ensure(ctx, ctx->tap, n * sizeof(float));
     if (rc) return rc;
     k_to_f32<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (float*)ctx->tap.p, n);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_to_f32", st);
     ctx->tap_elems = (int64_t)n;
     return DFD_OK;
 }
@@ -347,7 +347,7 @@ static int launch_dw(dfd_ctx* ctx, const EffBlock& b, const T* in, const float* 
                                                          b.s, b.pad, ppb)
     if (b.k == 3) DW_CASE(3); else DW_CASE(5);
 #undef DW_CASE
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_dw", st);
     return DFD_OK;
 }
 
@@ -370,10 +370,15 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
     T* e = (T*)ctx->act[2].p;
     DFD_CUDA(cudaMemsetAsync(ctx->d_pool, 0, (size_t)m * 1152 * sizeof(float), st));
 
+    static const char* L_EXP[16] = {"b0.expand", "b1.expand", "b2.expand", "b3.expand", "b4.expand", "b5.expand", "b6.expand", "b7.expand", "b8.expand", "b9.expand", "b10.expand", "b11.expand", "b12.expand", "b13.expand", "b14.expand", "b15.expand"};
+    static const char* L_DW[16] = {"b0.dw", "b1.dw", "b2.dw", "b3.dw", "b4.dw", "b5.dw", "b6.dw", "b7.dw", "b8.dw", "b9.dw", "b10.dw", "b11.dw", "b12.dw", "b13.dw", "b14.dw", "b15.dw"};
+    static const char* L_SE[16] = {"b0.se", "b1.se", "b2.se", "b3.se", "b4.se", "b5.se", "b6.se", "b7.se", "b8.se", "b9.se", "b10.se", "b11.se", "b12.se", "b13.se", "b14.se", "b15.se"};
+    static const char* L_PROJ[16] = {"b0.project", "b1.project", "b2.project", "b3.project", "b4.project", "b5.project", "b6.project", "b7.project", "b8.project", "b9.project", "b10.project", "b11.project", "b12.project", "b13.project", "b14.project", "b15.project"};
+    ctx->label = "stem";
     {
         int total = m * 112 * 112;
         k_stem<T><<<(total + 127) / 128, 128, 0, st>>>(in, Wf + o.stem_w, Wf + o.stem_b, x, total);
-        DFD_LAUNCH_CHECK();
+        DFD_LAUNCH_CHECK("k_stem", st);
         if ((rc = tap<T>(ctx, "stem", x, (size_t)total * 32, st))) return rc;
     }
     auto pw = [&](const T* A, size_t w_off, size_t b_off, const float* se, int hw, const T* res, T* C, int M, int N, int K,
@@ -383,7 +388,7 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
                                  (__nv_bfloat16*)C, M, N, K, act, st);
         }
         k_pw<T><<<dim3((M + 63) / 64, (N + 63) / 64), 256, 0, st>>>(A, Wf + w_off, Wf + b_off, se, hw, res, C, M, N, K, act);
-        DFD_LAUNCH_CHECK();
+        DFD_LAUNCH_CHECK("k_pw", st);
         return DFD_OK;
     };
     char nm[32];
@@ -394,6 +399,7 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         const T* dw_in = x;
         T* dw_out;
         if (b.cexp != b.cin) {
+            ctx->label = L_EXP[i];
             if ((rc = pw(x, f.we, f.be, nullptr, 0, nullptr, e, Min, b.cexp, b.cin, 1))) return rc;
             snprintf(nm, sizeof nm, "b%d.expand", i);
             if ((rc = tap<T>(ctx, nm, e, (size_t)Min * b.cexp, st))) return rc;
@@ -405,21 +411,24 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             size_t need = ((size_t)Min + Mout) * b.cexp * sizeof(T);
             if (need > ctx->act[2].bytes) { ctx->err = "internal: expanded buffer too small"; return DFD_ERR_CAPACITY; }
         } else dw_out = y;
+        ctx->label = L_DW[i];
         if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, st))) return rc;
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
+        ctx->label = L_SE[i];
         k_se<<<m, 256, 0, st>>>(ctx->d_pool, Wf + f.wr, Wf + f.br, Wf + f.wx, Wf + f.bx, ctx->d_sescale, b.cexp, b.se,
                                 1.0f / (float)(b.hout * b.hout));
-        DFD_LAUNCH_CHECK();
+        DFD_LAUNCH_CHECK("k_se", st);
         const bool skip = b.s == 1 && b.cin == b.cout;
         T* outp = (dw_out == y) ? x : y;       // block 0 wrote dw into y; its project output goes to x (input is dead, no skip)
         const float* se_arg = ctx->d_sescale;
         if (tc) {
             size_t tv = (size_t)Mout * b.cexp / 8;
             k_scale<<<(unsigned)((tv + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)dw_out, ctx->d_sescale, b.cexp, b.hout * b.hout, tv);
-            DFD_LAUNCH_CHECK();
+            DFD_LAUNCH_CHECK("k_scale", st);
             se_arg = nullptr;
         }
+        ctx->label = L_PROJ[i];
         if ((rc = pw(dw_out, f.wp, f.bp, se_arg, b.hout * b.hout, skip ? x : nullptr, outp, Mout, b.cout, b.cexp, 0))) return rc;
         snprintf(nm, sizeof nm, "b%d.out", i);
         if ((rc = tap<T>(ctx, nm, outp, (size_t)Mout * b.cout, st))) return rc;
@@ -428,15 +437,19 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
     // head 1x1 320->1280 + swish, global average pool, classifier
     {
         const int M = m * 49;
+        ctx->label = "head";
         if ((rc = pw(x, o.head_w, o.head_b, nullptr, 0, nullptr, e, M, 1280, 320, 1))) return rc;
+        ctx->label = "pool";
         k_pool<T><<<dim3(1280 / 128, m), 128, 0, st>>>(e, ctx->d_feat, 49, 1280);
-        DFD_LAUNCH_CHECK();
+        DFD_LAUNCH_CHECK("k_pool", st);
         if (!ctx->tap_name.empty() && ctx->tap_name == "features") {
             if ((rc = tap<float>(ctx, "features", ctx->d_feat, (size_t)m * 1280, st))) return rc;
         }
+        ctx->label = "fc";
         k_fc<<<m, 512, 0, st>>>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, Wf + o.fc2_w, Wf + o.fc2_b, Wf + o.fc3_w, Wf + o.fc3_b,
                                 logits);
-        DFD_LAUNCH_CHECK();
+        DFD_LAUNCH_CHECK("k_fc", st);
+        ctx->label = "";
     }
     return DFD_OK;
 }

@@ -150,18 +150,18 @@ int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H
     DFD_REQUIRE(dtype == DFD_F32 || dtype == DFD_BF16, DFD_ERR_INVALID, "face_prep: bad dtype");
     const int mc = ctx->cfg.max_crop;
     k_pil_coeffs<<<m, 320, 0, st>>>(boxes, ctx->d_pil);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_pil_coeffs", st);
     k_clahe_lut<<<dim3(64, m), 256, 0, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables, ctx->d_luts);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_clahe_lut", st);
     k_clahe_hpass<<<dim3(mc, m), 256, mc * 3, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables,
                                                     ctx->d_luts, ctx->d_pil, ctx->d_hpass, mc, nullptr, -1);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_clahe_hpass", st);
     if (dtype == DFD_F32)
         k_vpass_up_norm<float><<<dim3(4, m), 512, 0, st>>>(boxes, ctx->d_pil, ctx->d_hpass, mc, ctx->d_face160, (float*)out);
     else
         k_vpass_up_norm<__nv_bfloat16><<<dim3(4, m), 512, 0, st>>>(boxes, ctx->d_pil, ctx->d_hpass, mc, ctx->d_face160,
                                                                    (__nv_bfloat16*)out);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_vpass_up_norm", st);
     return DFD_OK;
 }
 
@@ -171,6 +171,6 @@ int dfd_dbg_clahe_launch(dfd_ctx* ctx, const uint8_t* frames, size_t frame_strid
     const int mc = ctx->cfg.max_crop;
     k_clahe_hpass<<<dim3(mc, i + 1), 256, mc * 3, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables,
                                                        ctx->d_luts, ctx->d_pil, nullptr, mc, out, i);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_clahe_hpass", st);
     return DFD_OK;
 }

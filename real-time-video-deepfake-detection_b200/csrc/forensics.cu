@@ -511,20 +511,20 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
     DFD_REQUIRE(n > 0 && n <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "forensics: batch exceeds max_batch");
     DFD_REQUIRE(H >= 1 && W >= 1 && row_pitch >= 3 * W, DFD_ERR_INVALID, "forensics: bad frame geometry");
     k_resize256<<<dim3(T, n), 256, 0, st>>>(frames, H, W, frame_stride, row_pitch, ctx->d_tile, ctx->d_gray);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_resize256", st);
     k_tile_stats<<<dim3(DFD_NBLK, n), 256, 0, st>>>(ctx->d_tile, ctx->d_gray, stream_ids, full, ctx->d_tables, ctx->d_state,
                                                      ctx->d_prev_gray, ctx->d_part);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_tile_stats", st);
     k_canny<<<n, 1024, T * T + 2 * 2048 * 4, st>>>(ctx->d_gray, &ctx->d_part[0].canny_count, sizeof(DfdFramePartials), nullptr);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_canny", st);
     k_ela<<<n, 512, T * T + 2 * 128 * 128, st>>>(ctx->d_tile, full, ctx->d_part, nullptr);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_ela", st);
     k_fft_rows<<<dim3(16, n), 1024, 0, st>>>(ctx->d_gray, ctx->d_twiddle, ctx->d_fft);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_fft_rows", st);
     k_fft_cols<<<dim3(DFD_FFT_GROUPS, n), 1024, 0, st>>>(ctx->d_fft, ctx->d_twiddle, ctx->d_part);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_fft_cols", st);
     k_finalize<<<(n + 63) / 64, 64, 0, st>>>(n, stream_ids, full, ctx->d_part, ctx->d_state, results);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_finalize", st);
     return DFD_OK;
 }
 
@@ -536,12 +536,12 @@ int dfd_forensics_init(dfd_ctx* ctx) {
 
 int dfd_dbg_jpeg_launch(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n, cudaStream_t st) {
     k_ela<<<n, 512, T * T + 2 * 128 * 128, st>>>(tiles, nullptr, nullptr, out);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_ela", st);
     return DFD_OK;
 }
 
 int dfd_dbg_canny_launch(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, cudaStream_t st) {
     k_canny<<<n, 1024, T * T + 2 * 2048 * 4, st>>>(gray, nullptr, 0, edges);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_canny", st);
     return DFD_OK;
 }

@@ -300,7 +300,7 @@ int dfd_gemm_bf16(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16* W, 
     if ((rc = make_map(ctx, &mb, W, (uint64_t)N, (uint64_t)K, (uint32_t)n_pad))) return rc;
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
     k_gemm_tcgen05<<<grid, GEMM_THREADS, smem, st>>>(ma, mb, p);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);
     return DFD_OK;
 }
 

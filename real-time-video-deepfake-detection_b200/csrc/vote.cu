@@ -159,14 +159,14 @@ static VoteCfg make_cfg(const dfd_ctx* ctx) {
 
 int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, cudaStream_t st) {
     k_faceprob<<<(m + 127) / 128, 128, 0, st>>>(m, logits, boxes, prob);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_faceprob", st);
     return DFD_OK;
 }
 
 int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
                     dfd_vote_record* rec, cudaStream_t st) {
     k_vote<<<(n + 63) / 64, 64, 0, st>>>(n, stream_ids, vote_input, np_flags, ctx->d_state, make_cfg(ctx), rec);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_vote", st);
     return DFD_OK;
 }
 
@@ -174,20 +174,20 @@ int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame,
                            const dfd_forensic_result* fres, const int32_t* stream_ids, dfd_vote_record* rec,
                            cudaStream_t st) {
     k_select_vote<<<(n + 63) / 64, 64, 0, st>>>(n, m, box_frame, face_prob, fres, stream_ids, ctx->d_state, make_cfg(ctx), rec);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_select_vote", st);
     return DFD_OK;
 }
 
 int dfd_reset_launch(dfd_ctx* ctx, int stream_id, cudaStream_t st) {
     int first = stream_id < 0 ? 0 : stream_id, count = stream_id < 0 ? ctx->cfg.max_streams : 1;
     k_reset<<<(count + 127) / 128, 128, 0, st>>>(ctx->d_state, first, count, 3, 0, 0, 0, 0.0);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_reset", st);
     return DFD_OK;
 }
 
 int dfd_configure_launch(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double thr, cudaStream_t st) {
     int first = stream_id < 0 ? 0 : stream_id, count = stream_id < 0 ? ctx->cfg.max_streams : 1;
     k_reset<<<(count + 127) / 128, 128, 0, st>>>(ctx->d_state, first, count, 2, 1, window_size, voting_window, thr);
-    DFD_LAUNCH_CHECK();
+    DFD_LAUNCH_CHECK("k_reset", st);
     return DFD_OK;
 }

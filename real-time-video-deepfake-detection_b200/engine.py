@@ -187,6 +187,20 @@ class Engine:
     def reset(self, stream_id=-1):
         self._check(self.lib.dfd_reset_stream(self.h, int(stream_id), self._stream()), "dfd_reset_stream")
 
+    # -- per-kernel timing ------------------------------------------------------------
+    def profile_start(self):
+        self._check(self.lib.dfd_profile_start(self.h, self._stream()), "dfd_profile_start")
+
+    def profile_stop(self):
+        """-> [(kernel:label, launches, total_ms)] in order of first appearance."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.dfd_profile_stop(self.h, buf, len(buf), self._stream()), "dfd_profile_stop")
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(",", 2)
+            out.append((name, int(cnt), float(ms)))
+        return out
+
     # -- diagnostics ------------------------------------------------------------------
     def dbg_tiles(self, n):
         tile = torch.empty((n, 256, 256, 3), dtype=torch.uint8, device=self.device)
