@@ -152,7 +152,7 @@ void dfd_destroy(dfd_ctx* ctx) {
     if (!ctx) return;
     void* ptrs[] = {ctx->d_tables, ctx->d_twiddle, ctx->d_state, ctx->d_prev_gray, ctx->d_tile, ctx->d_gray, ctx->d_fft,
                     ctx->d_part, ctx->d_fres, ctx->d_luts, ctx->d_pil, ctx->d_hpass, ctx->d_face160, ctx->d_wf32,
-                    ctx->d_wbf16, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
+                    ctx->d_wbf16, ctx->d_stem_wg, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
                     ctx->d_sescale, ctx->d_feat, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
     for (void* p : ptrs) if (p) cudaFree(p);
     dfd_gemm_free(ctx);

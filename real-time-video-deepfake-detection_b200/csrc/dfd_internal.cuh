@@ -79,6 +79,7 @@ struct dfd_ctx {
     float* d_wf32 = nullptr;              // packed folded fp32 parameters
     size_t w_floats = 0;
     __nv_bfloat16* d_wbf16 = nullptr;     // bf16 copies of the GEMM weights (same offsets)
+    __nv_bfloat16* d_stem_wg = nullptr;   // stem weights as a [32][32] K-major GEMM operand (27 taps + zero pad)
     DfdBuf act[3];                        // activation ping-pong + expanded buffer
     DfdBuf face_in;                       // prepared crops for analyze_batch
     float* d_pool = nullptr;              // [m][1152] SE squeeze sums

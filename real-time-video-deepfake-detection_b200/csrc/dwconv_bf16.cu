@@ -1,0 +1,146 @@
+// Depthwise kxk convolution + folded BN + swish + fused SE squeeze for bf16 NHWC activations
+// (the _depthwise_conv/_bn1/swish/avg-pool stage of every MBConv block).
+//
+// HBM-bound stage (12.2 MB/img of the 27.4 MB/img layer-granular traffic).  One CTA owns an output tile of
+// TH x TW pixels x 64 channels of one image:
+//   1. the (TH-1)*S+K by (TW-1)*S+K input patch is staged in shared memory with 16-byte cp.async
+//      (zero-fill outside the image = TF-SAME padding, and beyond C for ragged channel chunks);
+//      a pixel's 64 channels are one 128-byte row, so every later warp access is conflict-free;
+//   2. lane = channel pair, warp = output row: the warp slides along its row keeping TW fp32
+//      accumulator pairs in registers, so each staged input word is read once per kernel row
+//      and reused for up to K outputs;
+//   3. swish, bf16 pack, 128-byte coalesced stores; per-channel sums of the swish outputs (the SE
+//      squeeze) are reduced in shared memory and leave the CTA as 64 atomics.
+#include "dfd_internal.cuh"
+#include "effnet_plan.h"
+
+#define DW_CC 64                 // channels per CTA
+#define DW_WARPS 8
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ float dw_swish(float x) {
+    // x * sigmoid(x) = h + h*tanh(h), h = x/2 : one MUFU op
+    float h = 0.5f * x, t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+template <int K, int S, int TW, int TH>
+__global__ void __launch_bounds__(DW_WARPS * 32)
+k_dw_tile(const __nv_bfloat16* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+          __nv_bfloat16* __restrict__ out, float* __restrict__ pool, int C, int hin, int hout, int pad, int tiles_x) {
+    constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
+    extern __shared__ __align__(16) uint32_t smem_dw[];
+    uint32_t* patch = smem_dw;                               // [PH][PW][32] bf16x2
+    float* sw = (float*)(patch + PH * PW * 32);              // [K*K][64]
+    float* spool = sw + K * K * DW_CC;                       // [64]
+    const int tile = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
+    const int ty = tile / tiles_x, tx = tile % tiles_x;
+    const int oy0 = ty * TH, ox0 = tx * TW;
+    const int c0 = chunk * DW_CC;
+    const int iy0 = oy0 * S - pad, ix0 = ox0 * S - pad;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- stage the input patch (16-byte chunks; 8 chunks per pixel) ----
+    const uint32_t patch_s = (uint32_t)__cvta_generic_to_shared(patch);
+    const __nv_bfloat16* img = in + (size_t)b * hin * hin * C;
+    for (int idx = tid; idx < PH * PW * 8; idx += DW_WARPS * 32) {
+        const int pix = idx >> 3, part = idx & 7;
+        const int py = pix / PW, px = pix - py * PW;
+        const int iy = iy0 + py, ix = ix0 + px, c = c0 + part * 8;
+        const bool ok = iy >= 0 && iy < hin && ix >= 0 && ix < hin && c < C;
+        const __nv_bfloat16* src = ok ? img + ((size_t)iy * hin + ix) * C + c : in;
+        cp_async16(patch_s + (uint32_t)(pix * 128 + part * 16), src, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < K * K * DW_CC; i += DW_WARPS * 32) {
+        const int c = c0 + (i & 63);
+        sw[i] = c < C ? W[(size_t)(i >> 6) * C + c] : 0.f;
+    }
+    if (tid < DW_CC) spool[tid] = 0.f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int ch = c0 + 2 * lane;
+    const bool ch_ok = ch < C;                               // C is even: a pair is valid or not as a whole
+    const float b0 = ch_ok ? bias[ch] : 0.f, b1 = ch_ok ? bias[ch + 1] : 0.f;
+    float ps0 = 0.f, ps1 = 0.f;
+    for (int r = warp; r < TH; r += DW_WARPS) {
+        const int oy = oy0 + r;
+        if (oy >= hout) break;
+        float a0[TW], a1[TW];
+#pragma unroll
+        for (int i = 0; i < TW; i++) { a0[i] = b0; a1[i] = b1; }
+#pragma unroll
+        for (int ky = 0; ky < K; ky++) {
+            float w0[K], w1[K];
+#pragma unroll
+            for (int kx = 0; kx < K; kx++) {
+                const float2 w = *(const float2*)(sw + (ky * K + kx) * DW_CC + 2 * lane);
+                w0[kx] = w.x; w1[kx] = w.y;
+            }
+            const uint32_t* prow = patch + (size_t)((r * S + ky) * PW) * 32 + lane;
+#pragma unroll
+            for (int ix = 0; ix < PW; ix++) {
+                const uint32_t v = prow[ix * 32];
+                const float x0 = __uint_as_float(v << 16), x1 = __uint_as_float(v & 0xffff0000u);
+#pragma unroll
+                for (int kx = 0; kx < K; kx++) {
+                    if ((ix - kx) % S == 0 && (ix - kx) >= 0 && (ix - kx) / S < TW) {
+                        a0[(ix - kx) / S] = fmaf(x0, w0[kx], a0[(ix - kx) / S]);
+                        a1[(ix - kx) / S] = fmaf(x1, w1[kx], a1[(ix - kx) / S]);
+                    }
+                }
+            }
+        }
+        __nv_bfloat16* orow = out + (((size_t)b * hout + oy) * hout + ox0) * C + ch;
+#pragma unroll
+        for (int i = 0; i < TW; i++) {
+            if (ox0 + i < hout && ch_ok) {
+                const float y0 = dw_swish(a0[i]), y1 = dw_swish(a1[i]);
+                ps0 += y0; ps1 += y1;
+                *(__nv_bfloat162*)(orow + (size_t)i * C) = __floats2bfloat162_rn(y0, y1);
+            }
+        }
+    }
+    if (ch_ok) { atomicAdd(&spool[2 * lane], ps0); atomicAdd(&spool[2 * lane + 1], ps1); }
+    __syncthreads();
+    if (tid < DW_CC && c0 + tid < C) atomicAdd(pool + (size_t)b * C + c0 + tid, spool[tid]);
+}
+
+template <int K, int S, int TW, int TH>
+static int launch(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
+                  __nv_bfloat16* out, int m, cudaStream_t st) {
+    constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
+    const size_t smem = (size_t)PH * PW * 128 + (size_t)K * K * DW_CC * 4 + DW_CC * 4;
+    static bool attr = false;
+    if (!attr) {
+        DFD_CUDA(cudaFuncSetAttribute(k_dw_tile<K, S, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    const int tiles_x = (b.hout + TW - 1) / TW, tiles_y = (b.hout + TH - 1) / TH;
+    dim3 grid(tiles_x * tiles_y, (b.cexp + DW_CC - 1) / DW_CC, m);
+    k_dw_tile<K, S, TW, TH><<<grid, DW_WARPS * 32, smem, st>>>(in, W, bias, out, ctx->d_pool, b.cexp, b.hin, b.hout, b.pad, tiles_x);
+    DFD_LAUNCH_CHECK("k_dw_tile", st);
+    return DFD_OK;
+}
+
+int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
+                __nv_bfloat16* out, int m, cudaStream_t st) {
+    // tile shapes per output size: 112 -> 8x16, 56 -> 8x14, 28 / 14 -> 7x14, 7 -> 7x7
+    if (b.k == 3 && b.s == 1 && b.hout == 112) return launch<3, 1, 16, 8>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 3 && b.s == 2 && b.hout == 56) return launch<3, 2, 14, 8>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 56) return launch<3, 1, 14, 8>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 5 && b.s == 2 && b.hout == 28) return launch<5, 2, 14, 7>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 28) return launch<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 3 && b.s == 2 && b.hout == 14) return launch<3, 2, 14, 7>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 14) return launch<3, 1, 14, 7>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 14) return launch<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 5 && b.s == 2 && b.hout == 7) return launch<5, 2, 7, 7>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 7) return launch<5, 1, 7, 7>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 7) return launch<3, 1, 7, 7>(ctx, b, in, W, bias, out, m, st);
+    ctx->err = "dw_bf16: no tile configuration for this layer";
+    return DFD_ERR_INVALID;
+}

@@ -16,10 +16,16 @@
 #include "dfd_internal.cuh"
 #include "effnet_plan.h"
 #include <string.h>
+#include <type_traits>
 
 int dfd_gemm_bf16(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
                   const __nv_bfloat16* residual, __nv_bfloat16* C, int M, int N, int K, int act, cudaStream_t st);
+int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const float* se, int hw, const __nv_bfloat16* W,
+                     const float* bias, const __nv_bfloat16* residual, __nv_bfloat16* C, int M, int N, int K, int act,
+                     cudaStream_t st);
 bool dfd_gemm_bf16_enabled();
+int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
+                __nv_bfloat16* out, int m, cudaStream_t st);
 
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
 template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
@@ -308,11 +314,16 @@ int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n) {
     if (!ctx->d_wf32) {
         DFD_CUDA(cudaMalloc(&ctx->d_wf32, o.total * sizeof(float)));
         DFD_CUDA(cudaMalloc(&ctx->d_wbf16, o.total * sizeof(__nv_bfloat16)));
+        DFD_CUDA(cudaMalloc(&ctx->d_stem_wg, 32 * 32 * sizeof(__nv_bfloat16)));
     }
     DFD_CUDA(cudaMemcpy(ctx->d_wf32, blob, o.total * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<__nv_bfloat16> h(o.total);
     for (size_t i = 0; i < o.total; i++) h[i] = __float2bfloat16_rn(blob[i]);
     DFD_CUDA(cudaMemcpy(ctx->d_wbf16, h.data(), o.total * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    std::vector<__nv_bfloat16> wg(32 * 32);
+    for (int n = 0; n < 32; n++)
+        for (int k = 0; k < 32; k++) wg[n * 32 + k] = __float2bfloat16_rn(k < 27 ? blob[o.stem_w + (size_t)k * 32 + n] : 0.f);
+    DFD_CUDA(cudaMemcpy(ctx->d_stem_wg, wg.data(), wg.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     ctx->w_floats = o.total;
     ctx->has_weights = true;
     return DFD_OK;
@@ -377,8 +388,13 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
     ctx->label = "stem";
     {
         int total = m * 112 * 112;
-        k_stem<T><<<(total + 127) / 128, 128, 0, st>>>(in, Wf + o.stem_w, Wf + o.stem_b, x, total);
-        DFD_LAUNCH_CHECK("k_stem", st);
+        if (tc) {
+            if ((rc = dfd_gemm_bf16_ex(ctx, 2, (const __nv_bfloat16*)in, nullptr, 0, ctx->d_stem_wg, Wf + o.stem_b, nullptr,
+                                       (__nv_bfloat16*)x, total, 32, 32, 1, st))) return rc;
+        } else {
+            k_stem<T><<<(total + 127) / 128, 128, 0, st>>>(in, Wf + o.stem_w, Wf + o.stem_b, x, total);
+            DFD_LAUNCH_CHECK("k_stem", st);
+        }
         if ((rc = tap<T>(ctx, "stem", x, (size_t)total * 32, st))) return rc;
     }
     auto pw = [&](const T* A, size_t w_off, size_t b_off, const float* se, int hw, const T* res, T* C, int M, int N, int K,
@@ -412,7 +428,11 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             if (need > ctx->act[2].bytes) { ctx->err = "internal: expanded buffer too small"; return DFD_ERR_CAPACITY; }
         } else dw_out = y;
         ctx->label = L_DW[i];
-        if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, st))) return rc;
+        if constexpr (BF) {
+            if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, st))) return rc;
+        } else {
+            if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, st))) return rc;
+        }
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
@@ -421,15 +441,14 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         DFD_LAUNCH_CHECK("k_se", st);
         const bool skip = b.s == 1 && b.cin == b.cout;
         T* outp = (dw_out == y) ? x : y;       // block 0 wrote dw into y; its project output goes to x (input is dead, no skip)
-        const float* se_arg = ctx->d_sescale;
-        if (tc) {
-            size_t tv = (size_t)Mout * b.cexp / 8;
-            k_scale<<<(unsigned)((tv + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)dw_out, ctx->d_sescale, b.cexp, b.hout * b.hout, tv);
-            DFD_LAUNCH_CHECK("k_scale", st);
-            se_arg = nullptr;
-        }
         ctx->label = L_PROJ[i];
-        if ((rc = pw(dw_out, f.wp, f.bp, se_arg, b.hout * b.hout, skip ? x : nullptr, outp, Mout, b.cout, b.cexp, 0))) return rc;
+        if (tc) {      // the SE gate is applied while the A tile is staged (A_SCALE)
+            if ((rc = dfd_gemm_bf16_ex(ctx, 1, (const __nv_bfloat16*)dw_out, ctx->d_sescale, b.hout * b.hout,
+                                       ctx->d_wbf16 + f.wp, Wf + f.bp, (const __nv_bfloat16*)(skip ? x : nullptr),
+                                       (__nv_bfloat16*)outp, Mout, b.cout, b.cexp, 0, st))) return rc;
+        } else {
+            if ((rc = pw(dw_out, f.wp, f.bp, ctx->d_sescale, b.hout * b.hout, skip ? x : nullptr, outp, Mout, b.cout, b.cexp, 0))) return rc;
+        }
         snprintf(nm, sizeof nm, "b%d.out", i);
         if ((rc = tap<T>(ctx, nm, outp, (size_t)Mout * b.cout, st))) return rc;
         if (outp == y) { T* t = x; x = y; y = t; }

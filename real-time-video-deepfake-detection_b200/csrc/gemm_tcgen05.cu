@@ -1,31 +1,45 @@
-// bf16 1x1-convolution GEMM on the 5th-generation tensor cores (sm_100a).
+// bf16 convolution-as-GEMM on the 5th-generation tensor cores (sm_100a).
 //
-//   C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ) (+ residual[M,N])        A, W, C, residual bf16; accumulate fp32
+//   C[M,N] = act( A'[M,K] . W[N,K]^T + bias[N] ) (+ residual[M,N])     A, W, C, residual bf16; accumulate fp32 in TMEM
 //
-// A is the NHWC activation matrix (M = batch*H*W rows, K = input channels, K-major) and W the
-// BN-folded weight matrix [N][K] (K-major) of an expand / project / head convolution of the
-// reference's EfficientNet-B0 (model.py:63-72; SURVEY.md Appendix A "GEMM view").
+// A is the NHWC activation matrix (M = batch*H*W rows, K-major) and W the BN-folded weight matrix [N][K]
+// (K-major) of a convolution of the reference's EfficientNet-B0 (model.py:63-72):
+//   A_TMA    expand / head 1x1 convs: A' = A, tiles fetched by TMA
+//   A_SCALE  project 1x1 convs: A' = A * se[image][k] -- the squeeze-excite gate is applied while the
+//            tile is staged, so the gated tensor never exists in HBM
+//   A_STEM   stem 3x3 stride-2 conv 3->32: A' = im2col rows (27 taps, zero padded to 32) gathered on the fly
 //
-// Design (one persistent CTA per SM, warp-specialised, no cluster):
-//   warp 0  TMA producer: cp.async.bulk.tensor 2D loads of a 128 x 64 A tile and an N x 64 W tile
-//           (SWIZZLE_128B; out-of-bounds rows/columns are zero-filled by TMA, so ragged M, K=16..1152
-//           and N=16..256 need no padding copies) into a multi-stage smem ring, mbarrier complete_tx.
-//   warp 1  MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N, K=16)
-//           per 16-wide K step from smem descriptors; tcgen05.commit releases the smem stage and, after
-//           the last K block, publishes the TMEM accumulator.  Two accumulators (2 x N columns of TMEM)
-//           let the epilogue of tile i overlap the MMAs of tile i+1.
-//   warp 2  allocates / frees TMEM.
-//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 16 columns -> registers, + bias, swish, + residual,
-//           pack to bf16, 16-byte stores to C (row-contiguous NHWC).
-// These layers are HBM-bound (arithmetic intensity 10-250 flop/B): the design goal is
-// to stream A exactly once at full bandwidth; the tensor pipe has >10x headroom.
+// One persistent CTA per SM, warp-specialised (640 threads), no cluster:
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads (SWIZZLE_128B) of the W tile (N x 64) and (A_TMA,
+//               A_SCALE) the A tile (128 x 64) into a multi-stage smem ring; out-of-bounds rows/columns are
+//               zero-filled by TMA so ragged M, K = 16..1152 and N = 16..256 need no padding copies.
+//   warps 12-19 two groups of 4 staging warps working on alternate k-blocks:
+//               A_SCALE: wait for the raw TMA tile, multiply it in place in shared memory by the SE gates
+//                        (ld.shared -> fp32 mul -> bf16 -> st.shared at the swizzled address), fence.proxy.async;
+//               A_STEM:  gather the im2col row of each output pixel (15 aligned 4-byte loads) into the same
+//                        128-byte-swizzled K-major layout, fence.proxy.async.
+//   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N, K=16) per K step
+//               from smem descriptors; tcgen05.commit frees the smem stage and publishes the accumulator.
+//   warp 2      allocates / frees TMEM (two accumulators of N fp32 columns).
+//   warps 4-7 / 8-11  two epilogue sets in ping-pong (set s owns accumulator s and the tiles of its parity):
+//               tcgen05.ld (32 lanes x 32 columns) -> + bias (smem), swish (one MUFU tanh), + residual -> bf16 ->
+//               128-byte-swizzled smem staging (two 16 KB buffers per set) -> TMA tensor store of each
+//               64-column block (clips ragged M / N), so every global write is a full 128-byte line and the
+//               latency of one tile's epilogue hides behind the other set's.
+// These layers are HBM-bound (arithmetic intensity 10-250 flop/B): the design streams A once and writes C
+// once at full line width; the tensor pipe has >10x headroom.
 #include "dfd_internal.cuh"
 #include <cuda.h>
+#include <string.h>
 
 #define BLOCK_M 128
 #define BLOCK_K 64
-#define GEMM_THREADS 256
+#define GEMM_THREADS 640
 #define A_STAGE_BYTES (BLOCK_M * BLOCK_K * 2)
+#define STAGING_BLOCK_BYTES (BLOCK_M * 128)
+#define MAX_BIAS 1280
+
+enum { A_TMA = 0, A_SCALE = 1, A_STEM = 2 };
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -55,8 +69,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -68,14 +87,26 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void set_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // LBO unused for swizzled K-major (1), SBO = 8 rows * 128 B = 1024 B, version 1 (sm_100), layout SWIZZLE_128B (2).
@@ -89,7 +120,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
-__device__ __forceinline__ float swish_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x) = h + h * tanh(h), h = x/2 : one MUFU op
+__device__ __forceinline__ float swish_fast(float x) {
+    float h = 0.5f * x, t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 struct GemmParams {
     int M, N, K;
@@ -98,33 +134,45 @@ struct GemmParams {
     int num_tiles;        // m_blocks * n_blocks
     int stages;
     int act;
+    int a_mode;
+    int hw;               // A_SCALE: rows per image
     const float* bias;
     const __nv_bfloat16* residual;
-    __nv_bfloat16* C;
+    const __nv_bfloat16* A;    // A_STEM: NHWC input [B,224,224,3]
+    const float* se;           // A_SCALE: [images][K] gates
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2 * 8 + 4];     // full[8], empty[8], tmem_full[2], tmem_empty[2]
+    __shared__ __align__(8) uint64_t bars[3 * 8 + 4];     // full[8], empty[8], raw[8], tmem_full[2], tmem_empty[2]
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float sbias[MAX_BIAS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b_stage_bytes = (uint32_t)p.n_pad * BLOCK_K * 2;
     const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
     const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
-    const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
+    const uint32_t staging = smem_base + (uint32_t)p.stages * stage_bytes;     // 4 x 16 KB
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), raw0 = smem_u32(&bars[16]);
+    const uint32_t tfull0 = smem_u32(&bars[24]), tempty0 = smem_u32(&bars[26]);
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * (uint32_t)p.n_pad) tmem_cols <<= 1;
 
+    for (int i = threadIdx.x; i < p.n_pad * p.n_blocks && i < MAX_BIAS; i += GEMM_THREADS) sbias[i] = p.bias[i];
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        if (p.a_mode != A_STEM) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        // full[s]: A_TMA = the TMA thread; A_SCALE = 4 fix-up warps; A_STEM = TMA thread (W) + 4 gather warps
+        const uint32_t full_count = p.a_mode == A_TMA ? 1u : (p.a_mode == A_SCALE ? 4u : 5u);
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); mbar_init(raw0 + 8 * s, 1);
+        }
         for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -138,21 +186,25 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
+        // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            const uint32_t tx = p.a_mode == A_STEM ? b_stage_bytes : stage_bytes;
+            const uint32_t sig0 = p.a_mode == A_SCALE ? raw0 : full0;    // A_SCALE: the fix-up warps publish full[]
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
                 for (int kb = 0; kb < num_kb; kb++) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_STAGE_BYTES;
-                    mbar_expect_tx(full0 + 8 * stage, stage_bytes);
-                    tma_load_2d(sa, &map_a, kb * BLOCK_K, m_blk * BLOCK_M, full0 + 8 * stage);
-                    tma_load_2d(sb, &map_b, kb * BLOCK_K, n_blk * p.n_pad, full0 + 8 * stage);
+                    mbar_expect_tx(sig0 + 8 * stage, tx);
+                    if (p.a_mode != A_STEM) tma_load_2d(sa, &map_a, kb * BLOCK_K, m_blk * BLOCK_M, sig0 + 8 * stage);
+                    tma_load_2d(sb, &map_b, kb * BLOCK_K, n_blk * p.n_pad, sig0 + 8 * stage);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
+        // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
@@ -177,57 +229,158 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
-        const int ew = warp - 4;                                   // TMEM lane quarter = warp % 4
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
-            tc_fence_after();
-            const int m = m_blk * BLOCK_M + ew * 32 + lane;
-            const int n_base = n_blk * p.n_pad;
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            const bool row_ok = m < p.M;
-            __nv_bfloat16* crow = p.C + (size_t)m * p.N;
-            const __nv_bfloat16* rrow = p.residual ? p.residual + (size_t)m * p.N : nullptr;
-            for (int c = 0; c < p.n_pad; c += 16) {
-                uint32_t r[16];
-                tc_ld16(taddr + c, r);
-                tc_ld_wait();
-                const int n0 = n_base + c;
-                if (row_ok && n0 < p.N) {
+    } else if (warp >= 12) {
+        // ===== staging warps: two groups of 128 threads on alternate k-blocks =====
+        if (p.a_mode != A_TMA) {
+            const int g = (warp - 12) >> 2;
+            const int t = threadIdx.x - (12 + 4 * g) * 32;         // 0..127
+            int j = 0;                                             // running k-block index of this CTA
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.n_blocks) * BLOCK_M;
+                for (int kb = 0; kb < num_kb; kb++, j++) {
+                    if ((j & 1) != g) continue;
+                    const int stage = j % p.stages;
+                    const uint32_t phase = (uint32_t)(j / p.stages) & 1u;
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    if (p.a_mode == A_SCALE) {
+                        mbar_wait(raw0 + 8 * stage, phase);        // raw A (and W) tile landed
+                        const int c = t & 7;
+                        const int k = kb * BLOCK_K + c * 8;
+                        if (k < p.K) {
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int n = n0 + h * 8;
-                        if (n + 8 <= p.N) {
+                            for (int hb = 0; hb < 2; hb++) {
+                                uint4 v[4]; float4 s0[4], s1[4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    const int row = (hb * 4 + i) * 16 + (t >> 3);
+                                    int m = m0 + row; if (m >= p.M) m = p.M - 1;
+                                    const float* sp = p.se + (size_t)(m / p.hw) * p.K + k;
+                                    s0[i] = __ldg((const float4*)sp); s1[i] = __ldg((const float4*)(sp + 4));
+                                    v[i] = lds128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)));
+                                }
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    const int row = (hb * 4 + i) * 16 + (t >> 3);
+                                    __nv_bfloat162* h = (__nv_bfloat162*)&v[i];
+                                    float2 f;
+                                    f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * s0[i].x, f.y * s0[i].y);
+                                    f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * s0[i].z, f.y * s0[i].w);
+                                    f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * s1[i].x, f.y * s1[i].y);
+                                    f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * s1[i].z, f.y * s1[i].w);
+                                    sts128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)), v[i]);
+                                }
+                            }
+                        }
+                    } else {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        // stem im2col: row = output pixel; 3 kernel rows x 9 contiguous bf16 (3 px x 3 ch) -> 27 taps + 5 zeros
+                        const int row = t, m = m0 + row;
+                        uint32_t w[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i++) w[i] = 0;
+                        if (m < p.M) {
+                            const int ox = m % 112, oy = (m / 112) % 112, b = m / (112 * 112);
+                            uint32_t a[3][5];
+#pragma unroll
+                            for (int ky = 0; ky < 3; ky++) {
+                                const int iy = 2 * oy + ky;
+#pragma unroll
+                                for (int i = 0; i < 5; i++) a[ky][i] = 0;
+                                if (iy < 224) {
+                                    const uint32_t* src = (const uint32_t*)(p.A + (((size_t)b * 224 + iy) * 224 + 2 * ox) * 3);
+                                    a[ky][0] = __ldg(src); a[ky][1] = __ldg(src + 1); a[ky][2] = __ldg(src + 2);
+                                    if (ox < 111) { a[ky][3] = __ldg(src + 3); a[ky][4] = __ldg(src + 4) & 0xffffu; }   // third pixel is padding at the right edge
+                                }
+                            }
+                            w[0] = a[0][0]; w[1] = a[0][1]; w[2] = a[0][2]; w[3] = a[0][3];
+                            w[4] = a[0][4] | (a[1][0] << 16);
+                            w[5] = (a[1][0] >> 16) | (a[1][1] << 16);
+                            w[6] = (a[1][1] >> 16) | (a[1][2] << 16);
+                            w[7] = (a[1][2] >> 16) | (a[1][3] << 16);
+                            w[8] = (a[1][3] >> 16) | (a[1][4] << 16);
+                            w[9] = a[2][0]; w[10] = a[2][1]; w[11] = a[2][2]; w[12] = a[2][3]; w[13] = a[2][4];
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            sts128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full0 + 8 * stage);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: two sets of 4 warps in ping-pong; set s drains accumulator s =====
+        const int set = (warp - 4) >> 2;
+        const int q = warp & 3;                                    // TMEM lane quarter (= warp % 4)
+        const int row = q * 32 + lane;
+        const bool issuer = q == 0 && lane == 0;
+        const uint32_t my_staging = staging + (uint32_t)set * 2u * STAGING_BLOCK_BYTES;
+        const int nblk64 = (p.n_pad + 63) >> 6;
+        uint32_t blk_count = 0, acc_phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+            if ((it & 1) != set) continue;
+            const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
+            const int m = m_blk * BLOCK_M + row;
+            const int n_base = n_blk * p.n_pad;
+            mbar_wait(tfull0 + 8 * set, acc_phase);
+            acc_phase ^= 1;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.n_pad);
+            const bool row_ok = m < p.M;
+            const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
+            for (int jb = 0; jb < nblk64; jb++, blk_count++) {
+                const uint32_t buf = my_staging + (blk_count & 1u) * STAGING_BLOCK_BYTES;
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // this buffer's previous store has been read
+                set_bar_sync(1 + set);
+                const int cols_here = min(64, p.n_pad - jb * 64);
+                for (int c32 = 0; c32 < cols_here; c32 += 32) {
+                    uint32_t r[32];
+                    tc_ld32(taddr + jb * 64 + c32, r);            // columns beyond n_pad read the other accumulator's TMEM: ignored below
+                    tc_ld_wait();
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const int col = jb * 64 + c32 + h * 8;     // column inside the tile
+                        if (col < p.n_pad) {
+                            const int n = n_base + col;
                             float v[8];
-                            const float4 b0 = __ldg((const float4*)(p.bias + n)), b1 = __ldg((const float4*)(p.bias + n + 4));
+                            const float4 b0 = *(const float4*)(sbias + n), b1 = *(const float4*)(sbias + n + 4);
                             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                v[j] = __uint_as_float(r[h * 8 + j]) + bb[j];
-                                if (p.act) v[j] = swish_fast(v[j]);
+                            for (int jj = 0; jj < 8; jj++) {
+                                v[jj] = __uint_as_float(r[h * 8 + jj]) + bb[jj];
+                                if (p.act) v[jj] = swish_fast(v[jj]);
                             }
-                            if (rrow) {
-                                const uint4 rv = *(const uint4*)(rrow + n);
+                            if (rrow && n + 8 <= p.N) {
+                                const uint4 rv = __ldg((const uint4*)(rrow + n));
                                 const __nv_bfloat162* rh = (const __nv_bfloat162*)&rv;
 #pragma unroll
-                                for (int j = 0; j < 4; j++) { float2 f = __bfloat1622float2(rh[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                                for (int jj = 0; jj < 4; jj++) { float2 f = __bfloat1622float2(rh[jj]); v[2 * jj] += f.x; v[2 * jj + 1] += f.y; }
                             }
                             uint4 o;
                             __nv_bfloat162* oh = (__nv_bfloat162*)&o;
 #pragma unroll
-                            for (int j = 0; j < 4; j++) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                            *(uint4*)(crow + n) = o;
+                            for (int jj = 0; jj < 4; jj++) oh[jj] = __floats2bfloat162_rn(v[2 * jj], v[2 * jj + 1]);
+                            sts128(buf + (uint32_t)(row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4)), o);
                         }
                     }
                 }
+                if (jb == nblk64 - 1) {                            // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * set);
+                }
+                fence_async_smem();
+                set_bar_sync(1 + set);
+                if (issuer) {
+                    if (n_base + jb * 64 < p.N) tma_store_2d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, buf);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -270,48 +423,67 @@ static bool g_enabled = true;
 bool dfd_gemm_bf16_enabled() { return g_enabled; }
 void dfd_gemm_free(dfd_ctx*) {}
 
-int dfd_gemm_bf16(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
-                  const __nv_bfloat16* residual, __nv_bfloat16* C, int M, int N, int K, int act, cudaStream_t st) {
+// a_mode A_TMA: A = [M][K] matrix.  A_SCALE: A = [M][K] matrix gated by se[m / hw][k].  A_STEM: A = NHWC input
+// [M / 12544][224][224][3], K must be 32 (27 taps + zero pad), W = [32][32].
+int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const float* se, int hw, const __nv_bfloat16* W,
+                     const float* bias, const __nv_bfloat16* residual, __nv_bfloat16* C, int M, int N, int K, int act,
+                     cudaStream_t st) {
     int rc = get_encode(ctx);
     if (rc) return rc;
-    DFD_REQUIRE(K % 8 == 0 && N % 8 == 0, DFD_ERR_INVALID, "gemm: K and N must be multiples of 8");
+    DFD_REQUIRE(K % 8 == 0 && N % 8 == 0 && N <= MAX_BIAS, DFD_ERR_INVALID, "gemm: K and N must be multiples of 8, N <= 1280");
     GemmParams p;
-    p.M = M; p.N = N; p.K = K; p.act = act; p.bias = bias; p.residual = residual; p.C = C;
+    p.M = M; p.N = N; p.K = K; p.act = act; p.bias = bias; p.residual = residual;
+    p.a_mode = a_mode; p.A = A; p.se = se; p.hw = hw > 0 ? hw : 1;
     // N tiling: the smallest number of equal UMMA-N blocks (multiples of 16, <= 256) covering N
+    // (with several N blocks the block width is a multiple of 64 so the 64-column TMA stores of one block
+    // never touch its neighbour's columns)
     int nb = (N + 255) / 256;
-    int n_pad = ((N + nb - 1) / nb + 15) / 16 * 16;
+    int n_pad = nb == 1 ? (N + 15) / 16 * 16 : ((N + nb - 1) / nb + 63) / 64 * 64;
     p.n_pad = n_pad; p.n_blocks = (N + n_pad - 1) / n_pad;
     const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     p.num_tiles = m_blocks * p.n_blocks;
     const int stage_bytes = A_STAGE_BYTES + n_pad * BLOCK_K * 2;
-    int stages = (200 * 1024) / stage_bytes;
+    const int staging_bytes = 4 * STAGING_BLOCK_BYTES;       // two 16 KB buffers per epilogue set
+    int stages = (204 * 1024 - staging_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     if (stages > 2 * num_kb && stages > 4) stages = 2 * num_kb > 4 ? 2 * num_kb : 4;
+    DFD_REQUIRE(stages >= 2, DFD_ERR_INVALID, "gemm: tile does not fit shared memory");
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr_set = true;
     }
-    CUtensorMap ma, mb;
-    if ((rc = make_map(ctx, &ma, A, (uint64_t)M, (uint64_t)K, BLOCK_M))) return rc;
+    CUtensorMap ma, mb, mc;
+    if (a_mode != A_STEM) { if ((rc = make_map(ctx, &ma, A, (uint64_t)M, (uint64_t)K, BLOCK_M))) return rc; }
+    else memset(&ma, 0, sizeof ma);
     if ((rc = make_map(ctx, &mb, W, (uint64_t)N, (uint64_t)K, (uint32_t)n_pad))) return rc;
+    if ((rc = make_map(ctx, &mc, C, (uint64_t)M, (uint64_t)N, BLOCK_M))) return rc;
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    k_gemm_tcgen05<<<grid, GEMM_THREADS, smem, st>>>(ma, mb, p);
+    k_gemm_tcgen05<<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mc, p);
     DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);
     return DFD_OK;
 }
 
+int dfd_gemm_bf16(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
+                  const __nv_bfloat16* residual, __nv_bfloat16* C, int M, int N, int K, int act, cudaStream_t st) {
+    return dfd_gemm_bf16_ex(ctx, A_TMA, A, nullptr, 0, W, bias, residual, C, M, N, K, act, st);
+}
+
 // ---------------------------------------------------------------------------------------------
-// self-test against a CUDA-core reference (used by tests/test_gpu_gemm.py through dfd_gemm_selftest)
-__global__ void k_gemm_ref(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* res,
-                           float* C, int M, int N, int K, int act) {
+// self-test against a CUDA-core reference (tests/test_gpu_gemm.py through dfd_gemm_selftest)
+__global__ void k_gemm_ref(const __nv_bfloat16* A, const float* se, int hw, const __nv_bfloat16* W, const float* bias,
+                           const __nv_bfloat16* res, float* C, int M, int N, int K, int act) {
     int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
     if (n >= N || m >= M) return;
     float acc = 0.f;
-    for (int k = 0; k < K; k++) acc = fmaf(__bfloat162float(A[(size_t)m * K + k]), __bfloat162float(W[(size_t)n * K + k]), acc);
+    for (int k = 0; k < K; k++) {
+        float a = __bfloat162float(A[(size_t)m * K + k]);
+        if (se) a = __bfloat162float(__float2bfloat16_rn(a * se[(size_t)(m / hw) * K + k]));
+        acc = fmaf(a, __bfloat162float(W[(size_t)n * K + k]), acc);
+    }
     acc += bias[n];
     if (act) acc = acc / (1.0f + expf(-acc));
     if (res) acc += __bfloat162float(res[(size_t)m * N + n]);
@@ -326,12 +498,12 @@ __global__ void k_fill_bf16(__nv_bfloat16* x, size_t n, uint32_t seed, float sca
     x[i] = __float2bfloat16_rn(((float)(h & 0xffff) / 32768.0f - 1.0f) * scale);
 }
 
-__global__ void k_fill_f32(float* x, size_t n, uint32_t seed) {
+__global__ void k_fill_f32(float* x, size_t n, uint32_t seed, float lo, float hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t h = (uint32_t)i * 2246822519u ^ seed;
     h ^= h >> 15; h *= 0x85ebca6bu; h ^= h >> 13;
-    x[i] = (float)(h & 0xffff) / 65536.0f - 0.5f;
+    x[i] = lo + (hi - lo) * (float)(h & 0xffff) / 65536.0f;
 }
 
 __global__ void k_maxerr(const __nv_bfloat16* c, const float* ref, size_t n, float* out) {
@@ -342,28 +514,35 @@ __global__ void k_maxerr(const __nv_bfloat16* c, const float* ref, size_t n, flo
     atomicMax((int*)out, __float_as_int(e));        // non-negative floats order like ints
 }
 
+// with_residual bit 0: residual; bit 1: SE-gated A (A_SCALE) with hw = 49
 extern "C" int dfd_gemm_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int with_residual, double* max_err_host,
                                  void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool use_res = with_residual & 1, use_se = (with_residual & 2) != 0;
+    const int hw = 49, n_img = (M + hw - 1) / hw;
     __nv_bfloat16 *A, *W, *R, *C;
-    float *bias, *ref, *err;
+    float *bias, *ref, *err, *se;
     DFD_CUDA(cudaMalloc(&A, (size_t)M * K * 2));
-    DFD_CUDA(cudaMalloc(&W, (size_t)N * K * 2));
+    DFD_CUDA(cudaMalloc(&W, (size_t)N * K * 2 + 4096));
     DFD_CUDA(cudaMalloc(&R, (size_t)M * N * 2));
     DFD_CUDA(cudaMalloc(&C, (size_t)M * N * 2));
-    DFD_CUDA(cudaMalloc(&bias, (size_t)N * 4));
+    DFD_CUDA(cudaMalloc(&bias, (size_t)(N + 512) * 4));
+    DFD_CUDA(cudaMalloc(&se, (size_t)n_img * K * 4));
     DFD_CUDA(cudaMalloc(&ref, (size_t)M * N * 4));
     DFD_CUDA(cudaMalloc(&err, 4));
     DFD_CUDA(cudaMemsetAsync(err, 0, 4, st));
     DFD_CUDA(cudaMemsetAsync(C, 0xff, (size_t)M * N * 2, st));
+    DFD_CUDA(cudaMemsetAsync(bias, 0, (size_t)(N + 512) * 4, st));
     k_fill_bf16<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, st>>>(A, (size_t)M * K, 11u, 1.0f);
     k_fill_bf16<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(W, (size_t)N * K, 22u, 0.25f);
     k_fill_bf16<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, st>>>(R, (size_t)M * N, 33u, 1.0f);
-    k_fill_f32<<<(N + 255) / 256, 256, 0, st>>>(bias, (size_t)N, 44u);
-    int rc = dfd_gemm_bf16(ctx, A, W, bias, with_residual ? R : nullptr, C, M, N, K, act, st);
+    k_fill_f32<<<(N + 255) / 256, 256, 0, st>>>(bias, (size_t)N, 44u, -0.5f, 0.5f);
+    k_fill_f32<<<(unsigned)(((size_t)n_img * K + 255) / 256), 256, 0, st>>>(se, (size_t)n_img * K, 55u, 0.05f, 1.0f);
+    int rc = dfd_gemm_bf16_ex(ctx, use_se ? A_SCALE : A_TMA, A, use_se ? se : nullptr, hw, W, bias, use_res ? R : nullptr, C, M,
+                              N, K, act, st);
     if (rc == DFD_OK) {
-        k_gemm_ref<<<dim3((N + 127) / 128, M), 128, 0, st>>>(A, W, bias, with_residual ? R : nullptr, ref, M, N, K, act);
+        k_gemm_ref<<<dim3((N + 127) / 128, M), 128, 0, st>>>(A, use_se ? se : nullptr, hw, W, bias, use_res ? R : nullptr, ref, M, N, K, act);
         k_maxerr<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, st>>>(C, ref, (size_t)M * N, err);
         float e = 0.f;
         cudaError_t ce = cudaMemcpyAsync(&e, err, 4, cudaMemcpyDeviceToHost, st);
@@ -371,6 +550,6 @@ extern "C" int dfd_gemm_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int
         if (ce != cudaSuccess) { ctx->err = std::string("gemm selftest: ") + cudaGetErrorString(ce); rc = DFD_ERR_CUDA; }
         if (max_err_host) *max_err_host = (double)e;
     }
-    cudaFree(A); cudaFree(W); cudaFree(R); cudaFree(C); cudaFree(bias); cudaFree(ref); cudaFree(err);
+    cudaFree(A); cudaFree(W); cudaFree(R); cudaFree(C); cudaFree(bias); cudaFree(ref); cudaFree(err); cudaFree(se);
     return rc;
 }

@@ -68,3 +68,23 @@ def test_batch_invariance_fp32(setup):
     a = e.effnet_forward(xn).cpu()
     b = torch.cat([e.effnet_forward(xn[i:i + 1]).cpu() for i in range(4)])
     assert float((a[:4] - b).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["stem", "b0.dw", "b0.out", "b1.expand", "b1.dw", "b2.dw", "b3.dw", "b4.dw", "b5.dw", "b6.dw",
+                                  "b8.dw", "b9.out", "b11.dw", "b12.dw", "b15.dw", "b15.out", "features"])
+def test_bf16_activation_taps(setup, name):
+    """bf16 mode (tcgen05 GEMMs, tiled depthwise): every layer stays within bf16 rounding noise of the fp32
+    oracle -- an indexing bug (tile edge, padding, channel tail) would show as an O(1) error."""
+    e, sd, x, ref, taps = setup
+    xn = x[:3].permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    e.set_tap(name)
+    e.effnet_forward(xn)
+    got = e.activation(name).cpu()
+    e.set_tap("")
+    t = taps[name][:3]
+    want = t.permute(0, 2, 3, 1).reshape(-1) if t.dim() == 4 else t.reshape(-1)
+    err = (got - want).abs()
+    scale = float(want.abs().max())
+    print(name, "bf16 max abs err", float(err.max()), "mean", float(err.mean()), "scale", scale)
+    assert float(err.max()) <= 0.06 * max(scale, 1.0)
+    assert float(err.mean()) <= 0.01 * max(scale, 1.0)

@@ -21,7 +21,8 @@ def eng():
 
 @pytest.mark.parametrize("N,K", LAYERS)
 def test_gemm_layer_shapes(eng, N, K):
-    for M, act, res in ((12544, 1, 0), (49 * 5, 0, 1), (128 * 148 * 2 + 77, 1, 1)):
+    # res bit 0: residual add; bit 1: SE-gated A operand staged by the producer warps (A_SCALE, 49 rows / image)
+    for M, act, res in ((12544, 1, 0), (49 * 5, 0, 1), (128 * 148 * 2 + 77, 1, 1), (49 * 37, 0, 2), (12544, 0, 3)):
         err = eng.gemm_selftest(M, N, K, act, res)
         assert 0 <= err < 2e-2, (M, N, K, act, res, err)      # bf16 output rounding: <= 2^-8 relative
 
