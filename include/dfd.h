@@ -143,6 +143,8 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
 /* DeepfakeDetector.reset / FrameForensicAnalyzer.reset / TemporalTracker.reset
  * (deepfake_detection.py:344-355, 270-289; frame_analysis.py:391-395).  stream_id < 0 resets all. */
 int dfd_reset_stream(dfd_ctx* ctx, int stream_id, void* stream);
+/* what: 1 = FrameForensicAnalyzer state only, 2 = TemporalTracker state + frame_count only, 3 = both. */
+int dfd_reset_stream_part(dfd_ctx* ctx, int stream_id, int what, void* stream);
 
 /* Per-stream tracker parameters (TemporalTracker(window_size, voting_window, detection_threshold),
  * deepfake_detection.py:99); streams start with the context defaults.  Resets the stream's vote state. */

@@ -51,6 +51,7 @@ SYMBOLS = {
     "dfd_vote_update": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "dfd_analyze_batch": (_I, [_P, _P, _I, _I, _I, _S, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "dfd_reset_stream": (_I, [_P, _I, _P]),
+    "dfd_reset_stream_part": (_I, [_P, _I, _I, _P]),
     "dfd_configure_stream": (_I, [_P, _I, _I, _I, C.c_double, _P]),
     "dfd_launch_count": (C.c_int64, [_P]),
     "dfd_profile_start": (_I, [_P, _P]),

@@ -125,7 +125,7 @@ static int create_impl(dfd_ctx* ctx) {
     DFD_CUDA(cudaMalloc(&ctx->d_pil, nb * 2 * 160 * (2 + 64) * sizeof(int)));
     DFD_CUDA(cudaMalloc(&ctx->d_hpass, nb * (size_t)c.max_crop * 480));
     DFD_CUDA(cudaMalloc(&ctx->d_face160, nb * 160 * 480));
-    DFD_CUDA(cudaMalloc(&ctx->d_pool, nb * 1152 * sizeof(float)));
+    DFD_CUDA(cudaMalloc(&ctx->d_pool, nb * DFD_POOL_FLOATS * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_sescale, nb * 1152 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_feat, nb * 1280 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_logits, nb * sizeof(float)));
@@ -226,7 +226,14 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
 int dfd_reset_stream(dfd_ctx* ctx, int stream_id, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
     DFD_REQUIRE(stream_id < ctx->cfg.max_streams, DFD_ERR_CAPACITY, "reset_stream: id beyond max_streams");
-    return dfd_reset_launch(ctx, stream_id, (cudaStream_t)stream);
+    return dfd_reset_launch(ctx, stream_id, 3, (cudaStream_t)stream);
+}
+
+int dfd_reset_stream_part(dfd_ctx* ctx, int stream_id, int what, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DFD_REQUIRE(stream_id < ctx->cfg.max_streams, DFD_ERR_CAPACITY, "reset_stream: id beyond max_streams");
+    DFD_REQUIRE(what >= 1 && what <= 3, DFD_ERR_INVALID, "reset_stream_part: what must be 1, 2 or 3");
+    return dfd_reset_launch(ctx, stream_id, what, (cudaStream_t)stream);
 }
 
 int dfd_configure_stream(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double detection_threshold,

@@ -12,6 +12,7 @@
 #define DFD_MAX_VOTES 64
 #define DFD_MAX_SCORES 128
 #define DFD_RING 30                 // FrameForensicAnalyzer.temporal_diffs deque(maxlen=30)
+#define DFD_POOL_FLOATS 32768         // per-image SE squeeze partials: n_parts * C floats
 #define DFD_NBLK 64                 // 8x8 blocks of 32x32 on the 256^2 tile
 #define DFD_FFT_GROUPS 17           // 129 half-spectrum columns in groups of 8
 
@@ -82,7 +83,7 @@ struct dfd_ctx {
     __nv_bfloat16* d_stem_wg = nullptr;   // stem weights as a [32][32] K-major GEMM operand (27 taps + zero pad)
     DfdBuf act[3];                        // activation ping-pong + expanded buffer
     DfdBuf face_in;                       // prepared crops for analyze_batch
-    float* d_pool = nullptr;              // [m][1152] SE squeeze sums
+    float* d_pool = nullptr;              // [m][n_parts][C] SE squeeze partial sums (<= DFD_POOL_FLOATS per image)
     float* d_sescale = nullptr;           // [m][1152]
     float* d_feat = nullptr;              // [m][1280]
     float* d_logits = nullptr;            // [m]
@@ -149,5 +150,5 @@ int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_
 int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame, const double* face_prob,
                            const dfd_forensic_result* fres, const int32_t* stream_ids, dfd_vote_record* rec,
                            cudaStream_t st);
-int dfd_reset_launch(dfd_ctx* ctx, int stream_id, cudaStream_t st);
+int dfd_reset_launch(dfd_ctx* ctx, int stream_id, int what, cudaStream_t st);
 int dfd_configure_launch(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double thr, cudaStream_t st);

@@ -10,7 +10,8 @@
 //      accumulator pairs in registers, so each staged input word is read once per kernel row
 //      and reused for up to K outputs;
 //   3. swish, bf16 pack, 128-byte coalesced stores; per-channel sums of the swish outputs (the SE
-//      squeeze) are reduced in shared memory and leave the CTA as 64 atomics.
+//      squeeze) are reduced across the CTA's warps in a fixed order and written as one partial per
+//      (image, tile, channel) -- no atomics, so the forward pass is bit-reproducible; k_se adds the partials.
 #include "dfd_internal.cuh"
 #include "effnet_plan.h"
 
@@ -35,7 +36,7 @@ k_dw_tile(const __nv_bfloat16* __restrict__ in, const float* __restrict__ W, con
     extern __shared__ __align__(16) uint32_t smem_dw[];
     uint32_t* patch = smem_dw;                               // [PH][PW][32] bf16x2
     float* sw = (float*)(patch + PH * PW * 32);              // [K*K][64]
-    float* spool = sw + K * K * DW_CC;                       // [64]
+    float* spool = sw + K * K * DW_CC;                       // [DW_WARPS][64]
     const int tile = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
     const int ty = tile / tiles_x, tx = tile % tiles_x;
     const int oy0 = ty * TH, ox0 = tx * TW;
@@ -59,7 +60,6 @@ k_dw_tile(const __nv_bfloat16* __restrict__ in, const float* __restrict__ W, con
         const int c = c0 + (i & 63);
         sw[i] = c < C ? W[(size_t)(i >> 6) * C + c] : 0.f;
     }
-    if (tid < DW_CC) spool[tid] = 0.f;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
@@ -105,16 +105,21 @@ k_dw_tile(const __nv_bfloat16* __restrict__ in, const float* __restrict__ W, con
             }
         }
     }
-    if (ch_ok) { atomicAdd(&spool[2 * lane], ps0); atomicAdd(&spool[2 * lane + 1], ps1); }
+    spool[warp * DW_CC + 2 * lane] = ps0; spool[warp * DW_CC + 2 * lane + 1] = ps1;
     __syncthreads();
-    if (tid < DW_CC && c0 + tid < C) atomicAdd(pool + (size_t)b * C + c0 + tid, spool[tid]);
+    if (tid < DW_CC && c0 + tid < C) {                       // deterministic: fixed-order sum, one partial per tile
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < DW_WARPS; w++) s += spool[w * DW_CC + tid];
+        pool[((size_t)b * gridDim.x + tile) * C + c0 + tid] = s;
+    }
 }
 
 template <int K, int S, int TW, int TH>
 static int launch(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
-                  __nv_bfloat16* out, int m, cudaStream_t st) {
+                  __nv_bfloat16* out, int m, int* n_parts, cudaStream_t st) {
     constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
-    const size_t smem = (size_t)PH * PW * 128 + (size_t)K * K * DW_CC * 4 + DW_CC * 4;
+    const size_t smem = (size_t)PH * PW * 128 + (size_t)K * K * DW_CC * 4 + DW_WARPS * DW_CC * 4;
     static bool attr = false;
     if (!attr) {
         DFD_CUDA(cudaFuncSetAttribute(k_dw_tile<K, S, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -122,25 +127,27 @@ static int launch(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, cons
     }
     const int tiles_x = (b.hout + TW - 1) / TW, tiles_y = (b.hout + TH - 1) / TH;
     dim3 grid(tiles_x * tiles_y, (b.cexp + DW_CC - 1) / DW_CC, m);
+    *n_parts = tiles_x * tiles_y;
+    if ((size_t)grid.x * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
     k_dw_tile<K, S, TW, TH><<<grid, DW_WARPS * 32, smem, st>>>(in, W, bias, out, ctx->d_pool, b.cexp, b.hin, b.hout, b.pad, tiles_x);
     DFD_LAUNCH_CHECK("k_dw_tile", st);
     return DFD_OK;
 }
 
 int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
-                __nv_bfloat16* out, int m, cudaStream_t st) {
+                __nv_bfloat16* out, int m, int* n_parts, cudaStream_t st) {
     // tile shapes per output size: 112 -> 8x16, 56 -> 8x14, 28 / 14 -> 7x14, 7 -> 7x7
-    if (b.k == 3 && b.s == 1 && b.hout == 112) return launch<3, 1, 16, 8>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 3 && b.s == 2 && b.hout == 56) return launch<3, 2, 14, 8>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 56) return launch<3, 1, 14, 8>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 5 && b.s == 2 && b.hout == 28) return launch<5, 2, 14, 7>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 28) return launch<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 3 && b.s == 2 && b.hout == 14) return launch<3, 2, 14, 7>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 14) return launch<3, 1, 14, 7>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 14) return launch<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 5 && b.s == 2 && b.hout == 7) return launch<5, 2, 7, 7>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 7) return launch<5, 1, 7, 7>(ctx, b, in, W, bias, out, m, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 7) return launch<3, 1, 7, 7>(ctx, b, in, W, bias, out, m, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 112) return launch<3, 1, 16, 8>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 2 && b.hout == 56) return launch<3, 2, 14, 8>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 56) return launch<3, 1, 14, 8>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 2 && b.hout == 28) return launch<5, 2, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 28) return launch<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 2 && b.hout == 14) return launch<3, 2, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 14) return launch<3, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 14) return launch<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 2 && b.hout == 7) return launch<5, 2, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 7) return launch<5, 1, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 7) return launch<3, 1, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
     ctx->err = "dw_bf16: no tile configuration for this layer";
     return DFD_ERR_INVALID;
 }

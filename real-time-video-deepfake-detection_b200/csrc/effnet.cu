@@ -25,7 +25,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
                      cudaStream_t st);
 bool dfd_gemm_bf16_enabled();
 int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
-                __nv_bfloat16* out, int m, cudaStream_t st);
+                __nv_bfloat16* out, int m, int* n_parts, cudaStream_t st);
 
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
 template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
@@ -208,21 +208,25 @@ __global__ void __launch_bounds__(320) k_dw(const T* __restrict__ in, const floa
         for (int v = 0; v < VEC; v++) spool[ps * C + c0 + v] = psum[v];
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {      // deterministic: one partial per CTA, summed in order by k_se
         float s = 0.f;
         for (int q = 0; q < PS; q++) s += spool[q * C + c];
-        atomicAdd(pool + (size_t)b * C + c, s);
+        pool[((size_t)b * gridDim.x + blockIdx.x) * C + c] = s;
     }
 }
 
-// SE excite; also clears the pool for the next block.
-__global__ void __launch_bounds__(256) k_se(float* __restrict__ pool, const float* __restrict__ Wr, const float* __restrict__ br,
-                                            const float* __restrict__ Wx, const float* __restrict__ bx,
-                                            float* __restrict__ scale, int C, int se, float inv_hw) {
+// SE excite; sums the per-CTA squeeze partials of the depthwise kernel in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) k_se(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr,
+                                            const float* __restrict__ br, const float* __restrict__ Wx,
+                                            const float* __restrict__ bx, float* __restrict__ scale, int C, int se, float inv_hw) {
     __shared__ float s[1152];
     __shared__ float r[64];
     const int b = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += 256) { s[c] = pool[(size_t)b * C + c] * inv_hw; pool[(size_t)b * C + c] = 0.f; }
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f;
+        for (int q = 0; q < n_parts; q++) a += pool[((size_t)b * n_parts + q) * C + c];
+        s[c] = a * inv_hw;
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = warp; j < se; j += 8) {
@@ -342,7 +346,7 @@ static int tap(dfd_ctx* ctx, const char* name, const T* x, size_t n, cudaStream_
 
 template <typename T, int VEC>
 static int launch_dw(dfd_ctx* ctx, const EffBlock& b, const T* in, const float* W, const float* bias, T* out, int m,
-                     cudaStream_t st) {
+                     int* n_parts, cudaStream_t st) {
     const int CG = b.cexp / VEC;
     int threads = CG >= 256 ? CG : (256 / CG) * CG;
     if (threads > 1024) threads = CG;               // CG <= 288
@@ -352,6 +356,8 @@ static int launch_dw(dfd_ctx* ctx, const EffBlock& b, const T* in, const float* 
     int ppb = PS * 8;
     if (ppb > npix) ppb = npix;
     const int gx = (npix + ppb - 1) / ppb;
+    *n_parts = gx;
+    if ((size_t)gx * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
     size_t smem = (size_t)PS * b.cexp * sizeof(float);
 #define DW_CASE(KS)                                                                                         \
     k_dw<T, VEC, KS><<<dim3(gx, m), threads, smem, st>>>(in, W, bias, out, ctx->d_pool, b.cexp, b.hin, b.hout, \
@@ -379,7 +385,6 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
     T* x = (T*)ctx->act[0].p;
     T* y = (T*)ctx->act[1].p;
     T* e = (T*)ctx->act[2].p;
-    DFD_CUDA(cudaMemsetAsync(ctx->d_pool, 0, (size_t)m * 1152 * sizeof(float), st));
 
     static const char* L_EXP[16] = {"b0.expand", "b1.expand", "b2.expand", "b3.expand", "b4.expand", "b5.expand", "b6.expand", "b7.expand", "b8.expand", "b9.expand", "b10.expand", "b11.expand", "b12.expand", "b13.expand", "b14.expand", "b15.expand"};
     static const char* L_DW[16] = {"b0.dw", "b1.dw", "b2.dw", "b3.dw", "b4.dw", "b5.dw", "b6.dw", "b7.dw", "b8.dw", "b9.dw", "b10.dw", "b11.dw", "b12.dw", "b13.dw", "b14.dw", "b15.dw"};
@@ -428,15 +433,16 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             if (need > ctx->act[2].bytes) { ctx->err = "internal: expanded buffer too small"; return DFD_ERR_CAPACITY; }
         } else dw_out = y;
         ctx->label = L_DW[i];
+        int n_parts = 1;
         if constexpr (BF) {
-            if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, st))) return rc;
+            if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, &n_parts, st))) return rc;
         } else {
-            if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, st))) return rc;
+            if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, &n_parts, st))) return rc;
         }
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
-        k_se<<<m, 256, 0, st>>>(ctx->d_pool, Wf + f.wr, Wf + f.br, Wf + f.wx, Wf + f.bx, ctx->d_sescale, b.cexp, b.se,
+        k_se<<<m, 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, Wf + f.wx, Wf + f.bx, ctx->d_sescale, b.cexp, b.se,
                                 1.0f / (float)(b.hout * b.hout));
         DFD_LAUNCH_CHECK("k_se", st);
         const bool skip = b.s == 1 && b.cin == b.cout;

@@ -178,9 +178,9 @@ int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame,
     return DFD_OK;
 }
 
-int dfd_reset_launch(dfd_ctx* ctx, int stream_id, cudaStream_t st) {
+int dfd_reset_launch(dfd_ctx* ctx, int stream_id, int what, cudaStream_t st) {
     int first = stream_id < 0 ? 0 : stream_id, count = stream_id < 0 ? ctx->cfg.max_streams : 1;
-    k_reset<<<(count + 127) / 128, 128, 0, st>>>(ctx->d_state, first, count, 3, 0, 0, 0, 0.0);
+    k_reset<<<(count + 127) / 128, 128, 0, st>>>(ctx->d_state, first, count, what, 0, 0, 0, 0.0);
     DFD_LAUNCH_CHECK("k_reset", st);
     return DFD_OK;
 }

@@ -187,6 +187,12 @@ class Engine:
     def reset(self, stream_id=-1):
         self._check(self.lib.dfd_reset_stream(self.h, int(stream_id), self._stream()), "dfd_reset_stream")
 
+    def reset_forensics(self, stream_id):
+        self._check(self.lib.dfd_reset_stream_part(self.h, int(stream_id), 1, self._stream()), "dfd_reset_stream_part")
+
+    def reset_tracker(self, stream_id):
+        self._check(self.lib.dfd_reset_stream_part(self.h, int(stream_id), 2, self._stream()), "dfd_reset_stream_part")
+
     # -- per-kernel timing ------------------------------------------------------------
     def profile_start(self):
         self._check(self.lib.dfd_profile_start(self.h, self._stream()), "dfd_profile_start")

@@ -1,0 +1,69 @@
+"""CPU, world_size 2 over gloo: stream ownership, crop-balanced frame sharding and the verdict-record gather."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import dfd_b200  # noqa: F401
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import dfd_b200  # noqa: F401
+    from dfd_b200.engine import RECORD_DTYPE
+    from dfd_b200.sharding import StreamSharder
+    sh = StreamSharder()
+    stream_ids = np.arange(11)                       # 11 streams over 2 ranks: 6 + 5
+    idx, slots = sh.select(stream_ids)
+    assert all(sh.owner(s) == rank for s in stream_ids[idx])
+    assert list(slots) == [int(s) // world for s in stream_ids[idx]]
+    rec = np.zeros(len(idx), RECORD_DTYPE)
+    rec["stream_id"] = stream_ids[idx]
+    rec["verdict"] = (stream_ids[idx] % 3)
+    rec["vote_input"] = stream_ids[idx] / 10.0
+    buf = torch.from_numpy(rec.view(np.uint8).copy())
+    gathered = sh.gather_records(buf, max_per_rank=6)
+    allrec = StreamSharder.records_to_numpy(gathered)
+    assert sorted(allrec["stream_id"].tolist()) == list(range(11))
+    for r in allrec:
+        assert int(r["verdict"]) == int(r["stream_id"]) % 3 and abs(r["vote_input"] - r["stream_id"] / 10.0) < 1e-12
+    crops = [8, 1, 1, 1, 5, 2, 2, 3]
+    mine = sh.shard_frames_round_robin(len(crops), crops)
+    load = sum(crops[i] for i in mine)
+    t = torch.tensor([load, len(mine)], dtype=torch.int64)
+    lst = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(lst, t)
+    if rank == 0:
+        loads = [int(x[0]) for x in lst]
+        assert sum(loads) == sum(crops) and max(loads) - min(loads) <= 2, loads
+        assert sum(int(x[1]) for x in lst) == len(crops)
+    dist.barrier()
+    dist.destroy_process_group()
+    out.put((rank, "ok"))
+
+
+def test_stream_sharding_and_record_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got == [(0, "ok"), (1, "ok")]
