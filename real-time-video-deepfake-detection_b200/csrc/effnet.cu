@@ -215,32 +215,55 @@ __global__ void __launch_bounds__(320) k_dw(const T* __restrict__ in, const floa
     }
 }
 
-// SE excite; sums the per-CTA squeeze partials of the depthwise kernel in a fixed order (deterministic).
+// SE excite for SE_IPC images per CTA (the FC weights are read once per CTA instead of once per image);
+// sums the per-CTA squeeze partials of the depthwise kernel in a fixed order (deterministic).
+#define SE_IPC 4
 __global__ void __launch_bounds__(256) k_se(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr,
                                             const float* __restrict__ br, const float* __restrict__ Wx,
-                                            const float* __restrict__ bx, float* __restrict__ scale, int C, int se, float inv_hw) {
-    __shared__ float s[1152];
-    __shared__ float r[64];
-    const int b = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += 256) {
+                                            const float* __restrict__ bx, float* __restrict__ scale, int C, int se,
+                                            float inv_hw, int m) {
+    __shared__ float s[SE_IPC][1152];
+    __shared__ float r[SE_IPC][64];
+    const int b0 = blockIdx.x * SE_IPC;
+    for (int e = threadIdx.x; e < SE_IPC * C; e += 256) {
+        const int i = e / C, c = e - i * C, b = b0 + i;
         float a = 0.f;
-        for (int q = 0; q < n_parts; q++) a += pool[((size_t)b * n_parts + q) * C + c];
-        s[c] = a * inv_hw;
+        if (b < m)
+            for (int q = 0; q < n_parts; q++) a += pool[((size_t)b * n_parts + q) * C + c];
+        s[i][c] = a * inv_hw;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = warp; j < se; j += 8) {
-        float a = 0.f;
-        for (int c = lane; c < C; c += 32) a = fmaf(Wr[(size_t)j * C + c], s[c], a);
+        float a[SE_IPC];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) r[j] = swishf(a + br[j]);
+        for (int i = 0; i < SE_IPC; i++) a[i] = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float w = __ldg(Wr + (size_t)j * C + c);
+#pragma unroll
+            for (int i = 0; i < SE_IPC; i++) a[i] = fmaf(w, s[i][c], a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < SE_IPC; i++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+            if (lane == 0) r[i][j] = swishf(a[i] + br[j]);
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256) {
-        float a = bx[c];
-        for (int j = 0; j < se; j++) a = fmaf(Wx[(size_t)c * se + j], r[j], a);
-        scale[(size_t)b * C + c] = sigmoidf(a);
+        float a[SE_IPC];
+        const float bc = bx[c];
+#pragma unroll
+        for (int i = 0; i < SE_IPC; i++) a[i] = bc;
+        for (int j = 0; j < se; j++) {
+            const float w = __ldg(Wx + (size_t)c * se + j);
+#pragma unroll
+            for (int i = 0; i < SE_IPC; i++) a[i] = fmaf(w, r[i][j], a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < SE_IPC; i++)
+            if (b0 + i < m) scale[(size_t)(b0 + i) * C + c] = sigmoidf(a[i]);
     }
 }
 
@@ -442,8 +465,8 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
-        k_se<<<m, 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, Wf + f.wx, Wf + f.bx, ctx->d_sescale, b.cexp, b.se,
-                                1.0f / (float)(b.hout * b.hout));
+        k_se<<<(m + SE_IPC - 1) / SE_IPC, 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, Wf + f.wx, Wf + f.bx,
+                                                        ctx->d_sescale, b.cexp, b.se, 1.0f / (float)(b.hout * b.hout), m);
         DFD_LAUNCH_CHECK("k_se", st);
         const bool skip = b.s == 1 && b.cin == b.cout;
         T* outp = (dw_out == y) ? x : y;       // block 0 wrote dw into y; its project output goes to x (input is dead, no skip)
