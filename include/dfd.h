@@ -151,6 +151,10 @@ int dfd_reset_stream_part(dfd_ctx* ctx, int stream_id, int what, void* stream);
 int dfd_configure_stream(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double detection_threshold,
                          void* stream);
 
+/* Hang diagnosis: with DFD_FLIGHT=1 in the environment every launch is followed by a stream-ordered marker written to
+ * mapped host memory; the report names the last completed kernel and the pending ones (HOST buffer). */
+int dfd_flight_report(dfd_ctx* ctx, char* buf_host, size_t buf_bytes);
+
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t dfd_launch_count(dfd_ctx* ctx);
 
@@ -169,6 +173,9 @@ int dfd_dbg_canny(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, void
 /* tcgen05 GEMM self-test: C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual) on random bf16 data against a
  * CUDA-core reference; writes max |err| to *max_err_host (HOST double) and returns 0 if the kernel ran. */
 int dfd_gemm_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int with_residual, double* max_err_host, void* stream);
+/* Mean milliseconds per launch of one GEMM shape over `iters` launches (kernel tuning; flags: 1 = no stores, 2 = no epilogue
+ * math, 4 = SE-gated A, 8 = residual). */
+int dfd_gemm_bench(dfd_ctx* ctx, int M, int N, int K, int act, int flags, int iters, double* ms_host, void* stream);
 /* After dfd_face_prep_batch: the 160 x 160 x 3 RGB u8 image of box i. */
 int dfd_dbg_face160(dfd_ctx* ctx, int i, uint8_t* out_dev, void* stream);
 /* After dfd_face_prep_batch: the CLAHE'd crop of box i as w*h*3 BGR u8 (tight). */

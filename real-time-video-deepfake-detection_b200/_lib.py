@@ -53,6 +53,7 @@ SYMBOLS = {
     "dfd_reset_stream": (_I, [_P, _I, _P]),
     "dfd_reset_stream_part": (_I, [_P, _I, _I, _P]),
     "dfd_configure_stream": (_I, [_P, _I, _I, _I, C.c_double, _P]),
+    "dfd_flight_report": (_I, [_P, C.c_char_p, _S]),
     "dfd_launch_count": (C.c_int64, [_P]),
     "dfd_profile_start": (_I, [_P, _P]),
     "dfd_profile_stop": (_I, [_P, C.c_char_p, _S, _P]),
@@ -64,6 +65,7 @@ SYMBOLS = {
     "dfd_dbg_set_tap": (_I, [_P, C.c_char_p]),
     "dfd_dbg_activation": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),
     "dfd_gemm_selftest": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(C.c_double), _P]),
+    "dfd_gemm_bench": (_I, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_double), _P]),
 }
 
 _lib = None

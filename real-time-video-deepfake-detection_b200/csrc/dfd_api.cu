@@ -2,6 +2,7 @@
 #include "dfd_internal.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 int dfd_forensics_init(dfd_ctx* ctx);
 int dfd_dbg_jpeg_launch(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n, cudaStream_t st);
@@ -25,6 +26,23 @@ void dfd_prof_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st) {
     cudaEventRecord(ctx->prof_events[ctx->prof_used], st);
     ctx->prof_labels[ctx->prof_used] = std::string(kernel) + (ctx->label[0] ? std::string(":") + ctx->label : std::string());
     ctx->prof_used++;
+}
+
+__global__ void k_mark(unsigned long long* p, unsigned long long v) { *p = v; __threadfence_system(); }
+
+void dfd_flight_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st) {
+    if (ctx->flight_names.empty()) ctx->flight_names.resize(4096);
+    ctx->flight_seq++;
+    ctx->flight_names[ctx->flight_seq % 4096] = std::string(kernel) + ":" + ctx->label;
+    k_mark<<<1, 1, 0, st>>>(ctx->d_mark, ctx->flight_seq);     // completes after kernel #flight_seq on this stream
+}
+
+void dfd_trace(dfd_ctx* ctx, const char* kernel, cudaStream_t st) {
+    fprintf(stderr, "[dfd] %s:%s ...", kernel, ctx->label);
+    fflush(stderr);
+    cudaError_t e = cudaStreamSynchronize(st);
+    fprintf(stderr, " %s\n", e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    fflush(stderr);
 }
 
 extern "C" {
@@ -127,10 +145,19 @@ static int create_impl(dfd_ctx* ctx) {
     DFD_CUDA(cudaMalloc(&ctx->d_face160, nb * 160 * 480));
     DFD_CUDA(cudaMalloc(&ctx->d_pool, nb * DFD_POOL_FLOATS * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_sescale, nb * 1152 * sizeof(float)));
+    DFD_CUDA(cudaMalloc(&ctx->d_se_r, nb * 64 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_feat, nb * 1280 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_logits, nb * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_faceprob, nb * sizeof(double)));
     DFD_CUDA(cudaMalloc(&ctx->d_voteinput, nb * sizeof(double)));
+    if (ctx->flight) {
+        DFD_CUDA(cudaHostAlloc((void**)&ctx->h_mark, 8, cudaHostAllocMapped));
+        *ctx->h_mark = 0;
+        DFD_CUDA(cudaHostGetDevicePointer((void**)&ctx->d_mark, (void*)ctx->h_mark, 0));
+    }
+    DFD_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    DFD_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    DFD_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     int rc = dfd_forensics_init(ctx);
     if (rc) return rc;
     if ((rc = dfd_configure_launch(ctx, -1, c.window_size, c.voting_window, c.detection_threshold, 0))) return rc;
@@ -142,6 +169,9 @@ int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
     if (!cfg || !out) { g_create_err = "create: null argument"; return DFD_ERR_INVALID; }
     dfd_ctx* ctx = new dfd_ctx;
     ctx->cfg = *cfg;
+    ctx->trace = getenv("DFD_TRACE") != nullptr;
+    ctx->flight = getenv("DFD_FLIGHT") != nullptr;
+    ctx->no_overlap = getenv("DFD_NO_OVERLAP") != nullptr;
     int rc = create_impl(ctx);
     if (rc) { g_create_err = ctx->err; dfd_destroy(ctx); *out = nullptr; return rc; }
     *out = ctx;
@@ -153,8 +183,12 @@ void dfd_destroy(dfd_ctx* ctx) {
     void* ptrs[] = {ctx->d_tables, ctx->d_twiddle, ctx->d_state, ctx->d_prev_gray, ctx->d_tile, ctx->d_gray, ctx->d_fft,
                     ctx->d_part, ctx->d_fres, ctx->d_luts, ctx->d_pil, ctx->d_hpass, ctx->d_face160, ctx->d_wf32,
                     ctx->d_wbf16, ctx->d_stem_wg, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
-                    ctx->d_sescale, ctx->d_feat, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
+                    ctx->d_sescale, ctx->d_se_r, ctx->d_wxt, ctx->d_feat, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     dfd_gemm_free(ctx);
     delete ctx;
 }
@@ -210,8 +244,17 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
     DFD_REQUIRE(m == 0 || (boxes && box_frame), DFD_ERR_INVALID, "analyze_batch: boxes missing");
     cudaStream_t st = (cudaStream_t)stream;
     dfd_forensic_result* fres = forensic_out ? forensic_out : ctx->d_fres;
-    int rc = dfd_forensics_launch(ctx, frames, n, H, W, frame_stride, row_pitch, stream_ids, full, fres, st);
+    // The forensic signals and the face path are independent until the vote: fork the (ALU/latency-bound)
+    // forensic kernels onto the auxiliary stream so they overlap the (HBM-bound) classifier.
+    const bool overlap = m > 0 && !ctx->profiling && !ctx->trace && !ctx->no_overlap;
+    cudaStream_t fst = overlap ? ctx->aux : st;
+    if (overlap) {
+        DFD_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        DFD_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    }
+    int rc = dfd_forensics_launch(ctx, frames, n, H, W, frame_stride, row_pitch, stream_ids, full, fres, fst);
     if (rc) return rc;
+    if (overlap) DFD_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
     double* fprob = face_prob_out ? face_prob_out : ctx->d_faceprob;
     if (m > 0) {
         size_t esz = dtype == DFD_BF16 ? 2 : 4;
@@ -220,6 +263,7 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
         if ((rc = dfd_effnet_launch(ctx, ctx->face_in.p, m, dtype, ctx->d_logits, st))) return rc;
         if ((rc = dfd_faceprob_launch(ctx, ctx->d_logits, boxes, m, fprob, st))) return rc;
     }
+    if (overlap) DFD_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     return dfd_select_vote_launch(ctx, n, m, box_frame, fprob, fres, stream_ids, records, st);
 }
 
@@ -243,6 +287,18 @@ int dfd_configure_stream(dfd_ctx* ctx, int stream_id, int window_size, int votin
     DFD_REQUIRE(window_size >= 10 && window_size <= DFD_MAX_SCORES, DFD_ERR_INVALID, "configure_stream: window_size must be 10..128");
     DFD_REQUIRE(voting_window >= 1 && voting_window <= DFD_MAX_VOTES, DFD_ERR_INVALID, "configure_stream: voting_window must be 1..64");
     return dfd_configure_launch(ctx, stream_id, window_size, voting_window, detection_threshold, (cudaStream_t)stream);
+}
+
+/* Hang diagnosis (DFD_FLIGHT=1): the last kernel whose completion marker reached host memory and the ones after it. */
+int dfd_flight_report(dfd_ctx* ctx, char* buf, size_t n) {
+    if (!ctx || !ctx->flight || !buf || n == 0) return DFD_ERR_INVALID;
+    unsigned long long done = *ctx->h_mark, issued = ctx->flight_seq;
+    std::string out = "completed #" + std::to_string(done) + " of " + std::to_string(issued) + " issued;";
+    for (unsigned long long q = done > 2 ? done - 2 : 1; q <= issued && q <= done + 4; q++)
+        out += " [" + std::to_string(q) + (q <= done ? " done " : " PENDING ") + ctx->flight_names[q % 4096] + "]";
+    size_t k = out.size() < n - 1 ? out.size() : n - 1;
+    memcpy(buf, out.data(), k); buf[k] = 0;
+    return DFD_OK;
 }
 
 int64_t dfd_launch_count(dfd_ctx* ctx) { return ctx ? ctx->launches : 0; }

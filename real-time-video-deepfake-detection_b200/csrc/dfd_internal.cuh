@@ -85,6 +85,8 @@ struct dfd_ctx {
     DfdBuf face_in;                       // prepared crops for analyze_batch
     float* d_pool = nullptr;              // [m][n_parts][C] SE squeeze partial sums (<= DFD_POOL_FLOATS per image)
     float* d_sescale = nullptr;           // [m][1152]
+    float* d_se_r = nullptr;              // [m][64] squeezed activations between the two SE kernels
+    float* d_wxt = nullptr;               // transposed SE expand weights, all blocks
     float* d_feat = nullptr;              // [m][1280]
     float* d_logits = nullptr;            // [m]
     double* d_faceprob = nullptr;         // [m]
@@ -94,8 +96,18 @@ struct dfd_ctx {
     DfdBuf tap;
     int64_t tap_elems = 0;
     void* tmaps = nullptr;                // host-side cache of TMA descriptors (effnet_bf16.cu)
+    // analyze_batch runs the forensic kernels on a second stream, concurrently with face prep + classifier
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // per-launch profiling (bench.py roofline): an event after every launch, labelled
     bool profiling = false;
+    bool flight = false;                  // DFD_FLIGHT=1: stream-ordered completion markers in mapped host memory (hang diagnosis)
+    volatile unsigned long long* h_mark = nullptr;
+    unsigned long long* d_mark = nullptr;
+    unsigned long long flight_seq = 0;
+    std::vector<std::string> flight_names;
+    bool trace = false;                   // DFD_TRACE=1: synchronise after every launch and log it (debugging)
+    bool no_overlap = false;              // DFD_NO_OVERLAP=1: run the forensic kernels on the caller's stream
     const char* label = "";               // set by the launch code before each kernel
     std::vector<cudaEvent_t> prof_events;
     std::vector<std::string> prof_labels;
@@ -103,6 +115,8 @@ struct dfd_ctx {
 };
 
 void dfd_prof_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st);
+void dfd_trace(dfd_ctx* ctx, const char* kernel, cudaStream_t st);
+void dfd_flight_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st);
 
 #define DFD_CUDA(call)                                                                      \
     do {                                                                                    \
@@ -117,6 +131,8 @@ void dfd_prof_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st);
     do {                                                                                    \
         ctx->launches++;                                                                    \
         if (ctx->profiling) dfd_prof_mark(ctx, kname, st_);                                 \
+        if (ctx->trace) dfd_trace(ctx, kname, st_);                                         \
+        if (ctx->flight) dfd_flight_mark(ctx, kname, st_);                                  \
         cudaError_t e_ = cudaPeekAtLastError();                                             \
         if (e_ != cudaSuccess) {                                                            \
             ctx->err = std::string("kernel launch at ") + __FILE__ + ":" + std::to_string(__LINE__) + ": " + \

@@ -215,56 +215,74 @@ __global__ void __launch_bounds__(320) k_dw(const T* __restrict__ in, const floa
     }
 }
 
-// SE excite for SE_IPC images per CTA (the FC weights are read once per CTA instead of once per image);
-// sums the per-CTA squeeze partials of the depthwise kernel in a fixed order (deterministic).
-#define SE_IPC 4
-__global__ void __launch_bounds__(256) k_se(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr,
-                                            const float* __restrict__ br, const float* __restrict__ Wx,
-                                            const float* __restrict__ bx, float* __restrict__ scale, int C, int se,
-                                            float inv_hw, int m) {
-    __shared__ float s[SE_IPC][1152];
-    __shared__ float r[SE_IPC][64];
-    const int b0 = blockIdx.x * SE_IPC;
+// SE excite as two small kernels with full-chip parallelism and coalesced, unrolled weight reads.
+//   k_se_reduce : r[b][j] = swish(Wr[j] . mean[b] + br[j])      CTA = (8 squeeze channels, 8 images); warp = one j
+//   k_se_expand : g[b][c] = sigmoid(WxT[:, c] . r[b] + bx[c])   CTA = (256 channels, 8 images); thread = one c
+// The per-CTA squeeze partials of the depthwise kernel are summed here in a fixed order (deterministic).
+#define SE_IPC 8
+__global__ void __launch_bounds__(256) k_se_reduce(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr,
+                                                   const float* __restrict__ br, float* __restrict__ rbuf, int C, int se,
+                                                   float inv_hw, int m) {
+    __shared__ __align__(16) float s[SE_IPC][1152];
+    const int b0 = blockIdx.y * SE_IPC;
     for (int e = threadIdx.x; e < SE_IPC * C; e += 256) {
         const int i = e / C, c = e - i * C, b = b0 + i;
         float a = 0.f;
-        if (b < m)
+        if (b < m) {
+#pragma unroll 4
             for (int q = 0; q < n_parts; q++) a += pool[((size_t)b * n_parts + q) * C + c];
+        }
         s[i][c] = a * inv_hw;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < se; j += 8) {
-        float a[SE_IPC];
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= se) return;
+    float a[SE_IPC];
 #pragma unroll
-        for (int i = 0; i < SE_IPC; i++) a[i] = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float w = __ldg(Wr + (size_t)j * C + c);
-#pragma unroll
-            for (int i = 0; i < SE_IPC; i++) a[i] = fmaf(w, s[i][c], a[i]);
-        }
+    for (int i = 0; i < SE_IPC; i++) a[i] = 0.f;
+    const float4* w4 = (const float4*)(Wr + (size_t)j * C);
+#pragma unroll 3
+    for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+        const float4 w = __ldg(w4 + c4);
 #pragma unroll
         for (int i = 0; i < SE_IPC; i++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
-            if (lane == 0) r[i][j] = swishf(a[i] + br[j]);
+            const float4 x = *(const float4*)&s[i][c4 * 4];
+            a[i] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, a[i]))));
         }
+    }
+#pragma unroll
+    for (int i = 0; i < SE_IPC; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        if (lane == 0 && b0 + i < m) rbuf[(size_t)(b0 + i) * 64 + j] = swishf(a[i] + br[j]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_se_expand(const float* __restrict__ rbuf, const float* __restrict__ WxT,
+                                                   const float* __restrict__ bx, float* __restrict__ scale, int C, int se, int m) {
+    __shared__ float r[SE_IPC][64];
+    const int b0 = blockIdx.y * SE_IPC;
+    for (int e = threadIdx.x; e < SE_IPC * 64; e += 256) {
+        const int i = e >> 6, j = e & 63;
+        r[i][j] = (b0 + i < m && j < se) ? rbuf[(size_t)(b0 + i) * 64 + j] : 0.f;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += 256) {
-        float a[SE_IPC];
-        const float bc = bx[c];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    float a[SE_IPC];
+    const float bc = bx[c];
 #pragma unroll
-        for (int i = 0; i < SE_IPC; i++) a[i] = bc;
-        for (int j = 0; j < se; j++) {
-            const float w = __ldg(Wx + (size_t)c * se + j);
+    for (int i = 0; i < SE_IPC; i++) a[i] = bc;
+#pragma unroll 4
+    for (int j = 0; j < se; j++) {
+        const float w = __ldg(WxT + (size_t)j * C + c);
 #pragma unroll
-            for (int i = 0; i < SE_IPC; i++) a[i] = fmaf(w, r[i][j], a[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < SE_IPC; i++)
-            if (b0 + i < m) scale[(size_t)(b0 + i) * C + c] = sigmoidf(a[i]);
+        for (int i = 0; i < SE_IPC; i++) a[i] = fmaf(w, r[i][j], a[i]);
     }
+#pragma unroll
+    for (int i = 0; i < SE_IPC; i++)
+        if (b0 + i < m) scale[(size_t)(b0 + i) * C + c] = sigmoidf(a[i]);
 }
 
 // x *= se[img][c]   (bf16 mode: produces the A operand of the project GEMM)
@@ -347,6 +365,20 @@ int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n) {
     std::vector<__nv_bfloat16> h(o.total);
     for (size_t i = 0; i < o.total; i++) h[i] = __float2bfloat16_rn(blob[i]);
     DFD_CUDA(cudaMemcpy(ctx->d_wbf16, h.data(), o.total * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    {   // transposed SE expand weights WxT[j][c] (coalesced reads in k_se_expand)
+        size_t tot = 0;
+        for (int i = 0; i < 16; i++) tot += (size_t)EFF_BLOCKS[i].cexp * EFF_BLOCKS[i].se;
+        std::vector<float> wt(tot);
+        size_t at = 0;
+        for (int i = 0; i < 16; i++) {
+            const EffBlock& b = EFF_BLOCKS[i];
+            for (int j = 0; j < b.se; j++)
+                for (int c = 0; c < b.cexp; c++) wt[at + (size_t)j * b.cexp + c] = blob[o.blk[i].wx + (size_t)c * b.se + j];
+            at += (size_t)b.cexp * b.se;
+        }
+        if (!ctx->d_wxt) DFD_CUDA(cudaMalloc(&ctx->d_wxt, tot * sizeof(float)));
+        DFD_CUDA(cudaMemcpy(ctx->d_wxt, wt.data(), tot * sizeof(float), cudaMemcpyHostToDevice));
+    }
     std::vector<__nv_bfloat16> wg(32 * 32);
     for (int n = 0; n < 32; n++)
         for (int k = 0; k < 32; k++) wg[n * 32 + k] = __float2bfloat16_rn(k < 27 ? blob[o.stem_w + (size_t)k * 32 + n] : 0.f);
@@ -436,6 +468,8 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         return DFD_OK;
     };
     char nm[32];
+    size_t wxt_off[16];
+    { size_t acc = 0; for (int i = 0; i < 16; i++) { wxt_off[i] = acc; acc += (size_t)EFF_BLOCKS[i].cexp * EFF_BLOCKS[i].se; } }
     for (int i = 0; i < 16; i++) {
         const EffBlock& b = EFF_BLOCKS[i];
         const EffBlockOff& f = o.blk[i];
@@ -465,9 +499,15 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
-        k_se<<<(m + SE_IPC - 1) / SE_IPC, 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, Wf + f.wx, Wf + f.bx,
-                                                        ctx->d_sescale, b.cexp, b.se, 1.0f / (float)(b.hout * b.hout), m);
-        DFD_LAUNCH_CHECK("k_se", st);
+        {
+            const int mg = (m + SE_IPC - 1) / SE_IPC;
+            k_se_reduce<<<dim3((b.se + 7) / 8, mg), 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, ctx->d_se_r, b.cexp,
+                                                                  b.se, 1.0f / (float)(b.hout * b.hout), m);
+            DFD_LAUNCH_CHECK("k_se_reduce", st);
+            k_se_expand<<<dim3((b.cexp + 255) / 256, mg), 256, 0, st>>>(ctx->d_se_r, ctx->d_wxt + wxt_off[i], Wf + f.bx,
+                                                                        ctx->d_sescale, b.cexp, b.se, m);
+            DFD_LAUNCH_CHECK("k_se_expand", st);
+        }
         const bool skip = b.s == 1 && b.cin == b.cout;
         T* outp = (dw_out == y) ? x : y;       // block 0 wrote dw into y; its project output goes to x (input is dead, no skip)
         ctx->label = L_PROJ[i];

@@ -136,6 +136,8 @@ struct GemmParams {
     int act;
     int a_mode;
     int hw;               // A_SCALE: rows per image
+    int b_resident;       // W (all k-blocks) stays in shared memory for the whole kernel; the ring holds A only
+    int debug;            // diagnostics (dfd_gemm_bench): bit 0 = skip the TMA stores, bit 1 = skip the epilogue math
     const float* bias;
     const __nv_bfloat16* residual;
     const __nv_bfloat16* A;    // A_STEM: NHWC input [B,224,224,3]
@@ -146,20 +148,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[3 * 8 + 4];     // full[8], empty[8], raw[8], tmem_full[2], tmem_empty[2]
+    __shared__ __align__(8) uint64_t bars[3 * 8 + 5];     // full[8], empty[8], raw[8], tmem_full[2], tmem_empty[2], bfull
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float sbias[MAX_BIAS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b_stage_bytes = (uint32_t)p.n_pad * BLOCK_K * 2;
-    const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    const uint32_t stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0u : b_stage_bytes);
     const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
-    const uint32_t staging = smem_base + (uint32_t)p.stages * stage_bytes;     // 4 x 16 KB
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), raw0 = smem_u32(&bars[16]);
-    const uint32_t tfull0 = smem_u32(&bars[24]), tempty0 = smem_u32(&bars[26]);
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const uint32_t b_region = smem_base + (uint32_t)p.stages * stage_bytes;    // resident W: num_kb x (n_pad x 128 B)
+    const uint32_t staging = b_region + (p.b_resident ? (uint32_t)num_kb * b_stage_bytes : 0u);     // 4 x 16 KB
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), raw0 = smem_u32(&bars[16]);
+    const uint32_t tfull0 = smem_u32(&bars[24]), tempty0 = smem_u32(&bars[26]), bfull = smem_u32(&bars[28]);
+    // two accumulators of n_pad columns; the epilogue reads 32 columns at a time, so the last read of the second
+    // accumulator may extend to the next multiple of 32 -- it must stay inside the allocation
     uint32_t tmem_cols = 32;
-    while (tmem_cols < 2u * (uint32_t)p.n_pad) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)p.n_pad + (((uint32_t)p.n_pad + 31u) & ~31u)) tmem_cols <<= 1;
 
     for (int i = threadIdx.x; i < p.n_pad * p.n_blocks && i < MAX_BIAS; i += GEMM_THREADS) sbias[i] = p.bias[i];
     if (warp == 0 && lane == 0) {
@@ -169,11 +174,13 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         // full[s]: A_TMA = the TMA thread; A_SCALE = 4 fix-up warps; A_STEM = TMA thread (W) + 4 gather warps
-        const uint32_t full_count = p.a_mode == A_TMA ? 1u : (p.a_mode == A_SCALE ? 4u : 5u);
+        const uint32_t full_count = p.a_mode == A_TMA ? 1u : (p.a_mode == A_SCALE ? 4u : (p.b_resident ? 4u : 5u));
+        mbar_init(bfull, 1);
         for (int s = 0; s < p.stages; s++) {
             mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); mbar_init(raw0 + 8 * s, 1);
         }
-        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        // A_TMA: the 8 staging warps double as a second pair of epilogue groups (column halves) -> 8 arrivals
+        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, p.a_mode == A_TMA ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -189,17 +196,25 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx = p.a_mode == A_STEM ? b_stage_bytes : stage_bytes;
+            const bool load_a = p.a_mode != A_STEM, load_b = !p.b_resident;
+            const uint32_t tx = (load_a ? A_STAGE_BYTES : 0u) + (load_b ? b_stage_bytes : 0u);
             const uint32_t sig0 = p.a_mode == A_SCALE ? raw0 : full0;    // A_SCALE: the fix-up warps publish full[]
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
-                for (int kb = 0; kb < num_kb; kb++) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_STAGE_BYTES;
-                    mbar_expect_tx(sig0 + 8 * stage, tx);
-                    if (p.a_mode != A_STEM) tma_load_2d(sa, &map_a, kb * BLOCK_K, m_blk * BLOCK_M, sig0 + 8 * stage);
-                    tma_load_2d(sb, &map_b, kb * BLOCK_K, n_blk * p.n_pad, sig0 + 8 * stage);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (p.b_resident) {                                          // every tile reuses the same W: load it once
+                mbar_expect_tx(bfull, (uint32_t)num_kb * b_stage_bytes);
+                for (int kb = 0; kb < num_kb; kb++) tma_load_2d(b_region + kb * b_stage_bytes, &map_b, kb * BLOCK_K, 0, bfull);
+            }
+            if (tx != 0) {
+                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                    const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
+                    for (int kb = 0; kb < num_kb; kb++) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_STAGE_BYTES;
+                        const bool skip_b = (p.debug & 32) != 0;      // diagnostics only
+                        mbar_expect_tx(sig0 + 8 * stage, skip_b ? tx - b_stage_bytes : tx);
+                        if (load_a) tma_load_2d(sa, &map_a, kb * BLOCK_K, m_blk * BLOCK_M, sig0 + 8 * stage);
+                        if (load_b && !skip_b) tma_load_2d(sb, &map_b, kb * BLOCK_K, n_blk * p.n_pad, sig0 + 8 * stage);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -209,6 +224,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            if (p.b_resident) mbar_wait(bfull, 0);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
@@ -216,7 +232,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = 0; kb < num_kb; kb++) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_STAGE_BYTES;
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint32_t sb = p.b_resident ? b_region + kb * b_stage_bytes : sa + A_STAGE_BYTES;
                     const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
                     const int krem = p.K - kb * BLOCK_K;
                     const int ksteps = krem >= BLOCK_K ? BLOCK_K / 16 : (krem + 15) / 16;
@@ -229,12 +246,12 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 12 && p.a_mode != A_TMA) {
         // ===== staging warps: two groups of 128 threads on alternate k-blocks =====
-        if (p.a_mode != A_TMA) {
+        {
             const int g = (warp - 12) >> 2;
             const int t = threadIdx.x - (12 + 4 * g) * 32;         // 0..127
-            int j = 0;                                             // running k-block index of this CTA
+            int j = 0;                                             // running k-block index of this CTA (p.stages is even: stage parity == group)
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / p.n_blocks) * BLOCK_M;
                 for (int kb = 0; kb < num_kb; kb++, j++) {
@@ -311,12 +328,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: two sets of 4 warps in ping-pong; set s drains accumulator s =====
-        const int set = (warp - 4) >> 2;
+        // ===== epilogue groups of 4 warps (ping-pong over the two accumulators) =====
+        // A_SCALE / A_STEM: groups 0,1 (warps 4-11), each drains a whole accumulator.
+        // A_TMA: groups 0-3 (warps 4-19); group g drains accumulator g&1 and the 64-column blocks of parity g>>1.
+        const bool split = p.a_mode == A_TMA;
+        const int grp = (warp - 4) >> 2;
+        const int set = grp & 1, half = grp >> 1;
         const int q = warp & 3;                                    // TMEM lane quarter (= warp % 4)
         const int row = q * 32 + lane;
         const bool issuer = q == 0 && lane == 0;
-        const uint32_t my_staging = staging + (uint32_t)set * 2u * STAGING_BLOCK_BYTES;
+        // staging: 4 x 16 KB; unsplit groups own two buffers (double-buffered), split groups own one
+        const uint32_t my_staging = staging + (uint32_t)(split ? grp : 2 * set) * STAGING_BLOCK_BYTES;
         const int nblk64 = (p.n_pad + 63) >> 6;
         uint32_t blk_count = 0, acc_phase = 0;
         int it = 0;
@@ -331,15 +353,23 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.n_pad);
             const bool row_ok = m < p.M;
             const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
-            for (int jb = 0; jb < nblk64; jb++, blk_count++) {
-                const uint32_t buf = my_staging + (blk_count & 1u) * STAGING_BLOCK_BYTES;
-                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // this buffer's previous store has been read
-                set_bar_sync(1 + set);
+            for (int jb = split ? half : 0; jb < ((p.debug & 16) ? 0 : nblk64); jb += split ? 2 : 1, blk_count++) {
+                const uint32_t buf = my_staging + (split ? 0u : (blk_count & 1u) * STAGING_BLOCK_BYTES);
+                if (issuer) {                                      // this buffer's previous store has been read
+                    if (split) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
+                set_bar_sync(1 + grp);
                 const int cols_here = min(64, p.n_pad - jb * 64);
                 for (int c32 = 0; c32 < cols_here; c32 += 32) {
                     uint32_t r[32];
                     tc_ld32(taddr + jb * 64 + c32, r);            // columns beyond n_pad read the other accumulator's TMEM: ignored below
                     tc_ld_wait();
+                    if (jb + (split ? 2 : 1) >= nblk64 && c32 + 32 >= cols_here) {     // last TMEM read of this group for this tile:
+                        tc_fence_before();                                              // hand the accumulator back before the math
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * set);
+                    }
 #pragma unroll
                     for (int h = 0; h < 4; h++) {
                         const int col = jb * 64 + c32 + h * 8;     // column inside the tile
@@ -348,10 +378,12 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             float v[8];
                             const float4 b0 = *(const float4*)(sbias + n), b1 = *(const float4*)(sbias + n + 4);
                             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            if (p.act && !(p.debug & 2)) {
 #pragma unroll
-                            for (int jj = 0; jj < 8; jj++) {
-                                v[jj] = __uint_as_float(r[h * 8 + jj]) + bb[jj];
-                                if (p.act) v[jj] = swish_fast(v[jj]);
+                                for (int jj = 0; jj < 8; jj++) v[jj] = swish_fast(__uint_as_float(r[h * 8 + jj]) + bb[jj]);
+                            } else {
+#pragma unroll
+                                for (int jj = 0; jj < 8; jj++) v[jj] = __uint_as_float(r[h * 8 + jj]) + bb[jj];
                             }
                             if (rrow && n + 8 <= p.N) {
                                 const uint4 rv = __ldg((const uint4*)(rrow + n));
@@ -367,17 +399,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                 }
-                if (jb == nblk64 - 1) {                            // accumulator fully read: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8 * set);
-                }
                 fence_async_smem();
-                set_bar_sync(1 + set);
+                set_bar_sync(1 + grp);
                 if (issuer) {
-                    if (n_base + jb * 64 < p.N) tma_store_2d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, buf);
+                    if (n_base + jb * 64 < p.N && !(p.debug & 1)) tma_store_2d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, buf);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+            }
+            if ((split && half >= nblk64) || (p.debug & 16)) {     // no column block for this group: still release the accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * set);
             }
         }
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -420,6 +452,7 @@ static int make_map(dfd_ctx* ctx, CUtensorMap* m, const void* base, uint64_t row
 }
 
 static bool g_enabled = true;
+static int g_debug = 0;
 bool dfd_gemm_bf16_enabled() { return g_enabled; }
 void dfd_gemm_free(dfd_ctx*) {}
 
@@ -433,7 +466,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     DFD_REQUIRE(K % 8 == 0 && N % 8 == 0 && N <= MAX_BIAS, DFD_ERR_INVALID, "gemm: K and N must be multiples of 8, N <= 1280");
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.act = act; p.bias = bias; p.residual = residual;
-    p.a_mode = a_mode; p.A = A; p.se = se; p.hw = hw > 0 ? hw : 1;
+    p.a_mode = a_mode; p.A = A; p.se = se; p.hw = hw > 0 ? hw : 1; p.debug = g_debug;
     // N tiling: the smallest number of equal UMMA-N blocks (multiples of 16, <= 256) covering N
     // (with several N blocks the block width is a multiple of 64 so the 64-column TMA stores of one block
     // never touch its neighbour's columns)
@@ -442,15 +475,24 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     p.n_pad = n_pad; p.n_blocks = (N + n_pad - 1) / n_pad;
     const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     p.num_tiles = m_blocks * p.n_blocks;
-    const int stage_bytes = A_STAGE_BYTES + n_pad * BLOCK_K * 2;
-    const int staging_bytes = 4 * STAGING_BLOCK_BYTES;       // two 16 KB buffers per epilogue set
-    int stages = (204 * 1024 - staging_bytes) / stage_bytes;
-    if (stages > 8) stages = 8;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-    if (stages > 2 * num_kb && stages > 4) stages = 2 * num_kb > 4 ? 2 * num_kb : 4;
+    const int staging_bytes = 4 * STAGING_BLOCK_BYTES;       // two 16 KB buffers per epilogue set
+    // W stays resident in shared memory when it fits next to >= 3 A stages: every tile then loads only A
+    // (measured: 148 CTAs re-fetching the same few KB of W per tile serialise on one L2 slice, 1-2 us per tile)
+    const int b_bytes = num_kb * n_pad * BLOCK_K * 2;
+    p.b_resident = (p.n_blocks == 1 && b_bytes + staging_bytes + 3 * A_STAGE_BYTES <= 204 * 1024) ? 1 : 0;
+    const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : n_pad * BLOCK_K * 2);
+    int stages = (204 * 1024 - staging_bytes - (p.b_resident ? b_bytes : 0)) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (!p.b_resident && stages > 2 * num_kb && stages > 4) stages = 2 * num_kb > 4 ? 2 * num_kb : 4;
+    // The two staging groups take alternate k-blocks.  With an even stage count a stage is always served by the same
+    // group, so every waiter of a stage's mbarriers observes every phase; with an odd count a group would skip every
+    // other phase of a stage and a parity wait could alias with the phase two uses earlier (seen as a rare hang of
+    // b7.project with 3 stages).
+    if (a_mode != A_TMA) stages &= ~1;
     DFD_REQUIRE(stages >= 2, DFD_ERR_INVALID, "gemm: tile does not fit shared memory");
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
@@ -551,5 +593,45 @@ extern "C" int dfd_gemm_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int
         if (max_err_host) *max_err_host = (double)e;
     }
     cudaFree(A); cudaFree(W); cudaFree(R); cudaFree(C); cudaFree(bias); cudaFree(ref); cudaFree(err); cudaFree(se);
+    return rc;
+}
+
+// Times `iters` launches of one GEMM shape (diagnostics for kernel tuning; flags as GemmParams::debug, bit 2 = SE-gated A,
+// bit 3 = residual).  Writes the mean milliseconds per launch to *ms_host.
+extern "C" int dfd_gemm_bench(dfd_ctx* ctx, int M, int N, int K, int act, int flags, int iters, double* ms_host, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = 49, n_img = (M + hw - 1) / hw;
+    __nv_bfloat16 *A, *W, *R, *C;
+    float *bias, *se;
+    DFD_CUDA(cudaMalloc(&A, (size_t)M * K * 2));
+    DFD_CUDA(cudaMalloc(&W, (size_t)N * K * 2 + 4096));
+    DFD_CUDA(cudaMalloc(&R, (size_t)M * N * 2));
+    DFD_CUDA(cudaMalloc(&C, (size_t)M * N * 2));
+    DFD_CUDA(cudaMalloc(&bias, (size_t)(N + 512) * 4));
+    DFD_CUDA(cudaMalloc(&se, (size_t)n_img * K * 4));
+    DFD_CUDA(cudaMemsetAsync(bias, 0, (size_t)(N + 512) * 4, st));
+    k_fill_bf16<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, st>>>(A, (size_t)M * K, 11u, 1.0f);
+    k_fill_bf16<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(W, (size_t)N * K, 22u, 0.25f);
+    k_fill_bf16<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, st>>>(R, (size_t)M * N, 33u, 1.0f);
+    k_fill_f32<<<(unsigned)(((size_t)n_img * K + 255) / 256), 256, 0, st>>>(se, (size_t)n_img * K, 55u, 0.05f, 1.0f);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    g_debug = flags & (3 | 16 | 32);
+    int rc = DFD_OK;
+    for (int i = 0; i < iters + 2 && rc == DFD_OK; i++) {
+        if (i == 2) cudaEventRecord(e0, st);
+        rc = dfd_gemm_bf16_ex(ctx, (flags & 4) ? A_SCALE : A_TMA, A, (flags & 4) ? se : nullptr, hw, W, bias, (flags & 8) ? R : nullptr, C,
+                              M, N, K, act, st);
+    }
+    g_debug = 0;
+    cudaEventRecord(e1, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ce != cudaSuccess) { ctx->err = std::string("gemm bench: ") + cudaGetErrorString(ce); rc = DFD_ERR_CUDA; }
+    if (ms_host) *ms_host = (double)ms / (iters > 0 ? iters : 1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(A); cudaFree(W); cudaFree(R); cudaFree(C); cudaFree(bias); cudaFree(se);
     return rc;
 }

@@ -184,6 +184,34 @@ class Engine:
         self._check(self.lib.dfd_configure_stream(self.h, int(stream_id), int(window_size), int(voting_window),
                                                   float(detection_threshold), self._stream()), "dfd_configure_stream")
 
+    def capture_step(self, frames, stream_ids, full, boxes, box_frame, dtype="bf16", records_out=None, warmup=2):
+        """Capture one dfd_analyze_batch call on fixed device buffers into a CUDA graph (the ~100 kernel launches
+        of a step, including the forensic / classifier fork-join, replay as one submission).  Returns an object
+        with .replay() and .records; the caller refreshes the contents of `frames` / `boxes` between replays."""
+        sid = self._dev(stream_ids, torch.int32)
+        fl = self._dev(full, torch.uint8)
+        bx = self._dev(boxes, torch.int32)
+        bf = self._dev(box_frame, torch.int32)
+        n = frames.shape[0]
+        rec = records_out if records_out is not None else torch.empty(n * _lib.RECORD_BYTES, dtype=torch.uint8, device=self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                 # sizes every workspace and sets kernel attributes before capture
+                self.analyze_batch(frames, sid, fl, bx, bf, dtype=dtype, records_out=rec)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            _, _, fprob = self.analyze_batch(frames, sid, fl, bx, bf, dtype=dtype, records_out=rec)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+
+        class _Step:
+            pass
+        st = _Step()
+        st.graph, st.records, st.face_prob, st.replay = graph, rec, fprob, graph.replay
+        st._keep = (frames, sid, fl, bx, bf, side)
+        return st
+
     def reset(self, stream_id=-1):
         self._check(self.lib.dfd_reset_stream(self.h, int(stream_id), self._stream()), "dfd_reset_stream")
 
@@ -192,6 +220,11 @@ class Engine:
 
     def reset_tracker(self, stream_id):
         self._check(self.lib.dfd_reset_stream_part(self.h, int(stream_id), 2, self._stream()), "dfd_reset_stream_part")
+
+    def gemm_bench(self, M, N, K, act=1, flags=0, iters=10):
+        ms = C.c_double(0.0)
+        self._check(self.lib.dfd_gemm_bench(self.h, M, N, K, act, flags, iters, C.byref(ms), self._stream()), "dfd_gemm_bench")
+        return ms.value
 
     # -- per-kernel timing ------------------------------------------------------------
     def profile_start(self):
