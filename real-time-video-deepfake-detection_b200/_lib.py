@@ -64,6 +64,7 @@ SYMBOLS = {
     "dfd_dbg_face_clahe": (_I, [_P, _P, _I, _I, _S, _I, _P, _P, _I, _P, _P]),
     "dfd_dbg_set_tap": (_I, [_P, C.c_char_p]),
     "dfd_dbg_activation": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),
+    "dfd_dbg_set_option": (_I, [_P, C.c_char_p, _I]),
     "dfd_gemm_selftest": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(C.c_double), _P]),
     "dfd_gemm_bench": (_I, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_double), _P]),
 }

@@ -85,9 +85,12 @@ struct dfd_ctx {
     DfdBuf face_in;                       // prepared crops for analyze_batch
     float* d_pool = nullptr;              // [m][n_parts][C] SE squeeze partial sums (<= DFD_POOL_FLOATS per image)
     float* d_sescale = nullptr;           // [m][1152]
+    int* d_se_count = nullptr;            // [m] finished-CTA counters of the fused SE tail (self-resetting)
     float* d_se_r = nullptr;              // [m][64] squeezed activations between the two SE kernels
     float* d_wxt = nullptr;               // transposed SE expand weights, all blocks
     float* d_feat = nullptr;              // [m][1280]
+    float* d_fc_h1 = nullptr;             // [m][512] classifier hidden layers
+    float* d_fc_h2 = nullptr;             // [m][256]
     float* d_logits = nullptr;            // [m]
     double* d_faceprob = nullptr;         // [m]
     double* d_voteinput = nullptr;        // [n]
@@ -107,6 +110,8 @@ struct dfd_ctx {
     unsigned long long flight_seq = 0;
     std::vector<std::string> flight_names;
     bool trace = false;                   // DFD_TRACE=1: synchronise after every launch and log it (debugging)
+    bool no_fuse_se = false;              // "no_fuse_se": SE excite as the two k_se_* kernels instead of the depthwise kernels' tail
+    bool no_fuse = false;                 // DFD_NO_FUSE=1: expand GEMM + depthwise as two kernels (A/B testing of mbconv_fused.cu)
     bool no_overlap = false;              // DFD_NO_OVERLAP=1: run the forensic kernels on the caller's stream
     const char* label = "";               // set by the launch code before each kernel
     std::vector<cudaEvent_t> prof_events;

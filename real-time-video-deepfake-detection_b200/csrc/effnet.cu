@@ -9,12 +9,13 @@
 //   k_se        SE excite: mean -> reduce FC -> swish -> expand FC -> sigmoid  (one CTA per image)
 //   k_scale     x * se (bf16 mode only; fp32 mode applies the scale while loading A in k_pw)
 //   k_pool      global average pool of the head output
-//   k_fc        custom classifier 1280->512->256->1 (BN1d folded, ReLU)  (one CTA per image)
+//   k_fc_layer  custom classifier 1280->512->256->1 (BN1d folded, ReLU): one launch per layer, 8 images per CTA
 //
 // Activations are float (fp32 mode: true fp32 FMA everywhere, parity 1e-4) or bf16 (storage only;
 // all accumulation in fp32).
 #include "dfd_internal.cuh"
 #include "effnet_plan.h"
+#include "se_tail.cuh"
 #include <string.h>
 #include <type_traits>
 
@@ -25,7 +26,9 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
                      cudaStream_t st);
 bool dfd_gemm_bf16_enabled();
 int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
-                __nv_bfloat16* out, int m, int* n_parts, cudaStream_t st);
+                __nv_bfloat16* out, int m, int* n_parts, const SeTail& se, cudaStream_t st);
+int dfd_mbconv_front_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* x, const __nv_bfloat16* We, const float* be,
+                          const float* Wd, const float* bd, __nv_bfloat16* out, int m, int* n_parts, const SeTail& se, cudaStream_t st);
 
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
 template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
@@ -310,37 +313,44 @@ __global__ void k_pool(const T* __restrict__ x, float* __restrict__ feat, int hw
     feat[(size_t)b * C + c] = s / (float)hw;
 }
 
-__global__ void __launch_bounds__(512) k_fc(const float* __restrict__ feat, const float* __restrict__ W1, const float* __restrict__ b1,
-                                            const float* __restrict__ W2, const float* __restrict__ b2,
-                                            const float* __restrict__ W3, const float* __restrict__ b3, float* __restrict__ logits) {
-    __shared__ float f[1280];
-    __shared__ float h1[512];
-    __shared__ float h2[256];
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 1280; i += 512) f[i] = feat[(size_t)b * 1280 + i];
-    __syncthreads();
-    for (int j = warp; j < 512; j += 16) {
-        float a = 0.f;
-        for (int c = lane; c < 1280; c += 32) a = fmaf(W1[(size_t)j * 1280 + c], f[c], a);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) h1[j] = fmaxf(a + b1[j], 0.f);
+// One layer of the custom classifier (model.py:50-61, BatchNorm1d folded, Dropout = identity in eval):
+//   out[b][j] = act(W[j] . in[b] + bias[j]);  CTA = 8 outputs (one per warp) x FC_IPC images, so a weight row is
+// fetched once per FC_IPC images with coalesced 16-byte loads and every lane keeps FC_IPC accumulators.
+#define FC_IPC 8
+template <int IN>
+__global__ void __launch_bounds__(256) k_fc_layer(const float* __restrict__ in, const float* __restrict__ W,
+                                                  const float* __restrict__ bias, float* __restrict__ out, int J, int m, int relu) {
+    extern __shared__ __align__(16) float s_in[];           // [FC_IPC][IN]
+    const int b0 = blockIdx.y * FC_IPC;
+    for (int e = threadIdx.x; e < FC_IPC * (IN / 4); e += 256) {
+        const int i = e / (IN / 4), c4 = e - i * (IN / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + i < m) v = *(const float4*)(in + (size_t)(b0 + i) * IN + c4 * 4);
+        *(float4*)(s_in + i * IN + c4 * 4) = v;
     }
     __syncthreads();
-    for (int j = warp; j < 256; j += 16) {
-        float a = 0.f;
-        for (int c = lane; c < 512; c += 32) a = fmaf(W2[(size_t)j * 512 + c], h1[c], a);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= J) return;
+    float a[FC_IPC];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) h2[j] = fmaxf(a + b2[j], 0.f);
+    for (int i = 0; i < FC_IPC; i++) a[i] = 0.f;
+    const float4* w4 = (const float4*)(W + (size_t)j * IN);
+#pragma unroll 2
+    for (int c4 = lane; c4 < IN / 4; c4 += 32) {
+        const float4 w = __ldg(w4 + c4);
+#pragma unroll
+        for (int i = 0; i < FC_IPC; i++) {
+            const float4 x = *(const float4*)(s_in + i * IN + c4 * 4);
+            a[i] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, a[i]))));
+        }
     }
-    __syncthreads();
-    if (warp == 0) {
-        float a = 0.f;
-        for (int c = lane; c < 256; c += 32) a = fmaf(W3[c], h2[c], a);
+    const float bj = bias[j];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) logits[b] = a + b3[0];
+    for (int i = 0; i < FC_IPC; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        if (lane == 0 && b0 + i < m) { const float v = a[i] + bj; out[(size_t)(b0 + i) * J + j] = relu ? fmaxf(v, 0.f) : v; }
     }
 }
 
@@ -443,6 +453,7 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
 
     static const char* L_EXP[16] = {"b0.expand", "b1.expand", "b2.expand", "b3.expand", "b4.expand", "b5.expand", "b6.expand", "b7.expand", "b8.expand", "b9.expand", "b10.expand", "b11.expand", "b12.expand", "b13.expand", "b14.expand", "b15.expand"};
     static const char* L_DW[16] = {"b0.dw", "b1.dw", "b2.dw", "b3.dw", "b4.dw", "b5.dw", "b6.dw", "b7.dw", "b8.dw", "b9.dw", "b10.dw", "b11.dw", "b12.dw", "b13.dw", "b14.dw", "b15.dw"};
+    static const char* L_FRONT[16] = {"b0.front", "b1.front", "b2.front", "b3.front", "b4.front", "b5.front", "b6.front", "b7.front", "b8.front", "b9.front", "b10.front", "b11.front", "b12.front", "b13.front", "b14.front", "b15.front"};
     static const char* L_SE[16] = {"b0.se", "b1.se", "b2.se", "b3.se", "b4.se", "b5.se", "b6.se", "b7.se", "b8.se", "b9.se", "b10.se", "b11.se", "b12.se", "b13.se", "b14.se", "b15.se"};
     static const char* L_PROJ[16] = {"b0.project", "b1.project", "b2.project", "b3.project", "b4.project", "b5.project", "b6.project", "b7.project", "b8.project", "b9.project", "b10.project", "b11.project", "b12.project", "b13.project", "b14.project", "b15.project"};
     ctx->label = "stem";
@@ -476,30 +487,51 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         const int Min = m * b.hin * b.hin, Mout = m * b.hout * b.hout;
         const T* dw_in = x;
         T* dw_out;
-        if (b.cexp != b.cin) {
-            ctx->label = L_EXP[i];
-            if ((rc = pw(x, f.we, f.be, nullptr, 0, nullptr, e, Min, b.cexp, b.cin, 1))) return rc;
-            snprintf(nm, sizeof nm, "b%d.expand", i);
-            if ((rc = tap<T>(ctx, nm, e, (size_t)Min * b.cexp, st))) return rc;
-            dw_in = e;
-        }
-        // depthwise output: behind the expand output inside e (sized for block 1), or y for block 0
-        if (b.cexp != b.cin) {
-            dw_out = e + (size_t)Min * b.cexp;
-            size_t need = ((size_t)Min + Mout) * b.cexp * sizeof(T);
-            if (need > ctx->act[2].bytes) { ctx->err = "internal: expanded buffer too small"; return DFD_ERR_CAPACITY; }
-        } else dw_out = y;
-        ctx->label = L_DW[i];
         int n_parts = 1;
-        if constexpr (BF) {
-            if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, &n_parts, st))) return rc;
+        // bf16: expand + depthwise run as ONE kernel (mbconv_fused.cu) and the expanded tensor never reaches HBM;
+        // the two-kernel path remains for the ".expand" diagnostic tap and DFD_NO_FUSE=1 (A/B testing)
+        snprintf(nm, sizeof nm, "b%d.expand", i);
+        const bool fused = tc && b.cexp != b.cin && !ctx->no_fuse && ctx->tap_name != nm;
+        // bf16: the SE excite FCs run in the tail of the depthwise kernel (se_tail.cuh) unless DFD_NO_FUSE asks for k_se_*
+        SeTail se_t;
+        memset(&se_t, 0, sizeof se_t);
+        const bool se_fused = BF && !ctx->no_fuse_se;
+        if (se_fused) {
+            se_t.Wr = Wf + f.wr; se_t.br = Wf + f.br; se_t.WxT = ctx->d_wxt + wxt_off[i]; se_t.bx = Wf + f.bx;
+            se_t.scale = ctx->d_sescale; se_t.counter = ctx->d_se_count; se_t.se = b.se;
+            se_t.inv_hw = 1.0f / (float)(b.hout * b.hout);
+        }
+        if (fused) {
+            if constexpr (BF) {
+                dw_out = e;
+                ctx->label = L_FRONT[i];
+                if ((rc = dfd_mbconv_front_bf16(ctx, b, (const __nv_bfloat16*)x, ctx->d_wbf16 + f.we, Wf + f.be, Wf + f.wd, Wf + f.bd,
+                                                (__nv_bfloat16*)dw_out, m, &n_parts, se_t, st))) return rc;
+            }
         } else {
-            if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, &n_parts, st))) return rc;
+            if (b.cexp != b.cin) {
+                ctx->label = L_EXP[i];
+                if ((rc = pw(x, f.we, f.be, nullptr, 0, nullptr, e, Min, b.cexp, b.cin, 1))) return rc;
+                if ((rc = tap<T>(ctx, nm, e, (size_t)Min * b.cexp, st))) return rc;
+                dw_in = e;
+            }
+            // depthwise output: behind the expand output inside e (sized for block 1), or y for block 0
+            if (b.cexp != b.cin) {
+                dw_out = e + (size_t)Min * b.cexp;
+                size_t need = ((size_t)Min + Mout) * b.cexp * sizeof(T);
+                if (need > ctx->act[2].bytes) { ctx->err = "internal: expanded buffer too small"; return DFD_ERR_CAPACITY; }
+            } else dw_out = y;
+            ctx->label = L_DW[i];
+            if constexpr (BF) {
+                if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, &n_parts, se_t, st))) return rc;
+            } else {
+                if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, &n_parts, st))) return rc;
+            }
         }
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
-        {
+        if (!se_fused) {
             const int mg = (m + SE_IPC - 1) / SE_IPC;
             k_se_reduce<<<dim3((b.se + 7) / 8, mg), 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, ctx->d_se_r, b.cexp,
                                                                   b.se, 1.0f / (float)(b.hout * b.hout), m);
@@ -534,8 +566,19 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             if ((rc = tap<float>(ctx, "features", ctx->d_feat, (size_t)m * 1280, st))) return rc;
         }
         ctx->label = "fc";
-        k_fc<<<m, 512, 0, st>>>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, Wf + o.fc2_w, Wf + o.fc2_b, Wf + o.fc3_w, Wf + o.fc3_b,
-                                logits);
+        {
+            const int mg = (m + FC_IPC - 1) / FC_IPC;
+            static bool attr = false;
+            if (!attr) {
+                DFD_CUDA(cudaFuncSetAttribute(k_fc_layer<1280>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_IPC * 1280 * 4));
+                attr = true;
+            }
+            k_fc_layer<1280><<<dim3(512 / 8, mg), 256, FC_IPC * 1280 * 4, st>>>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, ctx->d_fc_h1, 512, m, 1);
+            DFD_LAUNCH_CHECK("k_fc", st);
+            k_fc_layer<512><<<dim3(256 / 8, mg), 256, FC_IPC * 512 * 4, st>>>(ctx->d_fc_h1, Wf + o.fc2_w, Wf + o.fc2_b, ctx->d_fc_h2, 256, m, 1);
+            DFD_LAUNCH_CHECK("k_fc", st);
+            k_fc_layer<256><<<dim3(1, mg), 256, FC_IPC * 256 * 4, st>>>(ctx->d_fc_h2, Wf + o.fc3_w, Wf + o.fc3_b, logits, 1, m, 0);
+        }
         DFD_LAUNCH_CHECK("k_fc", st);
         ctx->label = "";
     }

@@ -277,6 +277,9 @@ class Engine:
     def set_tap(self, name):
         self._check(self.lib.dfd_dbg_set_tap(self.h, (name or "").encode()), "dfd_dbg_set_tap")
 
+    def set_option(self, name, value):
+        self._check(self.lib.dfd_dbg_set_option(self.h, name.encode(), int(value)), "dfd_dbg_set_option")
+
     def activation(self, name):
         n = self.lib.dfd_dbg_activation(self.h, name.encode(), None, 0, self._stream())
         if n < 0:

@@ -23,6 +23,8 @@ def effnet_bytes(label, m, esz=2, tc=True):
     min_, mout = m * b.hin * b.hin, m * b.hout * b.hout
     if kind == "expand":
         return (min_ * b.cin + min_ * b.cexp) * esz + b.cexp * b.cin * esz
+    if kind == "front":     # fused expand 1x1 + depthwise: block input in, depthwise output out; the expanded tensor stays on chip
+        return (min_ * b.cin + mout * b.cexp) * esz + b.cexp * b.cin * esz + b.k * b.k * b.cexp * 4 + m * b.cexp * 4
     if kind == "dw":
         return (min_ * b.cexp + mout * b.cexp) * esz + b.k * b.k * b.cexp * 4 + m * b.cexp * 4
     if kind == "se":
