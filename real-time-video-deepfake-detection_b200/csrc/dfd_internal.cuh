@@ -85,7 +85,8 @@ struct dfd_ctx {
     DfdBuf face_in;                       // prepared crops for analyze_batch
     float* d_pool = nullptr;              // [m][n_parts][C] SE squeeze partial sums (<= DFD_POOL_FLOATS per image)
     float* d_sescale = nullptr;           // [m][1152]
-    int* d_se_count = nullptr;            // [m] finished-CTA counters of the fused SE tail (self-resetting)
+    float* d_front_aux = nullptr;         // mbconv_fused.cu: per block / chunk packed depthwise weights + biases
+    size_t front_aux_off[16] = {0};
     float* d_se_r = nullptr;              // [m][64] squeezed activations between the two SE kernels
     float* d_wxt = nullptr;               // transposed SE expand weights, all blocks
     float* d_feat = nullptr;              // [m][1280]
@@ -110,7 +111,7 @@ struct dfd_ctx {
     unsigned long long flight_seq = 0;
     std::vector<std::string> flight_names;
     bool trace = false;                   // DFD_TRACE=1: synchronise after every launch and log it (debugging)
-    bool no_fuse_se = false;              // "no_fuse_se": SE excite as the two k_se_* kernels instead of the depthwise kernels' tail
+    int se_mode = 1;                      // bf16 SE excite: 0 = k_se_reduce + k_se_expand, 1 = one k_se_excite launch
     bool no_fuse = false;                 // DFD_NO_FUSE=1: expand GEMM + depthwise as two kernels (A/B testing of mbconv_fused.cu)
     bool no_overlap = false;              // DFD_NO_OVERLAP=1: run the forensic kernels on the caller's stream
     const char* label = "";               // set by the launch code before each kernel

@@ -14,7 +14,6 @@
 //      (image, tile, channel) -- no atomics, so the forward pass is bit-reproducible; k_se adds the partials.
 #include "dfd_internal.cuh"
 #include "effnet_plan.h"
-#include "se_tail.cuh"
 
 #define DW_WARPS 8
 
@@ -45,8 +44,7 @@ __device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
 template <int K, int S, int TW, int TH, int CC>
 __global__ void __launch_bounds__(DW_WARPS * 32)
 k_dw_tile(const __nv_bfloat16* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
-          __nv_bfloat16* __restrict__ out, float* __restrict__ pool, int C, int hin, int hout, int pad, int tiles_x,
-          const SeTail se) {
+          __nv_bfloat16* __restrict__ out, float* __restrict__ pool, int C, int hin, int hout, int pad, int tiles_x) {
     constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
     constexpr int LP = CC / 2;                     // lanes (32-bit words) per pixel
     constexpr int RW = 32 / LP;                    // output rows per warp pass
@@ -128,12 +126,11 @@ k_dw_tile(const __nv_bfloat16* __restrict__ in, const float* __restrict__ W, con
         for (int wv = 0; wv < DW_WARPS * RW; wv++) sacc += spool[wv * CC + tid];
         pool[((size_t)b * gridDim.x + tile) * C + c0 + tid] = sacc;
     }
-    if (se.counter) se_tail_run(se, pool, gridDim.x, C, b, (float*)smem_dw);     // last CTA of the image: SE excite FCs
 }
 
 template <int K, int S, int TW, int TH, int CC>
 static int launch(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
-                  __nv_bfloat16* out, int m, int* n_parts, SeTail se, cudaStream_t st) {
+                  __nv_bfloat16* out, int m, int* n_parts, cudaStream_t st) {
     constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
     constexpr int PWP = (CC == 32 && (PW % 2 == 0)) ? PW + 1 : PW;
     constexpr int RW = 64 / CC;
@@ -147,26 +144,25 @@ static int launch(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, cons
     dim3 grid(tiles_x * tiles_y, (b.cexp + CC - 1) / CC, m);
     *n_parts = tiles_x * tiles_y;
     if ((size_t)grid.x * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
-    se.ctas_per_image = (int)(grid.x * grid.y);
-    k_dw_tile<K, S, TW, TH, CC><<<grid, DW_WARPS * 32, smem, st>>>(in, W, bias, out, ctx->d_pool, b.cexp, b.hin, b.hout, b.pad, tiles_x, se);
+    k_dw_tile<K, S, TW, TH, CC><<<grid, DW_WARPS * 32, smem, st>>>(in, W, bias, out, ctx->d_pool, b.cexp, b.hin, b.hout, b.pad, tiles_x);
     DFD_LAUNCH_CHECK("k_dw_tile", st);
     return DFD_OK;
 }
 
 int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
-                __nv_bfloat16* out, int m, int* n_parts, const SeTail& se, cudaStream_t st) {
+                __nv_bfloat16* out, int m, int* n_parts, cudaStream_t st) {
     // tile shapes per output size: 112 (C=32) -> 16x16 with 32-channel CTAs, 56 -> 8x14, 28 / 14 -> 7x14, 7 -> 7x7
-    if (b.k == 3 && b.s == 1 && b.hout == 112) return launch<3, 1, 16, 16, 32>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 3 && b.s == 2 && b.hout == 56) return launch<3, 2, 14, 8, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 56) return launch<3, 1, 14, 8, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 5 && b.s == 2 && b.hout == 28) return launch<5, 2, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 28) return launch<5, 1, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 3 && b.s == 2 && b.hout == 14) return launch<3, 2, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 14) return launch<3, 1, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 14) return launch<5, 1, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 5 && b.s == 2 && b.hout == 7) return launch<5, 2, 7, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 7) return launch<5, 1, 7, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 7) return launch<3, 1, 7, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, se, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 112) return launch<3, 1, 16, 16, 32>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 2 && b.hout == 56) return launch<3, 2, 14, 8, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 56) return launch<3, 1, 14, 8, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 2 && b.hout == 28) return launch<5, 2, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 28) return launch<5, 1, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 2 && b.hout == 14) return launch<3, 2, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 14) return launch<3, 1, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 14) return launch<5, 1, 14, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 2 && b.hout == 7) return launch<5, 2, 7, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 5 && b.s == 1 && b.hout == 7) return launch<5, 1, 7, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
+    if (b.k == 3 && b.s == 1 && b.hout == 7) return launch<3, 1, 7, 7, 64>(ctx, b, in, W, bias, out, m, n_parts, st);
     ctx->err = "dw_bf16: no tile configuration for this layer";
     return DFD_ERR_INVALID;
 }

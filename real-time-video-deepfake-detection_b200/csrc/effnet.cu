@@ -15,7 +15,6 @@
 // all accumulation in fp32).
 #include "dfd_internal.cuh"
 #include "effnet_plan.h"
-#include "se_tail.cuh"
 #include <string.h>
 #include <type_traits>
 
@@ -26,9 +25,10 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
                      cudaStream_t st);
 bool dfd_gemm_bf16_enabled();
 int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
-                __nv_bfloat16* out, int m, int* n_parts, const SeTail& se, cudaStream_t st);
-int dfd_mbconv_front_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* x, const __nv_bfloat16* We, const float* be,
-                          const float* Wd, const float* bd, __nv_bfloat16* out, int m, int* n_parts, const SeTail& se, cudaStream_t st);
+                __nv_bfloat16* out, int m, int* n_parts, cudaStream_t st);
+int dfd_mbconv_front_bf16(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __nv_bfloat16* We, __nv_bfloat16* out, int m,
+                          int* n_parts, cudaStream_t st);
+int dfd_front_pack(dfd_ctx* ctx, const float* blob);
 
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
 template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
@@ -288,6 +288,67 @@ __global__ void __launch_bounds__(256) k_se_expand(const float* __restrict__ rbu
         if (b0 + i < m) scale[(size_t)(b0 + i) * C + c] = sigmoidf(a[i]);
 }
 
+// SE excite in ONE launch (bf16 path): CTA = SE_X_IPC images; squeeze partials -> mean -> reduce FC -> swish -> expand FC
+// -> sigmoid.  Weight rows are read once per CTA with 16-byte loads and shared by the CTA's images.
+#define SE_X_IPC 2
+__global__ void __launch_bounds__(256) k_se_excite(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr,
+                                                   const float* __restrict__ br, const float* __restrict__ WxT,
+                                                   const float* __restrict__ bx, float* __restrict__ scale, int C, int se,
+                                                   float inv_hw, int m) {
+    __shared__ __align__(16) float mean[SE_X_IPC][1152];
+    __shared__ float r[SE_X_IPC][64];
+    const int b0 = blockIdx.x * SE_X_IPC;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < SE_X_IPC * C; e += 256) {
+        const int i = e / C, c = e - i * C, b = b0 + i;
+        float a = 0.f;
+        if (b < m) {
+            const float* pp = pool + (size_t)b * n_parts * C + c;
+#pragma unroll 4
+            for (int q = 0; q < n_parts; q++) a += pp[(size_t)q * C];
+        }
+        mean[i][c] = a * inv_hw;
+    }
+    __syncthreads();
+    for (int j = warp; j < se; j += 8) {
+        const float4* w4 = (const float4*)(Wr + (size_t)j * C);
+        float a[SE_X_IPC];
+#pragma unroll
+        for (int i = 0; i < SE_X_IPC; i++) a[i] = 0.f;
+#pragma unroll 3
+        for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+            const float4 w = __ldg(w4 + c4);
+#pragma unroll
+            for (int i = 0; i < SE_X_IPC; i++) {
+                const float4 x = *(const float4*)&mean[i][c4 * 4];
+                a[i] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, a[i]))));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SE_X_IPC; i++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+            if (lane == 0) r[i][j] = swishf(a[i] + br[j]);
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        float a[SE_X_IPC];
+        const float bc = bx[c];
+#pragma unroll
+        for (int i = 0; i < SE_X_IPC; i++) a[i] = bc;
+#pragma unroll 4
+        for (int j = 0; j < se; j++) {
+            const float w = __ldg(WxT + (size_t)j * C + c);
+#pragma unroll
+            for (int i = 0; i < SE_X_IPC; i++) a[i] = fmaf(w, r[i][j], a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < SE_X_IPC; i++)
+            if (b0 + i < m) scale[(size_t)(b0 + i) * C + c] = sigmoidf(a[i]);
+    }
+}
+
 // x *= se[img][c]   (bf16 mode: produces the A operand of the project GEMM)
 __global__ void __launch_bounds__(256) k_scale(__nv_bfloat16* __restrict__ x, const float* __restrict__ se, int C, int hw,
                                                size_t total_vec) {
@@ -393,6 +454,7 @@ int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n) {
     for (int n = 0; n < 32; n++)
         for (int k = 0; k < 32; k++) wg[n * 32 + k] = __float2bfloat16_rn(k < 27 ? blob[o.stem_w + (size_t)k * 32 + n] : 0.f);
     DFD_CUDA(cudaMemcpy(ctx->d_stem_wg, wg.data(), wg.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    { int rc = dfd_front_pack(ctx, blob); if (rc) return rc; }
     ctx->w_floats = o.total;
     ctx->has_weights = true;
     return DFD_OK;
@@ -492,21 +554,12 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         // the two-kernel path remains for the ".expand" diagnostic tap and DFD_NO_FUSE=1 (A/B testing)
         snprintf(nm, sizeof nm, "b%d.expand", i);
         const bool fused = tc && b.cexp != b.cin && !ctx->no_fuse && ctx->tap_name != nm;
-        // bf16: the SE excite FCs run in the tail of the depthwise kernel (se_tail.cuh) unless DFD_NO_FUSE asks for k_se_*
-        SeTail se_t;
-        memset(&se_t, 0, sizeof se_t);
-        const bool se_fused = BF && !ctx->no_fuse_se;
-        if (se_fused) {
-            se_t.Wr = Wf + f.wr; se_t.br = Wf + f.br; se_t.WxT = ctx->d_wxt + wxt_off[i]; se_t.bx = Wf + f.bx;
-            se_t.scale = ctx->d_sescale; se_t.counter = ctx->d_se_count; se_t.se = b.se;
-            se_t.inv_hw = 1.0f / (float)(b.hout * b.hout);
-        }
         if (fused) {
             if constexpr (BF) {
                 dw_out = e;
                 ctx->label = L_FRONT[i];
-                if ((rc = dfd_mbconv_front_bf16(ctx, b, (const __nv_bfloat16*)x, ctx->d_wbf16 + f.we, Wf + f.be, Wf + f.wd, Wf + f.bd,
-                                                (__nv_bfloat16*)dw_out, m, &n_parts, se_t, st))) return rc;
+                if ((rc = dfd_mbconv_front_bf16(ctx, i, (const __nv_bfloat16*)x, ctx->d_wbf16 + f.we, (__nv_bfloat16*)dw_out, m,
+                                                &n_parts, st))) return rc;
             }
         } else {
             if (b.cexp != b.cin) {
@@ -523,7 +576,7 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             } else dw_out = y;
             ctx->label = L_DW[i];
             if constexpr (BF) {
-                if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, &n_parts, se_t, st))) return rc;
+                if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, &n_parts, st))) return rc;
             } else {
                 if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, &n_parts, st))) return rc;
             }
@@ -531,7 +584,12 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
-        if (!se_fused) {
+        if (BF && ctx->se_mode != 0) {
+            k_se_excite<<<(m + SE_X_IPC - 1) / SE_X_IPC, 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, ctx->d_wxt + wxt_off[i],
+                                                                        Wf + f.bx, ctx->d_sescale, b.cexp, b.se,
+                                                                        1.0f / (float)(b.hout * b.hout), m);
+            DFD_LAUNCH_CHECK("k_se_excite", st);
+        } else {
             const int mg = (m + SE_IPC - 1) / SE_IPC;
             k_se_reduce<<<dim3((b.se + 7) / 8, mg), 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, ctx->d_se_r, b.cexp,
                                                                   b.se, 1.0f / (float)(b.hout * b.hout), m);

@@ -6,48 +6,55 @@
 //                                                                                         + SE squeeze partials
 //
 // The expanded tensor is 6x the block input and, layer by layer, was written once and read once: 14.4 MB of the
-// 27.4 MB/img layer-granular traffic.  Here it never leaves the SM: a CTA owns (image, TH x TW output tile,
-// CC-channel chunk), fetches the input patch with ONE 4-D TMA box per 64 input channels (zero fill outside the
-// image), multiplies it by the chunk's expand weights with tcgen05.mma (M = 128 patch pixels per instruction,
-// N = CC, K = cin), reads the accumulators back with tcgen05.ld, applies bias + swish, forces TF-"SAME" padding
-// pixels to zero (the reference pads the EXPANDED tensor) and leaves the bf16 patch in shared memory, where the
-// depthwise stage of dwconv_bf16.cu runs on it unchanged (lane = channel pair, warp = output row).
-// The halo is recomputed per tile; results are bit-identical to the unfused expand GEMM + k_dw_tile pair.
+// 27.4 MB/img layer-granular traffic.  Here it never leaves the SM.
 //
-// WHOLE = the tile is the whole output image (14x14 and 7x7 stages): only the hin x hin real pixels go through
-// the MMA and the padding ring of the patch is zero-filled directly.
+// Persistent, warp-specialised CTAs (320 threads, 2 per SM).  Work item = (image, TH x TW output tile); inside an
+// item the CC-wide channel chunks of the expanded tensor are produced and consumed one after the other:
+//   warp 0      producer: one 4-D TMA box per 64 input channels fetches the item's input patch (zero fill outside the
+//               image) into an A slot; per chunk a 2-D TMA box fetches the expand weights [CC][cin] and one bulk copy
+//               the chunk's packed depthwise weights + both biases into a 2-deep B ring.
+//   warp 1      MMA issuer: per chunk and per 128-pixel block of the patch, tcgen05.mma (M=128, N=CC, K=cin) into a
+//               4-deep ring of TMEM accumulators; tcgen05.commit publishes accumulators and frees smem slots.
+//   warps 2-9   consumers: tcgen05.ld (lane quarter = warp % 4, column half = warp group) -> + bias, swish, padding
+//               pixels forced to zero (the reference pads the EXPANDED tensor) -> bf16 patch in shared memory; then the
+//               depthwise stage of dwconv_bf16.cu on that patch (lane = channel pair, warp = output row, fp32x2 FMAs),
+//               swish, bf16 stores, per-channel squeeze partials (fixed order: deterministic).
+// So the TMA latency, the MMA and the TMEM drain of chunk c+1 hide behind the depthwise math of chunk c.
+// The halo is recomputed per tile.  The depthwise output is bit-identical to the unfused expand GEMM + k_dw_tile pair.
+//
+// WHOLE = the tile is the whole output image (14x14 and 7x7 stages): only the hin x hin real pixels go through the
+// MMA, the patch has no padding ring and the depthwise loops skip out-of-image taps instead.
 #include "dfd_internal.cuh"
 #include "effnet_plan.h"
 #include "tc_ptx.cuh"
-#include "se_tail.cuh"
 
-#define MF_THREADS 256
-#define MF_WARPS 8
-#define MF_PITCH_W 36            // 32-bit words per patch pixel: 128 B of channels + 16 B pad (conflict-free 16-byte stores)
+#define MF_THREADS 320
+#define MF_CWARPS 8               // consumer warps
+#define MF_NT 4                   // TMEM accumulator ring depth (128-row blocks)
+#define MF_NB 2                   // B ring depth (chunks)
 
 int dfd_tmap_bf16(dfd_ctx* ctx, CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 
 struct FrontParams {
-    const float* be;             // expand bias [C]
-    const float* Wd;             // depthwise weights [K*K][C]
-    const float* bd;             // depthwise bias [C]
+    const float* aux;            // packed per chunk: Wd[K*K][CC], 0.5*be[CC], bd[CC]
     __nv_bfloat16* out;          // [m][hout][hout][C]
     float* pool;                 // [m][tiles][C] SE squeeze partials
-    int C, cin, hin, hout, pad, tiles_x, num_kb;
-    SeTail se;                   // SE excite run by the last CTA of each image
+    int C, cin, hin, hout, tiles_x, tiles, num_kb, n_chunks, n_items, na;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ void mf_ffma2(uint64_t& d, uint64_t a, uint64_t b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
@@ -64,216 +71,339 @@ __device__ __forceinline__ uint32_t mf_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *(uint32_t*)&h;
 }
-
-constexpr int mf_pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+__device__ __forceinline__ uint64_t mf_fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mf_add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float mf_tanh(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+}
+// swish of two values with packed fp32 math: h = 0.5*x (+ hb = 0.5*bias), y = h + h*tanh(h).  Bit-identical to
+// swish_fast(x + bias): scaling by 0.5 is exact, so fma(x, 0.5, 0.5*b) rounds once exactly like (x + b) * 0.5.
+__device__ __forceinline__ uint64_t mf_swish2(uint64_t x, uint64_t half_bias) {
+    const uint64_t h = mf_fma2(x, mf_pack2(0.5f, 0.5f), half_bias);
+    float h0, h1;
+    mf_unpack2(h, h0, h1);
+    const uint64_t t = mf_pack2(mf_tanh(h0), mf_tanh(h1));
+    return mf_fma2(h, t, h);
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE>
 struct MfGeom {
-    static constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
-    static constexpr int NPIX = PH * PW;                         // patch pixels
-    static constexpr int BOX_W = WHOLE ? HIN : PW, BOX_H = WHOLE ? HIN : PH;
-    static constexpr int ROWS = BOX_W * BOX_H;                   // MMA rows that carry data
-    static constexpr int N_MB = (ROWS + 127) / 128;
-    static constexpr int TM_COLS = mf_pow2_cols(N_MB * CC);
-    static constexpr int A_KB_BYTES = N_MB * 128 * 128;          // one 64-channel k-block of the A operand
-    static constexpr int B_KB_BYTES = CC * 128;
-    static constexpr int PATCH_BYTES = NPIX * MF_PITCH_W * 4;
-    static constexpr int TAIL_FLOATS = K * K * CC + CC + MF_WARPS * CC;    // dw weights, expand bias, squeeze partials
-    static int region_bytes(int num_kb) {
-        int a = num_kb * A_KB_BYTES;
-        int r = a > PATCH_BYTES ? a : PATCH_BYTES;
-        return (r + 1023) & ~1023;
+    static constexpr int HOUT = (HIN + S - 1) / S;
+    static constexpr int PAD_TOTAL = (HOUT - 1) * S + K - HIN > 0 ? (HOUT - 1) * S + K - HIN : 0;
+    static constexpr int PAD = PAD_TOTAL / 2;                    // TF-"SAME": the smaller half goes in front
+    static constexpr int PH = WHOLE ? HIN : (TH - 1) * S + K, PW = WHOLE ? HIN : (TW - 1) * S + K;
+    static constexpr int NPIX = PH * PW;                         // patch pixels = MMA rows that carry data
+    static constexpr int N_MB = (NPIX + 127) / 128;
+    static constexpr int A_KB_BYTES = (NPIX * 128 + 1023) & ~1023;   // one 64-channel k-block of the A operand (tight)
+    static constexpr int AUX_FLOATS = (K * K + 2) * CC;          // Wd chunk, be chunk, bd chunk
+    static constexpr int AUX_BYTES = (AUX_FLOATS * 4 + 127) & ~127;
+    static constexpr int PITCH = CC * 2 + 16;                    // patch bytes per pixel (+16: conflict-free 16-byte stores)
+    static constexpr int PATCH_BYTES = (NPIX * PITCH + 127) & ~127;
+    static constexpr int TM_COLS = MF_NT * CC <= 128 ? 128 : 256;
+    static int b_stage_bytes(int num_kb) { return (num_kb * CC * 128 + AUX_BYTES + 1023) & ~1023; }
+    // (the MMA of the last 128-row block reads N_MB*128 rows from each k-block base; the overrun past the tight
+    //  A slots lands in the B ring / patch that follow them inside the same allocation: garbage rows, never used)
+    static size_t smem_bytes(int num_kb, int na) {
+        return 1024 + (size_t)na * num_kb * A_KB_BYTES + (size_t)MF_NB * b_stage_bytes(num_kb) + PATCH_BYTES + MF_CWARPS * CC * 4 + 256;
     }
-    static size_t smem_bytes(int num_kb) { return 1024 + (size_t)region_bytes(num_kb) + (size_t)num_kb * B_KB_BYTES + (size_t)TAIL_FLOATS * 4; }
 };
 
 template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE>
-__global__ void __launch_bounds__(MF_THREADS)
+__global__ void __launch_bounds__(MF_THREADS, 2)
 k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FrontParams p) {
     using G = MfGeom<K, S, TW, TH, CC, HIN, WHOLE>;
-    constexpr int PW = G::PW, NPIX = G::NPIX, ROWS = G::ROWS, N_MB = G::N_MB;
+    constexpr int PW = G::PW, NPIX = G::NPIX, N_MB = G::N_MB, PITCH = G::PITCH, PITCH_W = G::PITCH / 4, PAD = G::PAD;
     extern __shared__ __align__(1024) uint8_t smem_mf[];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[2 + 2 + MF_NB * 2 + MF_NT * 2];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
-    const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-    const int oy0 = ty * TH, ox0 = tx * TW;
-    const int c0 = chunk * CC;
-    const int iy0 = oy0 * S - p.pad, ix0 = ox0 * S - p.pad;
+    const uint32_t s0 = smem_u32(smem_mf);
+    const uint32_t a_base = (s0 + 1023u) & ~1023u;
+    const int a_slot_bytes = p.num_kb * G::A_KB_BYTES;
+    const int b_stage = (p.num_kb * CC * 128 + G::AUX_BYTES + 1023) & ~1023;
+    const uint32_t b_base = a_base + (uint32_t)(p.na * a_slot_bytes);
+    const uint32_t patch_s = b_base + (uint32_t)(MF_NB * b_stage);
+    uint8_t* gen = smem_mf + (a_base - s0);
+    const uint8_t* b_gen = gen + p.na * a_slot_bytes;
+    uint32_t* patch = (uint32_t*)(gen + p.na * a_slot_bytes + MF_NB * b_stage);
+    float* spool = (float*)((uint8_t*)patch + G::PATCH_BYTES);           // [MF_CWARPS][CC]
+    const int aux_off = p.num_kb * CC * 128;                              // aux block inside a B stage
 
-    const uint32_t region = (smem_u32(smem_mf) + 1023u) & ~1023u;
-    int rb = p.num_kb * G::A_KB_BYTES; if (rb < G::PATCH_BYTES) rb = G::PATCH_BYTES; rb = (rb + 1023) & ~1023;
-    const uint32_t bsm = region + (uint32_t)rb;
-    uint8_t* gen_base = smem_mf + (region - smem_u32(smem_mf));
-    uint32_t* patch = (uint32_t*)gen_base;                                  // aliases the A operand once the MMAs have retired
-    float* sw = (float*)(gen_base + rb + p.num_kb * G::B_KB_BYTES);         // [K*K][CC]
-    float* sbe = sw + K * K * CC;                                           // [CC]
-    float* spool = sbe + CC;                                                // [MF_WARPS][CC]
-    const uint32_t bar_tma = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    const uint32_t a_full = bar0, a_empty = bar0 + 16, b_full = bar0 + 32, b_empty = b_full + 8 * MF_NB;
+    const uint32_t t_full = b_empty + 8 * MF_NB, t_empty = t_full + 8 * MF_NT;
 
-    if (tid == 0) {                                  // the input patch + weight chunk are requested before anything else
-        mbar_init(bar_tma, 1); mbar_init(bar_mma, 1);
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+        for (int i = 0; i < MF_NB; i++) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 2); }
+        for (int i = 0; i < MF_NT; i++) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, MF_CWARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_tma, (uint32_t)p.num_kb * (uint32_t)(ROWS * 128 + G::B_KB_BYTES));
-        for (int kb = 0; kb < p.num_kb; kb++) {
-            tma_load_4d(region + kb * G::A_KB_BYTES, &map_x, kb * 64, WHOLE ? 0 : ix0, WHOLE ? 0 : iy0, b, bar_tma);
-            tma_load_2d(bsm + kb * G::B_KB_BYTES, &map_w, kb * 64, c0, bar_tma);
-        }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(G::TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < K * K * CC; i += MF_THREADS) {
-        const int c = c0 + (i % CC);
-        sw[i] = c < p.C ? p.Wd[(size_t)(i / CC) * p.C + c] : 0.f;
-    }
-    if (tid < CC) sbe[tid] = c0 + tid < p.C ? p.be[c0 + tid] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    // ---- one thread: wait for the TMA data, then issue every MMA of the tile ----
     if (warp == 0) {
+        // ===== producer =====
         if (lane == 0) {
-            mbar_wait(bar_tma, 0);
-            tc_fence_after();
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int b = item / p.tiles, tile = item - b * p.tiles;
+                const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+                const int iy0 = WHOLE ? 0 : ty * TH * S - PAD, ix0 = WHOLE ? 0 : tx * TW * S - PAD;
+                mbar_wait_backoff(a_empty + 8 * as, aph ^ 1, 64);
+                mbar_expect_tx(a_full + 8 * as, (uint32_t)(p.num_kb * NPIX * 128));
+                for (int kb = 0; kb < p.num_kb; kb++)
+                    tma_load_4d(a_base + as * a_slot_bytes + kb * G::A_KB_BYTES, &map_x, kb * 64, ix0, iy0, b, a_full + 8 * as);
+                if (++as == p.na) { as = 0; aph ^= 1; }
+                for (int ch = 0; ch < p.n_chunks; ch++) {
+                    mbar_wait_backoff(b_empty + 8 * bs, bph ^ 1, 64);
+                    const uint32_t dst = b_base + bs * b_stage;
+                    mbar_expect_tx(b_full + 8 * bs, (uint32_t)(p.num_kb * CC * 128 + G::AUX_FLOATS * 4));
+                    for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(dst + kb * CC * 128, &map_w, kb * 64, ch * CC, b_full + 8 * bs);
+                    bulk_load(dst + aux_off, p.aux + (size_t)ch * G::AUX_FLOATS, G::AUX_FLOATS * 4, b_full + 8 * bs);
+                    if (++bs == MF_NB) { bs = 0; bph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int ts = 0; uint32_t tph = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                mbar_wait_backoff(a_full + 8 * as, aph, 32);
+                tc_fence_after();
+                const uint32_t a_slot = a_base + as * a_slot_bytes;
+                for (int ch = 0; ch < p.n_chunks; ch++) {
+                    mbar_wait_backoff(b_full + 8 * bs, bph, 32);
+                    tc_fence_after();
+                    const uint32_t bsm = b_base + bs * b_stage;
 #pragma unroll 1
-            for (int mb = 0; mb < N_MB; mb++) {
-                for (int kb = 0; kb < p.num_kb; kb++) {
-                    const uint64_t adesc = make_smem_desc(region + kb * G::A_KB_BYTES + mb * 16384);
-                    const uint64_t bdesc = make_smem_desc(bsm + kb * G::B_KB_BYTES);
-                    const int krem = p.cin - kb * 64;
-                    const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
-                    for (int k = 0; k < ksteps; k++)
-                        tc_mma_bf16(tmem_base + (uint32_t)(mb * CC), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    for (int mb = 0; mb < N_MB; mb++) {
+                        mbar_wait_backoff(t_empty + 8 * ts, tph ^ 1, 32);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(ts * CC);
+                        for (int kb = 0; kb < p.num_kb; kb++) {
+                            const uint64_t adesc = make_smem_desc(a_slot + kb * G::A_KB_BYTES + mb * 16384);
+                            const uint64_t bdesc = make_smem_desc(bsm + kb * CC * 128);
+                            const int krem = p.cin - kb * 64;
+                            const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
+                            for (int k = 0; k < ksteps; k++)
+                                tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        }
+                        tc_commit(t_full + 8 * ts);
+                        if (++ts == MF_NT) { ts = 0; tph ^= 1; }
+                    }
+                    tc_commit(b_empty + 8 * bs);               // weights of this chunk consumed by the tensor core
+                    if (++bs == MF_NB) { bs = 0; bph ^= 1; }
                 }
-            }
-            tc_commit(bar_mma);
-        }
-        __syncwarp();
-    }
-    mbar_wait(bar_mma, 0);
-    tc_fence_after();
-
-    // ---- TMEM -> bias + swish -> bf16 patch in shared memory (padding pixels = 0) ----
-    const uint32_t patch_s = region;
-    if (WHOLE) {                                     // padding ring of the patch
-        for (int pix = tid; pix < NPIX; pix += MF_THREADS) {
-            const int py = pix / PW, px = pix - py * PW;
-            const int iy = py - p.pad, ix = px - p.pad;
-            if (iy < 0 || iy >= HIN || ix < 0 || ix >= HIN) {
-#pragma unroll
-                for (int j = 0; j < CC / 8; j++) sts128(patch_s + (uint32_t)(pix * (MF_PITCH_W * 4) + j * 16), make_uint4(0, 0, 0, 0));
+                tc_commit(a_empty + 8 * as);                   // every MMA reading this patch has retired
+                if (++as == p.na) { as = 0; aph ^= 1; }
             }
         }
-    }
-    {
-        const int q = warp & 3, pair = warp >> 2;
-        constexpr int NG = CC / 16;
-        for (int u = pair; u < N_MB * NG; u += 2) {
-            const int mb = u / NG, g = u - mb * NG;
-            if (mb * 128 + q * 32 >= ROWS) continue;                  // warp-uniform: no data rows in this lane quarter
-            const int r = mb * 128 + q * 32 + lane;
-            uint32_t v[16];
-            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * CC + g * 16), v);
-            tc_ld_wait();
-            bool inimg; int pp;
-            if (WHOLE) {
-                const int iy = r / HIN, ix = r - iy * HIN;
-                inimg = true;
-                pp = (iy + p.pad) * PW + ix + p.pad;
-            } else {
-                const int py = r / PW, px = r - py * PW;
-                const int iy = iy0 + py, ix = ix0 + px;
-                inimg = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.hin;
-                pp = r;
-            }
-            if (r < ROWS) {
-                uint32_t o[8];
+    } else {
+        // ===== consumers: TMEM -> patch, depthwise, stores =====
+        const int cw = warp - 2;                               // 0..7
+        const int ctid = tid - 64;                             // 0..255
+        const int q = warp & 3, hsel = cw >> 2;                // TMEM lane quarter (hardware: warp % 4), column half
+        constexpr int HC = CC / 2, NP = HC / 8;                // columns per warp, x8 pieces
+        const int pl = lane < CC / 2 ? lane : CC / 2 - 1;
+        int bs = 0; uint32_t bph = 0; int ts = 0; uint32_t tph = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int b = item / p.tiles, tile = item - b * p.tiles;
+            const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+            const int oy0 = ty * TH, ox0 = tx * TW;
+            const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
+            for (int chn = 0; chn < p.n_chunks; chn++) {
+                const int c0 = chn * CC;
+                mbar_wait(b_full + 8 * bs, bph);               // aux block (dw weights + biases) landed
+                const float* aux = (const float*)(b_gen + bs * b_stage + aux_off);
+                const float* sw = aux;                         // [K*K][CC]
+                const float* sbe = aux + K * K * CC;           // [CC] 0.5 * expand bias
+                const float* sbd = sbe + CC;                   // [CC]
+                // ---- epilogue of the expand GEMM: accumulator blocks -> bf16 patch ----
+#pragma unroll 1
+                for (int mb = 0; mb < N_MB; mb++) {
+                    mbar_wait(t_full + 8 * ts, tph);
+                    tc_fence_after();
+                    const int rowbase = mb * 128 + q * 32;
+                    const bool active = rowbase < NPIX;        // warp-uniform
+                    uint32_t v[NP][8];
+                    if (active) {
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * CC + hsel * HC);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float2 bb = *(const float2*)(sbe + g * 16 + 2 * j);
-                    const float a0 = swish_fast(__uint_as_float(v[2 * j]) + bb.x);
-                    const float a1 = swish_fast(__uint_as_float(v[2 * j + 1]) + bb.y);
-                    o[j] = inimg ? mf_bf16x2(a0, a1) : 0u;
+                        for (int i = 0; i < NP; i++) tc_ld8(taddr + i * 8, v[i]);
+                        tc_ld_wait();
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + 8 * ts);          // accumulator drained: hand it back before the math
+                    if (++ts == MF_NT) { ts = 0; tph ^= 1; }
+                    const int r = rowbase + lane;
+                    if (active && r < NPIX) {
+                        bool inimg = true;
+                        if (!WHOLE) {
+                            const int py = r / PW, px = r - py * PW;
+                            const int iy = iy0 + py, ix = ix0 + px;
+                            inimg = iy >= 0 && iy < HIN && ix >= 0 && ix < HIN;
+                        }
+                        const uint32_t dst = patch_s + (uint32_t)(r * PITCH + hsel * HC * 2);
+#pragma unroll
+                        for (int i = 0; i < NP; i++) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint64_t hb = *(const uint64_t*)(sbe + hsel * HC + i * 8 + 2 * j);      // 0.5 * bias pair
+                                const uint64_t y = mf_swish2(mf_pack2(__uint_as_float(v[i][2 * j]), __uint_as_float(v[i][2 * j + 1])), hb);
+                                float a0, a1;
+                                mf_unpack2(y, a0, a1);
+                                o[j] = inimg ? mf_bf16x2(a0, a1) : 0u;
+                            }
+                            sts128(dst + i * 16, make_uint4(o[0], o[1], o[2], o[3]));
+                        }
+                    }
                 }
-                const uint32_t dst = patch_s + (uint32_t)(pp * (MF_PITCH_W * 4) + g * 32);
-                sts128(dst, make_uint4(o[0], o[1], o[2], o[3]));
-                sts128(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
+                consumer_sync();
+                // ---- depthwise kxk + bias + swish + squeeze partials (lane = channel pair, warp = output row) ----
+                const int ch = c0 + 2 * pl;
+                const bool ch_ok = lane < CC / 2 && ch < p.C;
+                const uint64_t bias2 = *(const uint64_t*)(sbd + 2 * pl);
+                uint64_t ps = 0ull;
+                for (int r = cw; r < TH; r += MF_CWARPS) {
+                    const int oy = oy0 + r;
+                    if (oy >= p.hout) break;
+                    uint64_t acc[TW];
+#pragma unroll
+                    for (int i = 0; i < TW; i++) acc[i] = bias2;
+#pragma unroll
+                    for (int ky = 0; ky < K; ky++) {
+                        const int prow_i = WHOLE ? r * S + ky - PAD : r * S + ky;       // patch row
+                        if (WHOLE && (prow_i < 0 || prow_i >= HIN)) continue;           // warp-uniform: padding row
+                        uint64_t w[K];
+#pragma unroll
+                        for (int kx = 0; kx < K; kx++) w[kx] = *(const uint64_t*)(sw + (ky * K + kx) * CC + 2 * pl);
+                        const uint32_t* prow = patch + (size_t)(prow_i * PW) * PITCH_W + pl;
+#pragma unroll
+                        for (int ix = 0; ix < PW; ix++) {
+                            const uint32_t v = prow[ix * PITCH_W];
+                            const uint64_t x = mf_pack2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+                            // patch column ix feeds output column ox through tap kx when ox*S + kx - OFF == ix
+                            // (OFF = PAD when the patch is the bare image, 0 when the patch carries its own halo)
+                            constexpr int OFF = WHOLE ? PAD : 0;
+#pragma unroll
+                            for (int kx = 0; kx < K; kx++) {
+                                const int t = ix + OFF - kx;
+                                if (t >= 0 && t % S == 0 && t / S < TW) mf_ffma2(acc[t / S], x, w[kx]);
+                            }
+                        }
+                    }
+                    __nv_bfloat16* orow = p.out + (((size_t)b * p.hout + oy) * p.hout + ox0) * p.C + ch;
+#pragma unroll
+                    for (int i = 0; i < TW; i++) {
+                        if (ox0 + i < p.hout && ch_ok) {
+                            const uint64_t y = mf_swish2(acc[i], 0ull);
+                            ps = mf_add2(ps, y);
+                            float y0, y1;
+                            mf_unpack2(y, y0, y1);
+                            *(__nv_bfloat162*)(orow + (size_t)i * p.C) = __floats2bfloat162_rn(y0, y1);
+                        }
+                    }
+                }
+                float ps0, ps1;
+                mf_unpack2(ps, ps0, ps1);
+                if (lane < CC / 2) { spool[cw * CC + 2 * lane] = ps0; spool[cw * CC + 2 * lane + 1] = ps1; }
+                consumer_sync();                               // patch + aux reads done, squeeze partials complete
+                if (ctid < CC && c0 + ctid < p.C) {            // deterministic: fixed-order sum, one partial per (image, tile, channel)
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int wv = 0; wv < MF_CWARPS; wv++) sacc += spool[wv * CC + ctid];
+                    p.pool[((size_t)b * p.tiles + tile) * p.C + c0 + ctid] = sacc;
+                }
+                if (ctid == 0) mbar_arrive(b_empty + 8 * bs);  // (the tensor core's commit is the other arrival)
+                if (++bs == MF_NB) { bs = 0; bph ^= 1; }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {                                 // the accumulators are drained: free TMEM for the next CTA on this SM
+    if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TM_COLS) : "memory");
     }
+}
 
-    // ---- depthwise kxk + bias + swish + SE squeeze partials (lane = channel pair, warp = output row) ----
-    const int pl = lane < CC / 2 ? lane : CC / 2 - 1;
-    const int ch = c0 + 2 * pl;
-    const bool ch_ok = lane < CC / 2 && ch < p.C;
-    const uint64_t bias2 = ch_ok ? mf_pack2(p.bd[ch], p.bd[ch + 1]) : mf_pack2(0.f, 0.f);
-    float ps0 = 0.f, ps1 = 0.f;
-    for (int r = warp; r < TH; r += MF_WARPS) {
-        const int oy = oy0 + r;
-        if (oy >= p.hout) break;
-        uint64_t acc[TW];
-#pragma unroll
-        for (int i = 0; i < TW; i++) acc[i] = bias2;
-#pragma unroll
-        for (int ky = 0; ky < K; ky++) {
-            uint64_t w[K];
-#pragma unroll
-            for (int kx = 0; kx < K; kx++) w[kx] = *(const uint64_t*)(sw + (ky * K + kx) * CC + 2 * pl);
-            const uint32_t* prow = patch + (size_t)((r * S + ky) * PW) * MF_PITCH_W + pl;
-#pragma unroll
-            for (int ix = 0; ix < PW; ix++) {
-                const uint32_t v = prow[ix * MF_PITCH_W];
-                const uint64_t x = mf_pack2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
-#pragma unroll
-                for (int kx = 0; kx < K; kx++)
-                    if ((ix - kx) % S == 0 && (ix - kx) >= 0 && (ix - kx) / S < TW) mf_ffma2(acc[(ix - kx) / S], x, w[kx]);
-            }
-        }
-        __nv_bfloat16* orow = p.out + (((size_t)b * p.hout + oy) * p.hout + ox0) * p.C + ch;
-#pragma unroll
-        for (int i = 0; i < TW; i++) {
-            if (ox0 + i < p.hout && ch_ok) {
-                float y0, y1;
-                mf_unpack2(acc[i], y0, y1);
-                y0 = swish_fast(y0); y1 = swish_fast(y1);
-                ps0 += y0; ps1 += y1;
-                *(__nv_bfloat162*)(orow + (size_t)i * p.C) = __floats2bfloat162_rn(y0, y1);
+// ---------------------------------------------------------------------------------------------
+// chunk width per block: 48 divides every expanded width (96 .. 672) exactly; 1152 = 18 x 64
+static int front_cc(int blk) { return EFF_BLOCKS[blk].cexp == 1152 ? 64 : 48; }
+
+// Packs, per block and per chunk, the depthwise weights and both biases into one contiguous bulk-copy source.
+int dfd_front_pack(dfd_ctx* ctx, const float* blob) {
+    const EffOffsets o = eff_offsets();
+    size_t tot = 0;
+    for (int i = 1; i < 16; i++) {
+        const EffBlock& b = EFF_BLOCKS[i];
+        const int cc = front_cc(i), nch = (b.cexp + cc - 1) / cc;
+        ctx->front_aux_off[i] = tot;
+        tot += (size_t)nch * (b.k * b.k + 2) * cc;
+        tot = (tot + 31) & ~(size_t)31;               // 128-byte aligned blocks
+    }
+    std::vector<float> h(tot, 0.f);
+    for (int i = 1; i < 16; i++) {
+        const EffBlock& b = EFF_BLOCKS[i];
+        const EffBlockOff& f = o.blk[i];
+        const int cc = front_cc(i), nch = (b.cexp + cc - 1) / cc, kk = b.k * b.k;
+        for (int ch = 0; ch < nch; ch++) {
+            float* dst = h.data() + ctx->front_aux_off[i] + (size_t)ch * (kk + 2) * cc;
+            for (int j = 0; j < cc; j++) {
+                const int c = ch * cc + j;
+                if (c >= b.cexp) continue;
+                for (int t = 0; t < kk; t++) dst[t * cc + j] = blob[f.wd + (size_t)t * b.cexp + c];
+                dst[kk * cc + j] = 0.5f * blob[f.be + c];          // the epilogue's swish works on h = 0.5 * (acc + bias)
+                dst[(kk + 1) * cc + j] = blob[f.bd + c];
             }
         }
     }
-    if (lane < CC / 2) { spool[warp * CC + 2 * lane] = ps0; spool[warp * CC + 2 * lane + 1] = ps1; }
-    __syncthreads();
-    if (tid < CC && c0 + tid < p.C) {                // deterministic: fixed-order sum, one partial per (image, tile, channel)
-        float sacc = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < MF_WARPS; wv++) sacc += spool[wv * CC + tid];
-        p.pool[((size_t)b * gridDim.x + tile) * p.C + c0 + tid] = sacc;
-    }
-    if (p.se.counter) se_tail_run(p.se, p.pool, gridDim.x, p.C, b, (float*)patch);
+    if (!ctx->d_front_aux) DFD_CUDA(cudaMalloc(&ctx->d_front_aux, tot * sizeof(float)));
+    DFD_CUDA(cudaMemcpy(ctx->d_front_aux, h.data(), tot * sizeof(float), cudaMemcpyHostToDevice));
+    return DFD_OK;
 }
 
 template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE>
-static int launch_front(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* x, const __nv_bfloat16* We, const float* be,
-                        const float* Wd, const float* bd, __nv_bfloat16* out, int m, int* n_parts, const SeTail& se, cudaStream_t st) {
+static int launch_front(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __nv_bfloat16* We, __nv_bfloat16* out, int m,
+                        int* n_parts, cudaStream_t st) {
     using G = MfGeom<K, S, TW, TH, CC, HIN, WHOLE>;
+    const EffBlock& b = EFF_BLOCKS[blk];
+    DFD_REQUIRE(G::PAD == b.pad && G::HOUT == b.hout && front_cc(blk) == CC, DFD_ERR_INVALID, "mbconv_front: geometry mismatch");
     const int num_kb = (b.cin + 63) / 64;
-    const size_t smem = G::smem_bytes(num_kb);
+    // two A slots when two CTAs still fit one SM, else one
+    const size_t budget = 112 * 1024;
+    const int na = G::smem_bytes(num_kb, 2) <= budget ? 2 : 1;
+    const size_t smem = G::smem_bytes(num_kb, na);
     static size_t attr_bytes = 0;
     if (smem > attr_bytes) {
         DFD_CUDA(cudaFuncSetAttribute(k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // two CTAs per SM need the full shared-memory carve-out (the driver's default picks a smaller one)
+        DFD_CUDA(cudaFuncSetAttribute(k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_bytes = smem;
     }
     CUtensorMap mx, mw;
@@ -281,7 +411,7 @@ static int launch_front(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* x,
     {
         const uint64_t dims[4] = {(uint64_t)b.cin, (uint64_t)b.hin, (uint64_t)b.hin, (uint64_t)m};
         const uint64_t str[3] = {(uint64_t)b.cin * 2, (uint64_t)b.hin * b.cin * 2, (uint64_t)b.hin * b.hin * b.cin * 2};
-        const uint32_t box[4] = {64, (uint32_t)G::BOX_W, (uint32_t)G::BOX_H, 1};
+        const uint32_t box[4] = {64, (uint32_t)G::PW, (uint32_t)G::PH, 1};
         if ((rc = dfd_tmap_bf16(ctx, &mx, x, 4, dims, str, box))) return rc;
     }
     {
@@ -291,31 +421,35 @@ static int launch_front(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* x,
         if ((rc = dfd_tmap_bf16(ctx, &mw, We, 2, dims, str, box))) return rc;
     }
     FrontParams p;
-    p.be = be; p.Wd = Wd; p.bd = bd; p.out = out; p.pool = ctx->d_pool;
-    p.C = b.cexp; p.cin = b.cin; p.hin = b.hin; p.hout = b.hout; p.pad = b.pad; p.num_kb = num_kb;
+    p.aux = ctx->d_front_aux + ctx->front_aux_off[blk];
+    p.out = out; p.pool = ctx->d_pool;
+    p.C = b.cexp; p.cin = b.cin; p.hin = b.hin; p.hout = b.hout; p.num_kb = num_kb; p.na = na;
     const int tiles_x = (b.hout + TW - 1) / TW, tiles_y = (b.hout + TH - 1) / TH;
-    p.tiles_x = tiles_x;
-    dim3 grid(tiles_x * tiles_y, (b.cexp + CC - 1) / CC, m);
-    *n_parts = tiles_x * tiles_y;
-    if ((size_t)grid.x * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
-    p.se = se; p.se.ctas_per_image = (int)(grid.x * grid.y);
+    p.tiles_x = tiles_x; p.tiles = tiles_x * tiles_y;
+    p.n_chunks = (b.cexp + CC - 1) / CC;
+    p.n_items = m * p.tiles;
+    *n_parts = p.tiles;
+    if ((size_t)p.tiles * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
+    int grid = 2 * ctx->sm_count;
+    if (grid > p.n_items) grid = p.n_items;
     k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE><<<grid, MF_THREADS, smem, st>>>(mx, mw, p);
     DFD_LAUNCH_CHECK("k_mbconv_front", st);
     return DFD_OK;
 }
 
-// Expand 1x1 + depthwise of block `b` (cexp != cin) in one kernel.  x: block input, We: bf16 expand weights [cexp][cin].
-int dfd_mbconv_front_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* x, const __nv_bfloat16* We, const float* be,
-                          const float* Wd, const float* bd, __nv_bfloat16* out, int m, int* n_parts, const SeTail& se, cudaStream_t st) {
-#define MF_ARGS ctx, b, x, We, be, Wd, bd, out, m, n_parts, se, st
+// Expand 1x1 + depthwise of block `blk` (cexp != cin) in one kernel.  x: block input, We: bf16 expand weights [cexp][cin].
+int dfd_mbconv_front_bf16(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __nv_bfloat16* We, __nv_bfloat16* out, int m,
+                          int* n_parts, cudaStream_t st) {
+    const EffBlock& b = EFF_BLOCKS[blk];
+#define MF_ARGS ctx, blk, x, We, out, m, n_parts, st
     if (b.k == 3 && b.s == 2 && b.hin == 112) return launch_front<3, 2, 7, 8, 48, 112, false>(MF_ARGS);
     if (b.k == 3 && b.s == 1 && b.hin == 56) return launch_front<3, 1, 14, 14, 48, 56, false>(MF_ARGS);
     if (b.k == 5 && b.s == 2 && b.hin == 56) return launch_front<5, 2, 7, 7, 48, 56, false>(MF_ARGS);
-    if (b.k == 5 && b.s == 1 && b.hin == 28) return launch_front<5, 1, 14, 14, 64, 28, false>(MF_ARGS);
-    if (b.k == 3 && b.s == 2 && b.hin == 28) return launch_front<3, 2, 7, 7, 64, 28, false>(MF_ARGS);
-    if (b.k == 3 && b.s == 1 && b.hin == 14) return launch_front<3, 1, 14, 14, 64, 14, true>(MF_ARGS);
-    if (b.k == 5 && b.s == 1 && b.hin == 14) return launch_front<5, 1, 14, 14, 64, 14, true>(MF_ARGS);
-    if (b.k == 5 && b.s == 2 && b.hin == 14) return launch_front<5, 2, 7, 7, 64, 14, true>(MF_ARGS);
+    if (b.k == 5 && b.s == 1 && b.hin == 28) return launch_front<5, 1, 14, 14, 48, 28, false>(MF_ARGS);
+    if (b.k == 3 && b.s == 2 && b.hin == 28) return launch_front<3, 2, 7, 7, 48, 28, false>(MF_ARGS);
+    if (b.k == 3 && b.s == 1 && b.hin == 14) return launch_front<3, 1, 14, 14, 48, 14, true>(MF_ARGS);
+    if (b.k == 5 && b.s == 1 && b.hin == 14) return launch_front<5, 1, 14, 14, 48, 14, true>(MF_ARGS);
+    if (b.k == 5 && b.s == 2 && b.hin == 14) return launch_front<5, 2, 7, 7, 48, 14, true>(MF_ARGS);
     if (b.k == 5 && b.s == 1 && b.hin == 7) return launch_front<5, 1, 7, 7, 64, 7, true>(MF_ARGS);
     if (b.k == 3 && b.s == 1 && b.hin == 7) return launch_front<3, 1, 7, 7, 64, 7, true>(MF_ARGS);
 #undef MF_ARGS
