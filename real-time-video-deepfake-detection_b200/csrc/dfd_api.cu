@@ -175,6 +175,7 @@ int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
     ctx->flight = getenv("DFD_FLIGHT") != nullptr;
     ctx->no_overlap = getenv("DFD_NO_OVERLAP") != nullptr;
     ctx->no_fuse = getenv("DFD_NO_FUSE") != nullptr;
+    ctx->pdl = getenv("DFD_NO_PDL") == nullptr;
     if (getenv("DFD_SE_MODE")) ctx->se_mode = atoi(getenv("DFD_SE_MODE"));
     int rc = create_impl(ctx);
     if (rc) { g_create_err = ctx->err; dfd_destroy(ctx); *out = nullptr; return rc; }
@@ -350,6 +351,7 @@ int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value) {
     if (!ctx || !name) return DFD_ERR_INVALID;
     const std::string n = name;
     if (n == "no_fuse") ctx->no_fuse = value != 0;
+    else if (n == "pdl") ctx->pdl = value != 0;
     else if (n == "se_mode") ctx->se_mode = value;
     else if (n == "no_overlap") ctx->no_overlap = value != 0;
     else { ctx->err = "dbg_set_option: unknown option " + n; return DFD_ERR_INVALID; }

@@ -111,7 +111,8 @@ struct dfd_ctx {
     unsigned long long flight_seq = 0;
     std::vector<std::string> flight_names;
     bool trace = false;                   // DFD_TRACE=1: synchronise after every launch and log it (debugging)
-    int se_mode = 1;                      // bf16 SE excite: 0 = k_se_reduce + k_se_expand, 1 = one k_se_excite launch
+    int se_mode = 2;                      // bf16 SE excite: 0 = k_se_reduce + k_se_expand, 1 = k_se_excite (CTA per 4 images), 2 = k_se_cluster (8-CTA clusters, DSMEM)
+    bool pdl = true;                      // programmatic dependent launch between the tcgen05 / SE kernels (DFD_NO_PDL=1 or "pdl" option = 0 disables)
     bool no_fuse = false;                 // DFD_NO_FUSE=1: expand GEMM + depthwise as two kernels (A/B testing of mbconv_fused.cu)
     bool no_overlap = false;              // DFD_NO_OVERLAP=1: run the forensic kernels on the caller's stream
     const char* label = "";               // set by the launch code before each kernel
@@ -153,6 +154,26 @@ void dfd_flight_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st);
     } while (0)
 
 int dfd_ensure(dfd_ctx* ctx, DfdBuf& b, size_t bytes);
+
+// Programmatic dependent launch (PDL): the kernel may become resident while its predecessor in the stream is still
+// draining, run its prologue (barrier init, TMEM allocation, descriptor prefetch, weight loads) and block in
+// griddepcontrol.wait until the predecessor's memory is visible.  EVERY kernel launched this way executes
+// pdl_wait() before it reads or writes anything another kernel touches -- that keeps completion transitive along the
+// stream -- and pdl_trigger() right after its prologue.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dfd_launch(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // forensics.cu
 int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride, int row_pitch,

@@ -17,6 +17,8 @@
 #include "effnet_plan.h"
 #include <string.h>
 #include <type_traits>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 int dfd_gemm_bf16(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
                   const __nv_bfloat16* residual, __nv_bfloat16* C, int M, int N, int K, int act, cudaStream_t st);
@@ -289,39 +291,55 @@ __global__ void __launch_bounds__(256) k_se_expand(const float* __restrict__ rbu
 }
 
 // SE excite in ONE launch (bf16 path): CTA = SE_X_IPC images; squeeze partials -> mean -> reduce FC -> swish -> expand FC
-// -> sigmoid.  Weight rows are read once per CTA with 16-byte loads and shared by the CTA's images.
-#define SE_X_IPC 2
-__global__ void __launch_bounds__(256) k_se_excite(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr,
-                                                   const float* __restrict__ br, const float* __restrict__ WxT,
-                                                   const float* __restrict__ bx, float* __restrict__ scale, int C, int se,
-                                                   float inv_hw, int m) {
+// -> sigmoid.  The two FCs are latency-bound chains of L2 weight reads, so every loop keeps 8-16 independent
+// 16-byte / 4-byte loads in flight per lane and the weights are shared by the CTA's images.
+#define SE_X_IPC 4
+#define SE_X_THREADS 512
+__global__ void __launch_bounds__(SE_X_THREADS) k_se_excite(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr,
+                                                            const float* __restrict__ br, const float* __restrict__ WxT,
+                                                            const float* __restrict__ bx, float* __restrict__ scale, int C, int se,
+                                                            float inv_hw, int m) {
     __shared__ __align__(16) float mean[SE_X_IPC][1152];
     __shared__ float r[SE_X_IPC][64];
     const int b0 = blockIdx.x * SE_X_IPC;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int e = tid; e < SE_X_IPC * C; e += 256) {
+    for (int e = tid; e < SE_X_IPC * C; e += SE_X_THREADS) {
         const int i = e / C, c = e - i * C, b = b0 + i;
         float a = 0.f;
         if (b < m) {
             const float* pp = pool + (size_t)b * n_parts * C + c;
-#pragma unroll 4
-            for (int q = 0; q < n_parts; q++) a += pp[(size_t)q * C];
+            int q = 0;
+            for (; q + 8 <= n_parts; q += 8) {                 // fixed order, 8 loads in flight
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = pp[(size_t)(q + u) * C];
+#pragma unroll
+                for (int u = 0; u < 8; u++) a += v[u];
+            }
+            for (; q < n_parts; q++) a += pp[(size_t)q * C];
         }
         mean[i][c] = a * inv_hw;
     }
     __syncthreads();
-    for (int j = warp; j < se; j += 8) {
+    // reduce FC: warp per squeeze channel j; a lane reads C/128 float4 of the weight row (<= 9), all issued up front
+    for (int j = warp; j < se; j += SE_X_THREADS / 32) {
         const float4* w4 = (const float4*)(Wr + (size_t)j * C);
+        const int n4 = C >> 2;
+        float4 w[9];
+#pragma unroll
+        for (int u = 0; u < 9; u++) { const int c4 = lane + 32 * u; w[u] = c4 < n4 ? __ldg(w4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f); }
         float a[SE_X_IPC];
 #pragma unroll
         for (int i = 0; i < SE_X_IPC; i++) a[i] = 0.f;
-#pragma unroll 3
-        for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
-            const float4 w = __ldg(w4 + c4);
 #pragma unroll
-            for (int i = 0; i < SE_X_IPC; i++) {
-                const float4 x = *(const float4*)&mean[i][c4 * 4];
-                a[i] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, a[i]))));
+        for (int u = 0; u < 9; u++) {
+            const int c4 = lane + 32 * u;
+            if (c4 < n4) {
+#pragma unroll
+                for (int i = 0; i < SE_X_IPC; i++) {
+                    const float4 x = *(const float4*)&mean[i][c4 * 4];
+                    a[i] = fmaf(w[u].x, x.x, fmaf(w[u].y, x.y, fmaf(w[u].z, x.z, fmaf(w[u].w, x.w, a[i]))));
+                }
             }
         }
 #pragma unroll
@@ -332,20 +350,153 @@ __global__ void __launch_bounds__(256) k_se_excite(const float* __restrict__ poo
         }
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 256) {
-        float a[SE_X_IPC];
-        const float bc = bx[c];
+    // expand FC: a thread owns up to three channels (C <= 1152 < 3 * 512) and walks the squeeze channels 8 at a time
+    // with all 24 weight loads issued before the FMAs
+    {
+        float a[3][SE_X_IPC];
 #pragma unroll
-        for (int i = 0; i < SE_X_IPC; i++) a[i] = bc;
-#pragma unroll 4
-        for (int j = 0; j < se; j++) {
-            const float w = __ldg(WxT + (size_t)j * C + c);
+        for (int k = 0; k < 3; k++) {
+            const int c = tid + SE_X_THREADS * k;
+            const float bc = c < C ? bx[c] : 0.f;
 #pragma unroll
-            for (int i = 0; i < SE_X_IPC; i++) a[i] = fmaf(w, r[i][j], a[i]);
+            for (int i = 0; i < SE_X_IPC; i++) a[k][i] = bc;
+        }
+        for (int j0 = 0; j0 < se; j0 += 8) {
+            float w[3][8];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int c = tid + SE_X_THREADS * k;
+#pragma unroll
+                for (int u = 0; u < 8; u++) w[k][u] = (c < C && j0 + u < se) ? __ldg(WxT + (size_t)(j0 + u) * C + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (j0 + u < se) {
+#pragma unroll
+                    for (int i = 0; i < SE_X_IPC; i++) {
+                        const float rv = r[i][j0 + u];
+#pragma unroll
+                        for (int k = 0; k < 3; k++) a[k][i] = fmaf(w[k][u], rv, a[k][i]);
+                    }
+                }
+            }
         }
 #pragma unroll
-        for (int i = 0; i < SE_X_IPC; i++)
-            if (b0 + i < m) scale[(size_t)(b0 + i) * C + c] = sigmoidf(a[i]);
+        for (int k = 0; k < 3; k++) {
+            const int c = tid + SE_X_THREADS * k;
+            if (c < C) {
+#pragma unroll
+                for (int i = 0; i < SE_X_IPC; i++)
+                    if (b0 + i < m) scale[(size_t)(b0 + i) * C + c] = sigmoidf(a[k][i]);
+            }
+        }
+    }
+}
+
+// SE excite on a thread-block CLUSTER (bf16 path, default): 8 CTAs share 8 images.  Each CTA owns 1/8 of the
+// channels for the squeeze mean and the expand FC and 1/8 of the squeeze channels for the reduce FC, so a CTA reads only
+// 1/8 of each weight matrix; the means and the reduced activations are exchanged through distributed shared memory
+// (remote stores + cluster.sync).  One launch per block, latency of a few microseconds at batch 1 and 256 alike.
+#define SE_CL 8
+__global__ void __cluster_dims__(SE_CL, 1, 1) __launch_bounds__(256)
+k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr, const float* __restrict__ br,
+             const float* __restrict__ WxT, const float* __restrict__ bx, float* __restrict__ scale, int C, int se,
+             float inv_hw, int m) {
+    __shared__ __align__(16) float mean[SE_CL][1152];
+    __shared__ float r[SE_CL][64];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = (blockIdx.x / SE_CL) * SE_CL;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Cs = C / SE_CL;                                   // every expanded width is a multiple of 8
+    pdl_trigger();
+    pdl_wait();
+    float* mean_rem[SE_CL];
+    float* r_rem[SE_CL];
+#pragma unroll
+    for (int d = 0; d < SE_CL; d++) {
+        mean_rem[d] = cluster.map_shared_rank(&mean[0][0], d);
+        r_rem[d] = cluster.map_shared_rank(&r[0][0], d);
+    }
+    // phase 1: squeeze means of this CTA's channel slice for the 8 images -> every CTA of the cluster
+    for (int e = tid; e < SE_CL * Cs; e += 256) {
+        const int i = e / Cs, c = rank * Cs + (e - i * Cs), b = b0 + i;
+        float a = 0.f;
+        if (b < m) {
+            const float* pp = pool + (size_t)b * n_parts * C + c;
+            int q = 0;
+            for (; q + 8 <= n_parts; q += 8) {                 // fixed order, 8 loads in flight
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = pp[(size_t)(q + u) * C];
+#pragma unroll
+                for (int u = 0; u < 8; u++) a += v[u];
+            }
+            for (; q < n_parts; q++) a += pp[(size_t)q * C];
+        }
+        a *= inv_hw;
+#pragma unroll
+        for (int d = 0; d < SE_CL; d++) mean_rem[d][i * 1152 + c] = a;
+    }
+    cluster.sync();
+    // phase 2: reduce FC for squeeze channel j = rank + 8 * warp, all 8 images
+    {
+        const int j = rank + SE_CL * warp;
+        if (j < se) {
+            const float4* w4 = (const float4*)(Wr + (size_t)j * C);
+            const int n4 = C >> 2;
+            float4 w[9];
+#pragma unroll
+            for (int u = 0; u < 9; u++) { const int c4 = lane + 32 * u; w[u] = c4 < n4 ? __ldg(w4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f); }
+            float a[SE_CL];
+#pragma unroll
+            for (int i = 0; i < SE_CL; i++) a[i] = 0.f;
+#pragma unroll
+            for (int u = 0; u < 9; u++) {
+                const int c4 = lane + 32 * u;
+                if (c4 < n4) {
+#pragma unroll
+                    for (int i = 0; i < SE_CL; i++) {
+                        const float4 x = *(const float4*)&mean[i][c4 * 4];
+                        a[i] = fmaf(w[u].x, x.x, fmaf(w[u].y, x.y, fmaf(w[u].z, x.z, fmaf(w[u].w, x.w, a[i]))));
+                    }
+                }
+            }
+            const float bj = br[j];
+#pragma unroll
+            for (int i = 0; i < SE_CL; i++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+            }
+            if (lane < SE_CL) {                                 // lane d publishes the 8 values to CTA d
+#pragma unroll
+                for (int i = 0; i < SE_CL; i++) r_rem[lane][i * 64 + j] = swishf(a[i] + bj);
+            }
+        }
+    }
+    cluster.sync();
+    // phase 3: expand FC + sigmoid for this CTA's channel slice
+    for (int e = tid; e < 2 * Cs; e += 256) {                   // two threads per channel: images 0-3 / 4-7
+        const int half = e / Cs, c = rank * Cs + (e - half * Cs);
+        float a[4];
+        const float bc = bx[c];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = bc;
+        for (int j0 = 0; j0 < se; j0 += 16) {
+            float w[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) w[u] = j0 + u < se ? __ldg(WxT + (size_t)(j0 + u) * C + c) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                if (j0 + u < se) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) a[i] = fmaf(w[u], r[half * 4 + i][j0 + u], a[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (b0 + half * 4 + i < m) scale[(size_t)(b0 + half * 4 + i) * C + c] = sigmoidf(a[i]);
     }
 }
 
@@ -584,8 +735,15 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
-        if (BF && ctx->se_mode != 0) {
-            k_se_excite<<<(m + SE_X_IPC - 1) / SE_X_IPC, 256, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, ctx->d_wxt + wxt_off[i],
+        if (BF && ctx->se_mode == 3) {
+            // timing experiment only (DFD_SE_MODE=3): no SE excite at all, gates stay whatever they were
+        } else if (BF && ctx->se_mode == 2) {
+            DFD_CUDA(dfd_launch(ctx->pdl, k_se_cluster, dim3((m + SE_CL - 1) / SE_CL * SE_CL), dim3(256), 0, st, (const float*)ctx->d_pool, n_parts,
+                                (const float*)(Wf + f.wr), (const float*)(Wf + f.br), (const float*)(ctx->d_wxt + wxt_off[i]),
+                                (const float*)(Wf + f.bx), ctx->d_sescale, b.cexp, b.se, 1.0f / (float)(b.hout * b.hout), m));
+            DFD_LAUNCH_CHECK("k_se_cluster", st);
+        } else if (BF && ctx->se_mode != 0) {
+            k_se_excite<<<(m + SE_X_IPC - 1) / SE_X_IPC, SE_X_THREADS, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, ctx->d_wxt + wxt_off[i],
                                                                         Wf + f.bx, ctx->d_sescale, b.cexp, b.se,
                                                                         1.0f / (float)(b.hout * b.hout), m);
             DFD_LAUNCH_CHECK("k_se_excite", st);

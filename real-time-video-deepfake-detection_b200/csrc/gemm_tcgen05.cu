@@ -107,6 +107,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
+    // PDL: everything above (and the resident weight load below: static data) overlaps the predecessor's tail
+    if (warp == 0 && lane == 0 && p.b_resident) {                    // every tile reuses the same W: load it once
+        mbar_expect_tx(bfull, (uint32_t)num_kb * b_stage_bytes);
+        for (int kb = 0; kb < num_kb; kb++) tma_load_2d(b_region + kb * b_stage_bytes, &map_b, kb * BLOCK_K, 0, bfull);
+    }
+    pdl_trigger();
+    pdl_wait();
+
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
@@ -114,10 +122,6 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool load_a = p.a_mode != A_STEM, load_b = !p.b_resident;
             const uint32_t tx = (load_a ? A_STAGE_BYTES : 0u) + (load_b ? b_stage_bytes : 0u);
             const uint32_t sig0 = p.a_mode == A_SCALE ? raw0 : full0;    // A_SCALE: the fix-up warps publish full[]
-            if (p.b_resident) {                                          // every tile reuses the same W: load it once
-                mbar_expect_tx(bfull, (uint32_t)num_kb * b_stage_bytes);
-                for (int kb = 0; kb < num_kb; kb++) tma_load_2d(b_region + kb * b_stage_bytes, &map_b, kb * BLOCK_K, 0, bfull);
-            }
             if (tx != 0) {
                 for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                     const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
@@ -434,7 +438,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     if ((rc = make_map(ctx, &mb, W, (uint64_t)N, (uint64_t)K, (uint32_t)n_pad))) return rc;
     if ((rc = make_map(ctx, &mc, C, (uint64_t)M, (uint64_t)N, BLOCK_M))) return rc;
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    k_gemm_tcgen05<<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mc, p);
+    DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
     DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);
     return DFD_OK;
 }

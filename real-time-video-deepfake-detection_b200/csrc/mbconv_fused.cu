@@ -41,6 +41,7 @@ struct FrontParams {
     __nv_bfloat16* out;          // [m][hout][hout][C]
     float* pool;                 // [m][tiles][C] SE squeeze partials
     int C, cin, hin, hout, tiles_x, tiles, num_kb, n_chunks, n_items, na;
+    int csplit, cpi;             // small batches: an (image, tile) is split into csplit items of cpi chunks each
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -161,13 +162,17 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_trigger();                                             // PDL: the prologue above overlapped the predecessor's tail
+    pdl_wait();
 
     if (warp == 0) {
         // ===== producer =====
         if (lane == 0) {
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int b = item / p.tiles, tile = item - b * p.tiles;
+                const int it = item / p.csplit, cs = item - it * p.csplit;
+                const int ch_lo = cs * p.cpi, ch_hi = min(p.n_chunks, ch_lo + p.cpi);
+                const int b = it / p.tiles, tile = it - b * p.tiles;
                 const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
                 const int iy0 = WHOLE ? 0 : ty * TH * S - PAD, ix0 = WHOLE ? 0 : tx * TW * S - PAD;
                 mbar_wait_backoff(a_empty + 8 * as, aph ^ 1, 64);
@@ -175,7 +180,7 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 for (int kb = 0; kb < p.num_kb; kb++)
                     tma_load_4d(a_base + as * a_slot_bytes + kb * G::A_KB_BYTES, &map_x, kb * 64, ix0, iy0, b, a_full + 8 * as);
                 if (++as == p.na) { as = 0; aph ^= 1; }
-                for (int ch = 0; ch < p.n_chunks; ch++) {
+                for (int ch = ch_lo; ch < ch_hi; ch++) {
                     mbar_wait_backoff(b_empty + 8 * bs, bph ^ 1, 64);
                     const uint32_t dst = b_base + bs * b_stage;
                     mbar_expect_tx(b_full + 8 * bs, (uint32_t)(p.num_kb * CC * 128 + G::AUX_FLOATS * 4));
@@ -191,10 +196,12 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int ts = 0; uint32_t tph = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int cs = item % p.csplit;
+                const int ch_lo = cs * p.cpi, ch_hi = min(p.n_chunks, ch_lo + p.cpi);
                 mbar_wait_backoff(a_full + 8 * as, aph, 32);
                 tc_fence_after();
                 const uint32_t a_slot = a_base + as * a_slot_bytes;
-                for (int ch = 0; ch < p.n_chunks; ch++) {
+                for (int ch = ch_lo; ch < ch_hi; ch++) {
                     mbar_wait_backoff(b_full + 8 * bs, bph, 32);
                     tc_fence_after();
                     const uint32_t bsm = b_base + bs * b_stage;
@@ -230,11 +237,13 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int pl = lane < CC / 2 ? lane : CC / 2 - 1;
         int bs = 0; uint32_t bph = 0; int ts = 0; uint32_t tph = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const int b = item / p.tiles, tile = item - b * p.tiles;
+            const int it = item / p.csplit, cs = item - it * p.csplit;
+            const int ch_lo = cs * p.cpi, ch_hi = min(p.n_chunks, ch_lo + p.cpi);
+            const int b = it / p.tiles, tile = it - b * p.tiles;
             const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
             const int oy0 = ty * TH, ox0 = tx * TW;
             const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
-            for (int chn = 0; chn < p.n_chunks; chn++) {
+            for (int chn = ch_lo; chn < ch_hi; chn++) {
                 const int c0 = chn * CC;
                 mbar_wait(b_full + 8 * bs, bph);               // aux block (dw weights + biases) landed
                 const float* aux = (const float*)(b_gen + bs * b_stage + aux_off);
@@ -427,12 +436,17 @@ static int launch_front(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __n
     const int tiles_x = (b.hout + TW - 1) / TW, tiles_y = (b.hout + TH - 1) / TH;
     p.tiles_x = tiles_x; p.tiles = tiles_x * tiles_y;
     p.n_chunks = (b.cexp + CC - 1) / CC;
-    p.n_items = m * p.tiles;
+    // enough items to occupy every CTA slot at small batch: split the chunk loop of an (image, tile) across items
+    p.csplit = 1;
+    while (m * p.tiles * p.csplit < 2 * ctx->sm_count && p.csplit < p.n_chunks) p.csplit++;
+    p.cpi = (p.n_chunks + p.csplit - 1) / p.csplit;
+    p.csplit = (p.n_chunks + p.cpi - 1) / p.cpi;              // no empty items
+    p.n_items = m * p.tiles * p.csplit;
     *n_parts = p.tiles;
     if ((size_t)p.tiles * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
     int grid = 2 * ctx->sm_count;
     if (grid > p.n_items) grid = p.n_items;
-    k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE><<<grid, MF_THREADS, smem, st>>>(mx, mw, p);
+    DFD_CUDA(dfd_launch(ctx->pdl, k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE>, dim3(grid), dim3(MF_THREADS), smem, st, mx, mw, p));
     DFD_LAUNCH_CHECK("k_mbconv_front", st);
     return DFD_OK;
 }

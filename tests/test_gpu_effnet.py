@@ -123,18 +123,18 @@ def test_fused_front_matches_two_kernel_path(setup, blk):
 
 @pytest.mark.parametrize("blk", [0, 1, 4, 9, 15])
 def test_fused_se_tail_matches_se_kernels(setup, blk):
-    """The SE excite variants agree: two kernels (0), one k_se_excite launch (1, default)."""
+    """The SE excite variants agree: two kernels (0), one k_se_excite launch (1), 8-CTA cluster kernel (2, default)."""
     e, sd, x, ref, taps = setup
     xn = x[:5].permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
     got = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         e.set_option("se_mode", mode)
         e.set_tap(f"b{blk}.out")
         e.effnet_forward(xn)
         got[mode] = e.activation(f"b{blk}.out").cpu()
-    e.set_option("se_mode", 1)
+    e.set_option("se_mode", 2)
     e.set_tap("")
-    for mode in (1,):
+    for mode in (1, 2):
         assert float((got[0] - got[mode]).abs().max()) <= 2.0 ** -5 * max(1.0, float(got[0].abs().max()))
         assert float((got[0] - got[mode]).abs().mean()) <= 2.0 ** -9 * max(1.0, float(got[0].abs().max()))
 
@@ -144,7 +144,7 @@ def test_fused_paths_logits_close(setup):
     xn = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
     e.set_option("no_fuse", 1); e.set_option("se_mode", 0)
     a = e.effnet_forward(xn).cpu()
-    e.set_option("no_fuse", 0); e.set_option("se_mode", 1)
+    e.set_option("no_fuse", 0); e.set_option("se_mode", 2)
     b = e.effnet_forward(xn).cpu()
     c = e.effnet_forward(xn).cpu()
     print("fused vs unfused max |dlogit|", float((a - b).abs().max()))
