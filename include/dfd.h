@@ -188,7 +188,9 @@ int dfd_dbg_face_clahe(dfd_ctx* ctx, const uint8_t* frames, int H, int W, size_t
 int dfd_dbg_set_tap(dfd_ctx* ctx, const char* name);
 int64_t dfd_dbg_activation(dfd_ctx* ctx, const char* name, float* out_dev, int64_t n_floats, void* stream);
 /* A/B switches for the parity tests: "no_fuse" (1 = run the expand 1x1 GEMM and the depthwise kernel separately
- * instead of the fused mbconv_fused.cu kernel), "se_mode" (bf16 SE excite: 0 = two kernels, 1 = one kernel, 2 = one kernel on 8-CTA clusters), "no_overlap" (1 = forensic kernels on the caller's stream). */
+ * instead of the fused mbconv_fused.cu kernel), "se_mode" (bf16 SE excite: 0 = two kernels, 1 = one kernel, 2 = one kernel on 8-CTA clusters), "no_gated_w" (1 = blocks 0-4 gate the
+ * project GEMM's A operand instead of using per-image gated weights), "pdl" (0 = no programmatic dependent launch),
+ * "no_overlap" (1 = forensic kernels on the caller's stream). */
 int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value);
 
 #ifdef __cplusplus

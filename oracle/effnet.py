@@ -129,3 +129,58 @@ def forward(x, sd, taps=None):
     if taps is not None:
         taps["features"] = f
     return classifier(f, sd)
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16-storage restatement (second oracle for the bf16 mode of the CUDA path)
+# ---------------------------------------------------------------------------------------------
+def _r(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _fold(sd, prefix, eps):
+    g, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+    m, v = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+    s = g / torch.sqrt(v + eps)
+    return s, b - m * s
+
+
+@torch.no_grad()
+def forward_bf16_storage(x, sd, gated_weight_blocks=5):
+    """The same network with every stored activation and every GEMM operand rounded to bfloat16 at exactly the points
+    where the CUDA bf16 path rounds (fp32 accumulation, fp32 SE / pooling / classifier, BatchNorm folded into the
+    weights before they are rounded).  It separates the two sources of a bf16-vs-fp32 difference: the INHERENT loss of
+    bf16 storage (this function vs ``forward``) and the kernels' own error (CUDA bf16 logits vs this function).
+    Blocks < gated_weight_blocks fold the SE gate into the project weights (rounded), the others into the activation."""
+    x = _r(x)
+    s, b = _fold(sd, "net._bn0", BN_EPS)
+    w = _r(sd["net._conv_stem.weight"] * s.view(-1, 1, 1, 1))
+    x = _r(_swish(_conv_same(x, w, 2) + b.view(1, -1, 1, 1)))
+    for i, (k, st, cin, cexp, cout, se) in enumerate(BLOCKS):
+        p = f"net._blocks.{i}."
+        inp = x
+        if cexp != cin:
+            s, b = _fold(sd, p + "_bn0", BN_EPS)
+            w = _r(sd[p + "_expand_conv.weight"] * s.view(-1, 1, 1, 1))
+            x = _r(_swish(F.conv2d(x, w) + b.view(1, -1, 1, 1)))
+        s, b = _fold(sd, p + "_bn1", BN_EPS)
+        w = sd[p + "_depthwise_conv.weight"] * s.view(-1, 1, 1, 1)                 # fp32 weights on the CUDA cores
+        y = _swish(_conv_same(x, w, st, groups=cexp) + b.view(1, -1, 1, 1))       # fp32 before it is stored
+        sq = F.adaptive_avg_pool2d(y, 1)                                            # squeeze sums the unrounded values
+        sq = _swish(F.conv2d(sq, sd[p + "_se_reduce.weight"], sd[p + "_se_reduce.bias"]))
+        gate = torch.sigmoid(F.conv2d(sq, sd[p + "_se_expand.weight"], sd[p + "_se_expand.bias"]))
+        x = _r(y)
+        s, b = _fold(sd, p + "_bn2", BN_EPS)
+        wp = (sd[p + "_project_conv.weight"] * s.view(-1, 1, 1, 1)).flatten(1)      # (cout, cexp)
+        if i < gated_weight_blocks:
+            wg = _r(wp.unsqueeze(0) * gate.flatten(1).unsqueeze(1))                 # (B, cout, cexp) per-image weights
+            x = torch.einsum("bchw,boc->bohw", x, wg) + b.view(1, -1, 1, 1)
+        else:
+            x = F.conv2d(_r(x * gate), _r(wp).view(cout, cexp, 1, 1)) + b.view(1, -1, 1, 1)
+        if st == 1 and cin == cout:
+            x = x + inp
+        x = _r(x)
+    s, b = _fold(sd, "net._bn1", BN_EPS)
+    w = _r(sd["net._conv_head.weight"] * s.view(-1, 1, 1, 1))
+    x = _r(_swish(F.conv2d(x, w) + b.view(1, -1, 1, 1)))
+    return classifier(F.adaptive_avg_pool2d(x, 1).flatten(1), sd)

@@ -26,6 +26,8 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
                      const float* bias, const __nv_bfloat16* residual, __nv_bfloat16* C, int M, int N, int K, int act,
                      cudaStream_t st);
 bool dfd_gemm_bf16_enabled();
+int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16* Wg, const float* bias,
+                      const __nv_bfloat16* residual, __nv_bfloat16* C, int n_img, int hw, int N, int K, int act, cudaStream_t st);
 int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const float* W, const float* bias,
                 __nv_bfloat16* out, int m, int* n_parts, cudaStream_t st);
 int dfd_mbconv_front_bf16(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __nv_bfloat16* We, __nv_bfloat16* out, int m,
@@ -401,9 +403,10 @@ __global__ void __launch_bounds__(SE_X_THREADS) k_se_excite(const float* __restr
 __global__ void __cluster_dims__(SE_CL, 1, 1) __launch_bounds__(256)
 k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr, const float* __restrict__ br,
              const float* __restrict__ WxT, const float* __restrict__ bx, float* __restrict__ scale, int C, int se,
-             float inv_hw, int m) {
+             float inv_hw, int m, const float* __restrict__ Wp, __nv_bfloat16* __restrict__ Wg, int N) {
     __shared__ __align__(16) float mean[SE_CL][1152];
     __shared__ float r[SE_CL][64];
+    __shared__ float gsm[SE_CL][144];                           // this CTA's gates (8 images x channel slice)
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int b0 = (blockIdx.x / SE_CL) * SE_CL;
@@ -495,8 +498,23 @@ k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restric
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (b0 + half * 4 + i < m) scale[(size_t)(b0 + half * 4 + i) * C + c] = sigmoidf(a[i]);
+        for (int i = 0; i < 4; i++) {
+            const float g = sigmoidf(a[i]);
+            gsm[half * 4 + i][c - rank * Cs] = g;
+            if (b0 + half * 4 + i < m) scale[(size_t)(b0 + half * 4 + i) * C + c] = g;
+        }
+    }
+    // phase 4 (high-resolution blocks): fold the gate into a per-image copy of the project weights,
+    // Wg[b][n][k] = bf16(Wp[n][k] * g[b][k]), so the project GEMM needs no pass over its A operand (gemm A_IMG)
+    if (Wg) {
+        __syncthreads();
+        for (int idx = tid; idx < SE_CL * N * Cs; idx += 256) {
+            const int cl = idx % Cs, t = idx / Cs, n = t % N, i = t / N;
+            if (b0 + i < m) {
+                const int k = rank * Cs + cl;
+                Wg[((size_t)(b0 + i) * N + n) * C + k] = __float2bfloat16_rn(Wp[(size_t)n * C + k] * gsm[i][cl]);
+            }
+        }
     }
 }
 
@@ -735,12 +753,15 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
+        // blocks 0-4 (>= 784 rows per image): the SE gate is folded into per-image project weights by the SE kernel
+        const bool gated_w = BF && tc && i <= 4 && ctx->se_mode == 2 && !ctx->no_gated_w;
         if (BF && ctx->se_mode == 3) {
             // timing experiment only (DFD_SE_MODE=3): no SE excite at all, gates stay whatever they were
         } else if (BF && ctx->se_mode == 2) {
             DFD_CUDA(dfd_launch(ctx->pdl, k_se_cluster, dim3((m + SE_CL - 1) / SE_CL * SE_CL), dim3(256), 0, st, (const float*)ctx->d_pool, n_parts,
                                 (const float*)(Wf + f.wr), (const float*)(Wf + f.br), (const float*)(ctx->d_wxt + wxt_off[i]),
-                                (const float*)(Wf + f.bx), ctx->d_sescale, b.cexp, b.se, 1.0f / (float)(b.hout * b.hout), m));
+                                (const float*)(Wf + f.bx), ctx->d_sescale, b.cexp, b.se, 1.0f / (float)(b.hout * b.hout), m,
+                                (const float*)(gated_w ? Wf + f.wp : nullptr), gated_w ? ctx->d_wgated : (__nv_bfloat16*)nullptr, b.cout));
             DFD_LAUNCH_CHECK("k_se_cluster", st);
         } else if (BF && ctx->se_mode != 0) {
             k_se_excite<<<(m + SE_X_IPC - 1) / SE_X_IPC, SE_X_THREADS, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, ctx->d_wxt + wxt_off[i],
@@ -759,7 +780,10 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         const bool skip = b.s == 1 && b.cin == b.cout;
         T* outp = (dw_out == y) ? x : y;       // block 0 wrote dw into y; its project output goes to x (input is dead, no skip)
         ctx->label = L_PROJ[i];
-        if (tc) {      // the SE gate is applied while the A tile is staged (A_SCALE)
+        if (gated_w) {
+            if ((rc = dfd_gemm_bf16_img(ctx, (const __nv_bfloat16*)dw_out, ctx->d_wgated, Wf + f.bp, (const __nv_bfloat16*)(skip ? x : nullptr),
+                                        (__nv_bfloat16*)outp, m, b.hout * b.hout, b.cout, b.cexp, 0, st))) return rc;
+        } else if (tc) {      // the SE gate is applied while the A tile is staged (A_SCALE)
             if ((rc = dfd_gemm_bf16_ex(ctx, 1, (const __nv_bfloat16*)dw_out, ctx->d_sescale, b.hout * b.hout,
                                        ctx->d_wbf16 + f.wp, Wf + f.bp, (const __nv_bfloat16*)(skip ? x : nullptr),
                                        (__nv_bfloat16*)outp, Mout, b.cout, b.cexp, 0, st))) return rc;

@@ -8,6 +8,9 @@
 //   A_SCALE  project 1x1 convs: A' = A * se[image][k] -- the squeeze-excite gate is applied while the
 //            tile is staged, so the gated tensor never exists in HBM
 //   A_STEM   stem 3x3 stride-2 conv 3->32: A' = im2col rows (27 taps, zero padded to 32) gathered on the fly
+//   A_IMG    project 1x1 convs of the high-resolution blocks: the SE gate is folded into a PER-IMAGE weight matrix
+//            W_b = W * diag(g_b) (written by the SE kernel), tiles never straddle images (3-D tensor maps
+//            [image][row][k]) and A goes from TMA straight to the tensor core -- no staging pass over A at all
 //
 // One persistent CTA per SM, warp-specialised (640 threads), no cluster:
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads (SWIZZLE_128B) of the W tile (N x 64) and (A_TMA,
@@ -40,7 +43,7 @@
 #define STAGING_BLOCK_BYTES (BLOCK_M * 128)
 #define MAX_BIAS 1280
 
-enum { A_TMA = 0, A_SCALE = 1, A_STEM = 2 };
+enum { A_TMA = 0, A_SCALE = 1, A_STEM = 2, A_IMG = 3 };
 
 struct GemmParams {
     int M, N, K;
@@ -50,7 +53,8 @@ struct GemmParams {
     int stages;
     int act;
     int a_mode;
-    int hw;               // A_SCALE: rows per image
+    int hw;               // A_SCALE / A_IMG: rows per image
+    int tiles_per_img;    // A_IMG: ceil(hw / 128)
     int b_resident;       // W (all k-blocks) stays in shared memory for the whole kernel; the ring holds A only
     int debug;            // diagnostics (dfd_gemm_bench): bit 0 = skip the TMA stores, bit 1 = skip the epilogue math
     const float* bias;
@@ -68,6 +72,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __shared__ __align__(16) float sbias[MAX_BIAS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool plain = p.a_mode == A_TMA || p.a_mode == A_IMG;     // A goes from TMA straight to the MMA
     const uint32_t b_stage_bytes = (uint32_t)p.n_pad * BLOCK_K * 2;
     const uint32_t stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0u : b_stage_bytes);
     const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
@@ -89,13 +94,13 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         // full[s]: A_TMA = the TMA thread; A_SCALE = 4 fix-up warps; A_STEM = TMA thread (W) + 4 gather warps
-        const uint32_t full_count = p.a_mode == A_TMA ? 1u : (p.a_mode == A_SCALE ? 4u : (p.b_resident ? 4u : 5u));
+        const uint32_t full_count = plain ? 1u : (p.a_mode == A_SCALE ? 4u : (p.b_resident ? 4u : 5u));
         mbar_init(bfull, 1);
         for (int s = 0; s < p.stages; s++) {
             mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); mbar_init(raw0 + 8 * s, 1);
         }
         // A_TMA: the 8 staging warps double as a second pair of epilogue groups (column halves) -> 8 arrivals
-        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, p.a_mode == A_TMA ? 8 : 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, plain ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -130,8 +135,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_STAGE_BYTES;
                         const bool skip_b = (p.debug & 32) != 0;      // diagnostics only
                         mbar_expect_tx(sig0 + 8 * stage, skip_b ? tx - b_stage_bytes : tx);
-                        if (load_a) tma_load_2d(sa, &map_a, kb * BLOCK_K, m_blk * BLOCK_M, sig0 + 8 * stage);
-                        if (load_b && !skip_b) tma_load_2d(sb, &map_b, kb * BLOCK_K, n_blk * p.n_pad, sig0 + 8 * stage);
+                        if (p.a_mode == A_IMG) {
+                            const int img = tile / p.tiles_per_img, mb = tile - img * p.tiles_per_img;
+                            tma_load_3d(sa, &map_a, kb * BLOCK_K, mb * BLOCK_M, img, sig0 + 8 * stage);
+                            tma_load_3d(sb, &map_b, kb * BLOCK_K, 0, img, sig0 + 8 * stage);
+                        } else {
+                            if (load_a) tma_load_2d(sa, &map_a, kb * BLOCK_K, m_blk * BLOCK_M, sig0 + 8 * stage);
+                            if (load_b && !skip_b) tma_load_2d(sb, &map_b, kb * BLOCK_K, n_blk * p.n_pad, sig0 + 8 * stage);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -165,7 +176,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 12 && p.a_mode != A_TMA) {
+    } else if (warp >= 12 && !plain) {
         // ===== staging warps: two groups of 128 threads on alternate k-blocks =====
         {
             const int g = (warp - 12) >> 2;
@@ -250,7 +261,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== epilogue groups of 4 warps (ping-pong over the two accumulators) =====
         // A_SCALE / A_STEM: groups 0,1 (warps 4-11), each drains a whole accumulator.
         // A_TMA: groups 0-3 (warps 4-19); group g drains accumulator g&1 and the 64-column blocks of parity g>>1.
-        const bool split = p.a_mode == A_TMA;
+        const bool split = plain;
         const int grp = (warp - 4) >> 2;
         const int set = grp & 1, half = grp >> 1;
         const int q = warp & 3;                                    // TMEM lane quarter (= warp % 4)
@@ -263,14 +274,20 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
             if ((it & 1) != set) continue;
-            const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
-            const int m = m_blk * BLOCK_M + row;
+            int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
+            int m = m_blk * BLOCK_M + row;
+            bool row_ok = m < p.M;
+            int img = 0;
+            if (p.a_mode == A_IMG) {                               // tile = (image, 128-row block inside the image)
+                img = tile / p.tiles_per_img; m_blk = tile - img * p.tiles_per_img; n_blk = 0;
+                row_ok = m_blk * BLOCK_M + row < p.hw;
+                m = img * p.hw + m_blk * BLOCK_M + row;
+            }
             const int n_base = n_blk * p.n_pad;
             mbar_wait(tfull0 + 8 * set, acc_phase);
             acc_phase ^= 1;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.n_pad);
-            const bool row_ok = m < p.M;
             const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
             for (int jb = split ? half : 0; jb < ((p.debug & 16) ? 0 : nblk64); jb += split ? 2 : 1, blk_count++) {
                 const uint32_t buf = my_staging + (split ? 0u : (blk_count & 1u) * STAGING_BLOCK_BYTES);
@@ -321,7 +338,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 fence_async_smem();
                 set_bar_sync(1 + grp);
                 if (issuer) {
-                    if (n_base + jb * 64 < p.N && !(p.debug & 1)) tma_store_2d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, buf);
+                    if (n_base + jb * 64 < p.N && !(p.debug & 1)) {
+                        if (p.a_mode == A_IMG) tma_store_3d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, img, buf);
+                        else tma_store_2d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, buf);
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -400,7 +420,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     DFD_REQUIRE(K % 8 == 0 && N % 8 == 0 && N <= MAX_BIAS, DFD_ERR_INVALID, "gemm: K and N must be multiples of 8, N <= 1280");
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.act = act; p.bias = bias; p.residual = residual;
-    p.a_mode = a_mode; p.A = A; p.se = se; p.hw = hw > 0 ? hw : 1; p.debug = g_debug;
+    p.a_mode = a_mode; p.A = A; p.se = se; p.hw = hw > 0 ? hw : 1; p.debug = g_debug; p.tiles_per_img = 1;
     // N tiling: the smallest number of equal UMMA-N blocks (multiples of 16, <= 256) covering N
     // (with several N blocks the block width is a multiple of 64 so the 64-column TMA stores of one block
     // never touch its neighbour's columns)
@@ -437,6 +457,54 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     else memset(&ma, 0, sizeof ma);
     if ((rc = make_map(ctx, &mb, W, (uint64_t)N, (uint64_t)K, (uint32_t)n_pad))) return rc;
     if ((rc = make_map(ctx, &mc, C, (uint64_t)M, (uint64_t)N, BLOCK_M))) return rc;
+    int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+    DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
+    DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);
+    return DFD_OK;
+}
+
+// Project 1x1 conv with per-image gated weights: C[img] = A[img] (hw x K) . Wg[img] (N x K)^T + bias (+ residual).
+int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16* Wg, const float* bias,
+                      const __nv_bfloat16* residual, __nv_bfloat16* C, int n_img, int hw, int N, int K, int act, cudaStream_t st) {
+    int rc = get_encode(ctx);
+    if (rc) return rc;
+    DFD_REQUIRE(K % 8 == 0 && N % 8 == 0 && N <= 256, DFD_ERR_INVALID, "gemm_img: K and N must be multiples of 8, N <= 256");
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.M = n_img * hw; p.N = N; p.K = K; p.act = act; p.bias = bias; p.residual = residual;
+    p.a_mode = A_IMG; p.A = A; p.se = nullptr; p.hw = hw; p.debug = 0;
+    p.n_pad = (N + 15) / 16 * 16; p.n_blocks = 1;
+    p.tiles_per_img = (hw + BLOCK_M - 1) / BLOCK_M;
+    p.num_tiles = n_img * p.tiles_per_img;
+    p.b_resident = 0;
+    const int staging_bytes = 4 * STAGING_BLOCK_BYTES;
+    const int stage_bytes = A_STAGE_BYTES + p.n_pad * BLOCK_K * 2;
+    int stages = (204 * 1024 - staging_bytes) / stage_bytes;
+    if (stages > 8) stages = 8;
+    DFD_REQUIRE(stages >= 2, DFD_ERR_INVALID, "gemm_img: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        attr_set = true;
+    }
+    CUtensorMap ma, mb, mc;
+    {
+        const uint64_t d[3] = {(uint64_t)K, (uint64_t)hw, (uint64_t)n_img}, s[2] = {(uint64_t)K * 2, (uint64_t)hw * K * 2};
+        const uint32_t b[3] = {BLOCK_K, BLOCK_M, 1};
+        if ((rc = dfd_tmap_bf16(ctx, &ma, A, 3, d, s, b))) return rc;
+    }
+    {
+        const uint64_t d[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)n_img}, s[2] = {(uint64_t)K * 2, (uint64_t)N * K * 2};
+        const uint32_t b[3] = {BLOCK_K, (uint32_t)p.n_pad, 1};
+        if ((rc = dfd_tmap_bf16(ctx, &mb, Wg, 3, d, s, b))) return rc;
+    }
+    {
+        const uint64_t d[3] = {(uint64_t)N, (uint64_t)hw, (uint64_t)n_img}, s[2] = {(uint64_t)N * 2, (uint64_t)hw * N * 2};
+        const uint32_t b[3] = {BLOCK_K, BLOCK_M, 1};
+        if ((rc = dfd_tmap_bf16(ctx, &mc, C, 3, d, s, b))) return rc;
+    }
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
     DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
     DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);

@@ -175,13 +175,13 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const int b = it / p.tiles, tile = it - b * p.tiles;
                 const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
                 const int iy0 = WHOLE ? 0 : ty * TH * S - PAD, ix0 = WHOLE ? 0 : tx * TW * S - PAD;
-                mbar_wait_backoff(a_empty + 8 * as, aph ^ 1, 64);
+                mbar_wait_backoff(a_empty + 8 * as, aph ^ 1, 256);
                 mbar_expect_tx(a_full + 8 * as, (uint32_t)(p.num_kb * NPIX * 128));
                 for (int kb = 0; kb < p.num_kb; kb++)
                     tma_load_4d(a_base + as * a_slot_bytes + kb * G::A_KB_BYTES, &map_x, kb * 64, ix0, iy0, b, a_full + 8 * as);
                 if (++as == p.na) { as = 0; aph ^= 1; }
                 for (int ch = ch_lo; ch < ch_hi; ch++) {
-                    mbar_wait_backoff(b_empty + 8 * bs, bph ^ 1, 64);
+                    mbar_wait_backoff(b_empty + 8 * bs, bph ^ 1, 256);
                     const uint32_t dst = b_base + bs * b_stage;
                     mbar_expect_tx(b_full + 8 * bs, (uint32_t)(p.num_kb * CC * 128 + G::AUX_FLOATS * 4));
                     for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(dst + kb * CC * 128, &map_w, kb * 64, ch * CC, b_full + 8 * bs);
@@ -198,16 +198,16 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int cs = item % p.csplit;
                 const int ch_lo = cs * p.cpi, ch_hi = min(p.n_chunks, ch_lo + p.cpi);
-                mbar_wait_backoff(a_full + 8 * as, aph, 32);
+                mbar_wait_backoff(a_full + 8 * as, aph, 128);
                 tc_fence_after();
                 const uint32_t a_slot = a_base + as * a_slot_bytes;
                 for (int ch = ch_lo; ch < ch_hi; ch++) {
-                    mbar_wait_backoff(b_full + 8 * bs, bph, 32);
+                    mbar_wait_backoff(b_full + 8 * bs, bph, 128);
                     tc_fence_after();
                     const uint32_t bsm = b_base + bs * b_stage;
 #pragma unroll 1
                     for (int mb = 0; mb < N_MB; mb++) {
-                        mbar_wait_backoff(t_empty + 8 * ts, tph ^ 1, 32);
+                        mbar_wait_backoff(t_empty + 8 * ts, tph ^ 1, 96);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)(ts * CC);
                         for (int kb = 0; kb < p.num_kb; kb++) {
