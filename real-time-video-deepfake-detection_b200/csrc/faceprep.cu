@@ -8,8 +8,8 @@
 // All u8 stages are bit-exact (px_*.h, checked on the CPU against cv2 / PIL by tests/hostcheck).
 //
 //   k_pil_coeffs        Pillow resample coefficients for both axes of every box (double math)
-//   k_clahe_lut         per (box, CLAHE tile): L histogram in smem -> clipped, redistributed LUT
-//   k_clahe_hpass       per (box, crop row): LAB/CLAHE/LAB2BGR row into smem, Pillow horizontal pass
+//   k_clahe_lut         per (box, row of 8 CLAHE tiles), warp per tile: L histogram in smem -> clipped, redistributed LUT
+//   k_clahe_hpass       per (box, 16 crop rows), warp per row: LAB/CLAHE/LAB2BGR row into smem, Pillow horizontal pass
 //   k_vpass_up_norm     per (box, 56-row band): Pillow vertical pass into smem, bilinear 224, normalise
 #include "dfd_internal.cuh"
 #include "px_resize.h"
@@ -29,75 +29,118 @@ __global__ void k_pil_coeffs(const int32_t* __restrict__ boxes, int* __restrict_
     for (int i = 0; i < cnt; i++) o[2 + i] = k[i];
 }
 
+// CTA = one row of 8 CLAHE tiles of one box; warp = one tile.  The L channel alone is needed here (3 gamma + 1 cube-root
+// table look-ups per pixel, tables staged in shared memory); bins are counted with warp-aggregated shared atomics and
+// the clipped / redistributed / cumulative LUT is built by the warp itself (dfd_clahe_lut_warp).
 __global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ frames, size_t fstride, int pitch,
                                                    const int32_t* __restrict__ boxes, const int32_t* __restrict__ frame_idx,
                                                    const DfdColorTables* __restrict__ tab, uint8_t* __restrict__ luts) {
-    const int m = blockIdx.y, tile = blockIdx.x;
-    const int ty = tile >> 3, tx = tile & 7;
+    __shared__ int hist[8][256];
+    __shared__ __align__(16) uint16_t s_gamma[256];
+    __shared__ __align__(16) uint16_t s_cbrt[3072];
+    // blockDim.x / 32 tiles per CTA (8 at large batch, 2 at small batch so one box still fills the chip)
+    const int m = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nthr = blockDim.x;
+    const int tile = blockIdx.x * (nthr >> 5) + warp, ty = tile >> 3, tx = tile & 7;
     const int bx = boxes[m * 4], by = boxes[m * 4 + 1], bw = boxes[m * 4 + 2], bh = boxes[m * 4 + 3];
     const DfdClaheGeom g = dfd_clahe_geom(bw, bh);
-    __shared__ int hist[256];
-    hist[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < 8 * 256; i += nthr) (&hist[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 256 / 8; i += nthr) ((uint4*)s_gamma)[i] = ((const uint4*)tab->gamma)[i];
+    for (int i = threadIdx.x; i < 3072 / 8; i += nthr) ((uint4*)s_cbrt)[i] = ((const uint4*)tab->cbrt)[i];
     __syncthreads();
     const uint8_t* f = frames + (size_t)frame_idx[m] * fstride;
     const int area = g.tw * g.th;
-    for (int p = threadIdx.x; p < area; p += 256) {
-        int y = ty * g.th + p / g.tw, x = tx * g.tw + p % g.tw;
-        if (x >= bw) x = dfd_reflect101(x, bw);
-        if (y >= bh) y = dfd_reflect101(y, bh);
-        const uint8_t* px = f + (size_t)(by + y) * pitch + (size_t)(bx + x) * 3;
-        int L, A, B;
-        dfd_bgr2lab(tab, px[0], px[1], px[2], &L, &A, &B);
-        atomicAdd(&hist[L], 1);
+    const unsigned magic = g.tw > 1 ? 0xffffffffu / (unsigned)g.tw + 1u : 0u;   // p / tw == umulhi(p, magic) for p * tw < 2^32
+    int* h = hist[warp];
+    for (int p0 = 0; p0 < area; p0 += 32) {
+        const int p = p0 + lane;
+        const bool ok = p < area;
+        int L = 0;
+        if (ok) {
+            const int yy = g.tw > 1 ? (int)__umulhi((unsigned)p, magic) : p, xx = p - yy * g.tw;
+            int y = ty * g.th + yy, x = tx * g.tw + xx;
+            if (x >= bw) x = dfd_reflect101(x, bw);
+            if (y >= bh) y = dfd_reflect101(y, bh);
+            const uint8_t* px = f + (size_t)(by + y) * pitch + (size_t)(bx + x) * 3;
+            L = dfd_bgr2lab_L(s_gamma, s_cbrt, px[0], px[1], px[2]);
+        }
+        // warp-aggregated histogram update: one shared atomic per distinct value
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(act, L);
+            if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&h[L], __popc(peers));
+        }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) dfd_clahe_lut(hist, g.clip, g.lut_scale, luts + ((size_t)m * 64 + tile) * 256);
+    __syncwarp();
+    dfd_clahe_lut_warp(h, g.clip, g.lut_scale, luts + ((size_t)m * 64 + ty * 8 + tx) * 256, lane);
 }
 
+// CTA = HP_ROWS consecutive crop rows of one box, warp = one row at a time: BGR -> LAB -> CLAHE(L) -> LAB2BGR -> RGB row
+// in shared memory, then Pillow's horizontal resampling pass of that row to 160 pixels.  The colour tables and the
+// box's 64 CLAHE LUTs are staged in shared memory once per CTA (11 table gathers + 4 LUT gathers per pixel).
+#define HP_ROWS 16
 __global__ void __launch_bounds__(256) k_clahe_hpass(const uint8_t* __restrict__ frames, size_t fstride, int pitch,
                                                      const int32_t* __restrict__ boxes, const int32_t* __restrict__ frame_idx,
                                                      const DfdColorTables* __restrict__ tab, const uint8_t* __restrict__ luts,
                                                      const int* __restrict__ pil, uint8_t* __restrict__ hpass, int max_crop,
-                                                     uint8_t* __restrict__ dbg_clahe, int dbg_box) {
-    extern __shared__ __align__(16) uint8_t row[];           // bw * 3 RGB
-    const int m = blockIdx.y, y = blockIdx.x;
+                                                     uint8_t* __restrict__ dbg_clahe, int dbg_box, int rows_per_cta) {
+    extern __shared__ __align__(16) uint8_t hp_smem[];
+    DfdColorTables* s_tab = (DfdColorTables*)hp_smem;                               // sizeof is a multiple of 16
+    uint8_t* s_lut = hp_smem + sizeof(DfdColorTables);                              // [64][256]
+    uint8_t* s_rows = s_lut + 64 * 256;                                             // [8 warps][max_crop * 3]
+    const int m = blockIdx.y, y0 = blockIdx.x * rows_per_cta;
     const int bx = boxes[m * 4], by = boxes[m * 4 + 1], bw = boxes[m * 4 + 2], bh = boxes[m * 4 + 3];
-    if (y >= bh) return;
-    const DfdClaheGeom g = dfd_clahe_geom(bw, bh);
-    const uint8_t* f = frames + (size_t)frame_idx[m] * fstride + (size_t)(by + y) * pitch + (size_t)bx * 3;
-    const uint8_t* lut = luts + (size_t)m * 64 * 256;
-    for (int x = threadIdx.x; x < bw; x += 256) {
-        int L, A, B, ob, og, orr;
-        dfd_bgr2lab(tab, f[x * 3], f[x * 3 + 1], f[x * 3 + 2], &L, &A, &B);
-        L = dfd_clahe_apply(lut, g, x, y, L);
-        dfd_lab2bgr(tab, L, A, B, &ob, &og, &orr);
-        row[x * 3] = (uint8_t)orr; row[x * 3 + 1] = (uint8_t)og; row[x * 3 + 2] = (uint8_t)ob;   // RGB order (:376)
-        if (dbg_clahe && m == dbg_box) {
-            uint8_t* d = dbg_clahe + ((size_t)y * bw + x) * 3;
-            d[0] = (uint8_t)ob; d[1] = (uint8_t)og; d[2] = (uint8_t)orr;
-        }
-    }
+    if (y0 >= bh) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (int)(sizeof(DfdColorTables) / 16); i += 256) ((uint4*)s_tab)[i] = ((const uint4*)tab)[i];
+    for (int i = threadIdx.x; i < 64 * 256 / 16; i += 256) ((uint4*)s_lut)[i] = ((const uint4*)(luts + (size_t)m * 64 * 256))[i];
     __syncthreads();
-    if (!hpass) return;
+    const DfdClaheGeom g = dfd_clahe_geom(bw, bh);
+    uint8_t* row = s_rows + (size_t)warp * max_crop * 3;
     const int* pc = pil + ((size_t)m * 2 + 0) * 160 * PIL_STRIDE;
-    uint8_t* out = hpass + (((size_t)m * max_crop + y) * 160) * 3;
-    for (int o = threadIdx.x; o < 480; o += 256) {
-        int xx = o / 3, c = o % 3;
-        const int* k = pc + xx * PIL_STRIDE;
-        int xmin = k[0], cnt = k[1];
-        int acc = 1 << (DFD_PIL_PRECISION - 1);
-        for (int t = 0; t < cnt; t++) acc += row[(xmin + t) * 3 + c] * k[2 + t];
-        out[o] = (uint8_t)dfd_pil_clip8(acc);
+    for (int y = y0 + warp; y < y0 + rows_per_cta && y < bh; y += 8) {
+        const uint8_t* f = frames + (size_t)frame_idx[m] * fstride + (size_t)(by + y) * pitch + (size_t)bx * 3;
+        for (int x = lane; x < bw; x += 32) {
+            int L, A, B, ob, og, orr;
+            dfd_bgr2lab(s_tab, f[x * 3], f[x * 3 + 1], f[x * 3 + 2], &L, &A, &B);
+            L = dfd_clahe_apply(s_lut, g, x, y, L);
+            dfd_lab2bgr(s_tab, L, A, B, &ob, &og, &orr);
+            row[x * 3] = (uint8_t)orr; row[x * 3 + 1] = (uint8_t)og; row[x * 3 + 2] = (uint8_t)ob;   // RGB order (:376)
+            if (dbg_clahe && m == dbg_box) {
+                uint8_t* d = dbg_clahe + ((size_t)y * bw + x) * 3;
+                d[0] = (uint8_t)ob; d[1] = (uint8_t)og; d[2] = (uint8_t)orr;
+            }
+        }
+        __syncwarp();
+        if (hpass) {
+            uint8_t* out = hpass + (((size_t)m * max_crop + y) * 160) * 3;
+            for (int o = lane; o < 480; o += 32) {
+                const int xx = o / 3, c = o - xx * 3;
+                const int* k = pc + xx * PIL_STRIDE;
+                const int xmin = k[0], cnt = k[1];
+                int acc = 1 << (DFD_PIL_PRECISION - 1);
+                for (int t = 0; t < cnt; t++) acc += row[(xmin + t) * 3 + c] * k[2 + t];
+                out[o] = (uint8_t)dfd_pil_clip8(acc);
+            }
+        }
+        __syncwarp();
     }
 }
 
 template <typename OutT>
-__device__ __forceinline__ void store_px(OutT* o, float a, float b, float c);
+__device__ __forceinline__ void store8(OutT* o, const float* v);
 template <>
-__device__ __forceinline__ void store_px<float>(float* o, float a, float b, float c) { o[0] = a; o[1] = b; o[2] = c; }
+__device__ __forceinline__ void store8<float>(float* o, const float* v) {
+    ((float4*)o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    ((float4*)o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
 template <>
-__device__ __forceinline__ void store_px<__nv_bfloat16>(__nv_bfloat16* o, float a, float b, float c) {
-    o[0] = __float2bfloat16_rn(a); o[1] = __float2bfloat16_rn(b); o[2] = __float2bfloat16_rn(c);
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* o, const float* v) {
+    uint4 t;
+    __nv_bfloat162* h = (__nv_bfloat162*)&t;
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *(uint4*)o = t;
 }
 
 template <typename OutT>
@@ -124,22 +167,27 @@ __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict
     }
     __syncthreads();
     const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-    for (int o = threadIdx.x; o < 56 * 224; o += 512) {
-        int y = band * 56 + o / 224, x = o % 224;
-        int y0, y1, x0, x1; float h0, h1, w0, w1;
+    // a thread produces 8 consecutive values of an output row (672 = 84 x 8 per row) and stores them as 16-byte vectors
+    for (int o = threadIdx.x; o < 56 * 84; o += 512) {
+        const int yr = o / 84, v8 = o - yr * 84;
+        const int y = band * 56 + yr;
+        int y0, y1; float h0, h1;
         dfd_torch_bilinear_coef(y, 160, 224, &y0, &y1, &h0, &h1);
-        dfd_torch_bilinear_coef(x, 160, 224, &x0, &x1, &w0, &w1);
-        float v[3];
+        const uint8_t* r0 = s160[y0 - r_first];
+        const uint8_t* r1 = s160[y1 - r_first];
+        float v[8];
+        int xprev = -1, x0 = 0, x1 = 0; float w0 = 0.f, w1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            float p00 = s160[y0 - r_first][x0 * 3 + c], p01 = s160[y0 - r_first][x1 * 3 + c];
-            float p10 = s160[y1 - r_first][x0 * 3 + c], p11 = s160[y1 - r_first][x1 * 3 + c];
+        for (int j = 0; j < 8; j++) {
+            const int e = v8 * 8 + j, x = e / 3, c = e - x * 3;
+            if (x != xprev) { dfd_torch_bilinear_coef(x, 160, 224, &x0, &x1, &w0, &w1); xprev = x; }
+            const float p00 = r0[x0 * 3 + c], p01 = r0[x1 * 3 + c], p10 = r1[x0 * 3 + c], p11 = r1[x1 * 3 + c];
             float t = DFD_FADD(DFD_FMUL(h0, DFD_FADD(DFD_FMUL(w0, p00), DFD_FMUL(w1, p01))),
                                DFD_FMUL(h1, DFD_FADD(DFD_FMUL(w0, p10), DFD_FMUL(w1, p11))));
             t = DFD_FDIV(t, 255.0f);
-            v[c] = DFD_FDIV(DFD_FSUB(t, mean[c]), stdv[c]);
+            v[j] = DFD_FDIV(DFD_FSUB(t, c == 0 ? mean[0] : (c == 1 ? mean[1] : mean[2])), c == 0 ? stdv[0] : (c == 1 ? stdv[1] : stdv[2]));
         }
-        store_px<OutT>(out + (((size_t)m * 224 + y) * 224 + x) * 3, v[0], v[1], v[2]);
+        store8<OutT>(out + (((size_t)m * 224 + y) * 224) * 3 + v8 * 8, v);
     }
 }
 
@@ -151,10 +199,19 @@ int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H
     const int mc = ctx->cfg.max_crop;
     k_pil_coeffs<<<m, 320, 0, st>>>(boxes, ctx->d_pil);
     DFD_LAUNCH_CHECK("k_pil_coeffs", st);
-    k_clahe_lut<<<dim3(64, m), 256, 0, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables, ctx->d_luts);
+    const int lut_warps = m >= 16 ? 8 : 2;
+    k_clahe_lut<<<dim3(64 / lut_warps, m), 32 * lut_warps, 0, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables, ctx->d_luts);
     DFD_LAUNCH_CHECK("k_clahe_lut", st);
-    k_clahe_hpass<<<dim3(mc, m), 256, mc * 3, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables,
-                                                    ctx->d_luts, ctx->d_pil, ctx->d_hpass, mc, nullptr, -1);
+    const size_t hp_smem = sizeof(DfdColorTables) + 64 * 256 + (size_t)8 * mc * 3;
+    static size_t hp_attr = 0;
+    if (hp_smem > hp_attr) {
+        DFD_CUDA(cudaFuncSetAttribute(k_clahe_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem));
+        hp_attr = hp_smem;
+    }
+    const int hp_rows = m >= 16 ? HP_ROWS : 8;
+    k_clahe_hpass<<<dim3((mc + hp_rows - 1) / hp_rows, m), 256, hp_smem, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx,
+                                                                               ctx->d_tables, ctx->d_luts, ctx->d_pil, ctx->d_hpass, mc,
+                                                                               nullptr, -1, hp_rows);
     DFD_LAUNCH_CHECK("k_clahe_hpass", st);
     if (dtype == DFD_F32)
         k_vpass_up_norm<float><<<dim3(4, m), 512, 0, st>>>(boxes, ctx->d_pil, ctx->d_hpass, mc, ctx->d_face160, (float*)out);
@@ -169,8 +226,10 @@ int dfd_dbg_clahe_launch(dfd_ctx* ctx, const uint8_t* frames, size_t frame_strid
                          const int32_t* frame_idx, int i, uint8_t* out, cudaStream_t st) {
     // luts of the last dfd_face_prep_batch call are reused; only box i is written
     const int mc = ctx->cfg.max_crop;
-    k_clahe_hpass<<<dim3(mc, i + 1), 256, mc * 3, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables,
-                                                       ctx->d_luts, ctx->d_pil, nullptr, mc, out, i);
+    const size_t hp_smem = sizeof(DfdColorTables) + 64 * 256 + (size_t)8 * mc * 3;
+    DFD_CUDA(cudaFuncSetAttribute(k_clahe_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem));
+    k_clahe_hpass<<<dim3((mc + HP_ROWS - 1) / HP_ROWS, i + 1), 256, hp_smem, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx,
+                                                                                   ctx->d_tables, ctx->d_luts, ctx->d_pil, nullptr, mc, out, i, HP_ROWS);
     DFD_LAUNCH_CHECK("k_clahe_hpass", st);
     return DFD_OK;
 }

@@ -49,6 +49,50 @@ DFD_HD void dfd_clahe_lut(int* hist, int clip, float lut_scale, uint8_t* lut) {
     }
 }
 
+#if defined(__CUDACC__)
+// The same LUT built by one WARP (lane = 8 consecutive bins): clip + excess by warp reduction, the residual
+// "every step-th bin" increment in closed form, the cumulative sum by a shuffle scan.  hist is in shared memory.
+__device__ __forceinline__ void dfd_clahe_lut_warp(const int* hist, int clip, float lut_scale, uint8_t* lut, int lane) {
+    int h[8];
+    int excess = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int v = hist[lane * 8 + j];
+        if (v > clip) { excess += v - clip; v = clip; }
+        h[j] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) excess += __shfl_xor_sync(0xffffffffu, excess, o);
+    const int batch = excess / 256;
+    const int residual = excess - batch * 256;
+    int step = residual ? 256 / residual : 1;
+    if (step < 1) step = 1;
+    int run = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = lane * 8 + j;
+        h[j] += batch;
+        if (residual != 0 && i % step == 0 && i / step < residual) h[j]++;     // bins 0, step, 2*step, ... (residual of them)
+        run += h[j];
+        h[j] = run;                                                             // inclusive prefix inside the lane
+    }
+    int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int base = incl - run;                                                // exclusive prefix of the lanes before
+    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t v = (uint32_t)dfd_sat_u8(DFD_RINTF(DFD_FMUL((float)(base + h[j]), lut_scale)));
+        if (j < 4) w0 |= v << (8 * j); else w1 |= v << (8 * (j - 4));
+    }
+    *(uint2*)(lut + lane * 8) = make_uint2(w0, w1);
+}
+#endif
+
 // luts: [8][8][256] for this crop.  (x,y) in the ORIGINAL crop.
 DFD_HD int dfd_clahe_apply(const uint8_t* luts, const DfdClaheGeom& g, int x, int y, int val) {
     float inv_tw = 1.0f / (float)g.tw, inv_th = 1.0f / (float)g.th;

@@ -50,6 +50,13 @@ DFD_HD void dfd_bgr2lab(const DfdColorTables* T, int b, int g, int r, int* L, in
     *L = dfd_sat_u8(l); *A = dfd_sat_u8(a); *B = dfd_sat_u8(bb);
 }
 
+// L channel alone (the CLAHE histogram pass needs nothing else): same arithmetic as dfd_bgr2lab, fY only.
+DFD_HD int dfd_bgr2lab_L(const uint16_t* gamma, const uint16_t* cbrt, int b, int g, int r) {
+    int R = gamma[r], G = gamma[g], Bl = gamma[b];
+    int fY = cbrt[(R * 871 + G * 2929 + Bl * 296 + 2048) >> 12];
+    return dfd_sat_u8((296 * fY - 1336934 + 16384) >> 15);
+}
+
 // ---- Lab -> BGR (Lab2RGBinteger) (B.5) --------------------------------------
 DFD_HD int dfd_ab_to_xz(int i) {            // abToXZ_b[i - minABvalue]
     const int BASE = 16384;
