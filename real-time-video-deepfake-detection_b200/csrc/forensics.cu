@@ -22,6 +22,8 @@
 #define T 256
 
 // ---------------------------------------------------------------------------------------------
+// CTA = one output row of one frame; a thread reads the 2x2 taps of its pixel straight from the frame (12 byte loads
+// that the L1 merges per sector; staging the two source rows in shared memory with 16-byte loads measured slower).
 __global__ void __launch_bounds__(256) k_resize256(const uint8_t* __restrict__ frames, int H, int W, size_t fstride,
                                                    int pitch, uint8_t* __restrict__ tile, uint8_t* __restrict__ gray) {
     const int n = blockIdx.y, y = blockIdx.x, x = threadIdx.x;
@@ -64,6 +66,10 @@ __device__ __forceinline__ V block_sum_256(V v, V* sh /* [8] */) {
     return r;
 }
 
+// CTA = one 32x32 block of one frame.  A thread owns 4 vertically adjacent pixels of one column, so the 5x5 Gaussian runs
+// separably on an 8x5 register window (40 shared loads for 4 pixels instead of 100) and the Laplacian reads the same
+// registers.  Every sum is an exact integer: warp sums use redux.sync on 32-bit pieces (the one 64-bit quantity, the sum
+// of squared noise residuals, is reduced as 16-bit halves), one barrier, then 11 threads add the 8 warp partials.
 __global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ tile, const uint8_t* __restrict__ gray,
                                                     const int32_t* __restrict__ stream_ids,
                                                     const uint8_t* __restrict__ full, const DfdColorTables* __restrict__ tab,
@@ -73,63 +79,107 @@ __global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ 
     const int by = blk >> 3, bx = blk & 7;
     const bool is_full = full[n] != 0;
     const int sid = stream_ids[n];
-    __shared__ uint8_t sg[36][36];
-    __shared__ long long shll[8];
+    __shared__ uint8_t sg[36][40];
+    __shared__ int wpart[8][12];
     __shared__ unsigned int shue[6];
     const uint8_t* g = gray + (size_t)n * T * T;
     for (int i = threadIdx.x; i < 36 * 36; i += 256) {
-        int ly = i / 36, lx = i % 36;
+        int ly = i / 36, lx = i - ly * 36;
         int gy = dfd_reflect101(by * 32 + ly - 2, T), gx = dfd_reflect101(bx * 32 + lx - 2, T);
         sg[ly][lx] = g[gy * T + gx];
     }
     if (threadIdx.x < 6) shue[threadIdx.x] = 0;
     __syncthreads();
     uint8_t* prev = prev_gray + (size_t)sid * T * T;
-    long long nsx = 0, nsxx = 0, ls = 0, lss = 0, ss = 0, sss = 0, vs = 0, vss = 0, td = 0;
+    const int lx = threadIdx.x & 31, ly0 = (threadIdx.x >> 5) * 4, warp = threadIdx.x >> 5;
+    int ls = 0, lss = 0, td = 0, nsx = 0, ss = 0, sss = 0, vs = 0, vss = 0;
+    unsigned nsxx_lo = 0, nsxx_hi = 0;
+    if (is_full) {
+        int ctr[8][3];                              // columns lx+1..lx+3 of window rows 0..7 (window row j = block row ly0 + j - 2)
+        int hrow[8];                                // horizontal [1 4 6 4 1] sums of the 8 window rows
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int p = threadIdx.x + k * 256;
-        int ly = p >> 5, lx = p & 31;
-        int gy = by * 32 + ly, gx = bx * 32 + lx;
-        int c = sg[ly + 2][lx + 2];
-        int lap = sg[ly + 1][lx + 2] + sg[ly + 3][lx + 2] + sg[ly + 2][lx + 1] + sg[ly + 2][lx + 3] - 4 * c;
-        ls += lap; lss += lap * lap;
-        size_t gi = (size_t)gy * T + gx;
-        int pv = prev[gi];
-        td += dfd_absi(c - pv);
-        prev[gi] = (uint8_t)c;
-        if (is_full) {
-            const int kk[5] = {1, 4, 6, 4, 1};
-            int acc = 0;
+        for (int j = 0; j < 8; j++) {
+            const int a0 = sg[ly0 + j][lx], a1 = sg[ly0 + j][lx + 1], a2 = sg[ly0 + j][lx + 2], a3 = sg[ly0 + j][lx + 3], a4 = sg[ly0 + j][lx + 4];
+            ctr[j][0] = a1; ctr[j][1] = a2; ctr[j][2] = a3;
+            hrow[j] = a0 + 4 * a1 + 6 * a2 + 4 * a3 + a4;
+        }
+        const size_t g0 = (size_t)(by * 32 + ly0) * T + bx * 32 + lx;
+        int pv[4]; uint8_t t3[4][3];
 #pragma unroll
-            for (int j = 0; j < 5; j++) {
-                int row = 0;
+        for (int k = 0; k < 4; k++) {                // every global load of the thread is issued before the first use
+            pv[k] = prev[g0 + (size_t)k * T];
+            const uint8_t* tp = tile + ((size_t)n * T * T + g0 + (size_t)k * T) * 3;
+            t3[k][0] = tp[0]; t3[k][1] = tp[1]; t3[k][2] = tp[2];
+        }
 #pragma unroll
-                for (int i = 0; i < 5; i++) row += kk[i] * sg[ly + j][lx + i];
-                acc += kk[j] * row;
-            }
-            long long x = 256 * c - acc;
-            nsx += x; nsxx += x * x;
-            const uint8_t* t3 = tile + ((size_t)n * T * T + gi) * 3;
-            int h, s, v;
-            dfd_bgr2hsv(tab, t3[0], t3[1], t3[2], &h, &s, &v);
-            ss += s; sss += s * s; vs += v; vss += v * v;
+        for (int k = 0; k < 4; k++) {
+            const int c = ctr[k + 2][1];
+            const int lap = ctr[k + 1][1] + ctr[k + 3][1] + ctr[k + 2][0] + ctr[k + 2][2] - 4 * c;
+            ls += lap; lss += lap * lap;
+            td += dfd_absi(c - pv[k]);
+            prev[g0 + (size_t)k * T] = (uint8_t)c;
+            const int acc = hrow[k] + 4 * hrow[k + 1] + 6 * hrow[k + 2] + 4 * hrow[k + 3] + hrow[k + 4];
+            const int x = 256 * c - acc;            // |x| <= 65280
+            nsx += x;
+            const unsigned x2 = (unsigned)(x * x);  // < 2^32
+            nsxx_lo += x2 & 0xffffu; nsxx_hi += x2 >> 16;
+            int h, sv, v;
+            dfd_bgr2hsv(tab, t3[k][0], t3[k][1], t3[k][2], &h, &sv, &v);
+            ss += sv; sss += sv * sv; vs += v; vss += v * v;
             atomicOr(&shue[h >> 5], 1u << (h & 31));
         }
+    } else {
+        const size_t g0 = (size_t)(by * 32 + ly0) * T + bx * 32 + lx;
+        int pv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pv[k] = prev[g0 + (size_t)k * T];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ly = ly0 + k;
+            const int c = sg[ly + 2][lx + 2];
+            const int lap = sg[ly + 1][lx + 2] + sg[ly + 3][lx + 2] + sg[ly + 2][lx + 1] + sg[ly + 2][lx + 3] - 4 * c;
+            ls += lap; lss += lap * lap;
+            td += dfd_absi(c - pv[k]);
+            prev[g0 + (size_t)k * T] = (uint8_t)c;
+        }
     }
+    int q[11] = {ls, lss, td, nsx, (int)nsxx_lo, (int)nsxx_hi, ss, sss, vs, vss, 0};
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        if (i < 3 || is_full) {
+            const int r = __reduce_add_sync(0xffffffffu, q[i]);
+            if (lx == 0) wpart[warp][i] = r;
+        }
+    }
+    __syncthreads();
     DfdFramePartials* P = part + n;
-    long long r;
-    r = block_sum_256(ls, shll);  if (threadIdx.x == 0) P->lap_s[blk] = r;
-    r = block_sum_256(lss, shll); if (threadIdx.x == 0) P->lap_ss[blk] = r;
-    r = block_sum_256(td, shll);  if (threadIdx.x == 0) P->tdiff[blk] = (int)r;
+    if (threadIdx.x < 10 && (threadIdx.x < 3 || is_full)) {
+        long long r = 0;
+        if (threadIdx.x == 4 || threadIdx.x == 5) {                // unsigned halves of the squared residuals
+            for (int w = 0; w < 8; w++) r += (unsigned)wpart[w][threadIdx.x];
+        } else {
+            for (int w = 0; w < 8; w++) r += wpart[w][threadIdx.x];
+        }
+        switch (threadIdx.x) {
+            case 0: P->lap_s[blk] = r; break;
+            case 1: P->lap_ss[blk] = r; break;
+            case 2: P->tdiff[blk] = (int)r; break;
+            case 3: P->noise_sx[blk] = r; break;
+            case 4: wpart[0][10] = 0; P->noise_sxx[blk] = r; break;          // low halves; the high halves are added below
+            case 6: P->sat_s[blk] = (unsigned long long)r; break;
+            case 7: P->sat_ss[blk] = (unsigned long long)r; break;
+            case 8: P->val_s[blk] = (unsigned long long)r; break;
+            case 9: P->val_ss[blk] = (unsigned long long)r; break;
+            default: break;
+        }
+    }
     if (is_full) {
-        r = block_sum_256(nsx, shll);  if (threadIdx.x == 0) P->noise_sx[blk] = r;
-        r = block_sum_256(nsxx, shll); if (threadIdx.x == 0) P->noise_sxx[blk] = r;
-        r = block_sum_256(ss, shll);   if (threadIdx.x == 0) P->sat_s[blk] = (unsigned long long)r;
-        r = block_sum_256(sss, shll);  if (threadIdx.x == 0) P->sat_ss[blk] = (unsigned long long)r;
-        r = block_sum_256(vs, shll);   if (threadIdx.x == 0) P->val_s[blk] = (unsigned long long)r;
-        r = block_sum_256(vss, shll);  if (threadIdx.x == 0) P->val_ss[blk] = (unsigned long long)r;
         __syncthreads();
+        if (threadIdx.x == 5) {
+            long long hi = 0;
+            for (int w = 0; w < 8; w++) hi += (unsigned)wpart[w][5];
+            P->noise_sxx[blk] += hi << 16;
+        }
         if (threadIdx.x < 6) P->hue_bits[blk][threadIdx.x] = shue[threadIdx.x];
     }
 }
