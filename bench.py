@@ -415,7 +415,9 @@ def main():
                        "submission": "one CUDA graph replay per step" if graphs is not None else "host launches",
                        "collective": "nccl all_gather of 72-B verdict records" if world > 1 else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(ms_e2e.item()) / K, "note": "pinned host frames, H2D double-buffered on a copy stream"},
+                    "ms_per_step": float(ms_e2e.item()) / K, "h2d_gbs_per_gpu": round(h2d / (float(ms_e2e.item()) / K) / 1e6, 1),
+                    "note": "pinned host frames, H2D double-buffered on a copy stream; bound by the PCIe Gen5 x16 link "
+                            "(2.76 MB of raw frame per frame), not by the kernels"},
             "gpu_launches": int(launches), "crops_per_sec": value, "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu, "latency": latency, "top_kernels": functions[:6],
         }

@@ -34,6 +34,7 @@
 #include "dfd_internal.cuh"
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 #include "tc_ptx.cuh"
 
 #define BLOCK_M 128
@@ -60,6 +61,8 @@ struct GemmParams {
     const float* bias;
     const __nv_bfloat16* residual;
     const __nv_bfloat16* A;    // A_STEM: NHWC input [B,224,224,3]
+    __nv_bfloat16* C;          // output matrix (dense epilogue: the 128 x N tile is one contiguous block of C)
+    int dense_c;               // N <= 64 and one N block: stage the tile densely and write it with ONE bulk copy
     const float* se;           // A_SCALE: [images][K] gates
 };
 
@@ -194,14 +197,19 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int c = t & 7;
                         const int k = kb * BLOCK_K + c * 8;
                         if (k < p.K) {
+                            // image of a row without a division per row: one division per tile, then the (at most 3, hw >= 49)
+                            // image boundaries inside the 128-row tile by comparison
+                            const int img0 = m0 / p.hw, rem0 = m0 - img0 * p.hw;
+                            const int last = p.M - 1 - m0;                         // rows beyond M are clamped to the last row
 #pragma unroll
                             for (int hb = 0; hb < 2; hb++) {
                                 uint4 v[4]; float4 s0[4], s1[4];
 #pragma unroll
                                 for (int i = 0; i < 4; i++) {
                                     const int row = (hb * 4 + i) * 16 + (t >> 3);
-                                    int m = m0 + row; if (m >= p.M) m = p.M - 1;
-                                    const float* sp = p.se + (size_t)(m / p.hw) * p.K + k;
+                                    const int rr = rem0 + (row < last ? row : last);
+                                    const int img = img0 + (rr >= p.hw) + (rr >= 2 * p.hw) + (rr >= 3 * p.hw);
+                                    const float* sp = p.se + (size_t)img * p.K + k;
                                     s0[i] = __ldg((const float4*)sp); s1[i] = __ldg((const float4*)(sp + 4));
                                     v[i] = lds128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)));
                                 }
@@ -331,7 +339,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             __nv_bfloat162* oh = (__nv_bfloat162*)&o;
 #pragma unroll
                             for (int jj = 0; jj < 4; jj++) oh[jj] = __floats2bfloat162_rn(v[2 * jj], v[2 * jj + 1]);
-                            sts128(buf + (uint32_t)(row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4)), o);
+                            if (p.dense_c) { if (col < p.N) sts128(buf + (uint32_t)(row * (p.N * 2) + (col >> 3) * 16), o); }
+                            else sts128(buf + (uint32_t)(row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4)), o);
                         }
                     }
                 }
@@ -339,7 +348,15 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 set_bar_sync(1 + grp);
                 if (issuer) {
                     if (n_base + jb * 64 < p.N && !(p.debug & 1)) {
-                        if (p.a_mode == A_IMG) tma_store_3d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, img, buf);
+                        if (p.dense_c) {
+                            // rows of a narrow C tile are 32-128 bytes: 128 separate row writes through the tensor path cost
+                            // more than the tile's math; the tile is contiguous in C, so it goes out as ONE bulk copy
+                            const int lim = p.a_mode == A_IMG ? p.hw : p.M;
+                            const int rows = min(BLOCK_M, lim - m_blk * BLOCK_M);
+                            const size_t g_row = (size_t)(p.a_mode == A_IMG ? img * p.hw : 0) + (size_t)m_blk * BLOCK_M;
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                         ::"l"(p.C + g_row * p.N), "r"(buf), "r"((uint32_t)(rows * p.N * 2)) : "memory");
+                        } else if (p.a_mode == A_IMG) tma_store_3d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, img, buf);
                         else tma_store_2d(&map_c, n_base + jb * 64, m_blk * BLOCK_M, buf);
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -405,6 +422,7 @@ int dfd_tmap_bf16(dfd_ctx* ctx, CUtensorMap* m, const void* base, int rank, cons
     return DFD_OK;
 }
 
+static bool g_no_dense = getenv("DFD_NO_DENSE_C") != nullptr;     // A/B switch for the dense bulk-store epilogue
 static bool g_enabled = true;
 static int g_debug = 0;
 bool dfd_gemm_bf16_enabled() { return g_enabled; }
@@ -421,6 +439,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.act = act; p.bias = bias; p.residual = residual;
     p.a_mode = a_mode; p.A = A; p.se = se; p.hw = hw > 0 ? hw : 1; p.debug = g_debug; p.tiles_per_img = 1;
+    p.C = C; p.dense_c = (N <= 64 && !g_no_dense) ? 1 : 0;
     // N tiling: the smallest number of equal UMMA-N blocks (multiples of 16, <= 256) covering N
     // (with several N blocks the block width is a multiple of 64 so the 64-column TMA stores of one block
     // never touch its neighbour's columns)
@@ -473,6 +492,7 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
     memset(&p, 0, sizeof p);
     p.M = n_img * hw; p.N = N; p.K = K; p.act = act; p.bias = bias; p.residual = residual;
     p.a_mode = A_IMG; p.A = A; p.se = nullptr; p.hw = hw; p.debug = 0;
+    p.C = C; p.dense_c = (N <= 64 && !g_no_dense) ? 1 : 0;
     p.n_pad = (N + 15) / 16 * 16; p.n_blocks = 1;
     p.tiles_per_img = (hw + BLOCK_M - 1) / BLOCK_M;
     p.num_tiles = n_img * p.tiles_per_img;
