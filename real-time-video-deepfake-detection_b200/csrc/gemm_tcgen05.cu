@@ -62,6 +62,7 @@ struct GemmParams {
     const __nv_bfloat16* residual;
     const __nv_bfloat16* A;    // A_STEM: NHWC input [B,224,224,3]
     __nv_bfloat16* C;          // output matrix (dense epilogue: the 128 x N tile is one contiguous block of C)
+    int epi_db;                // staging modes: 1 = two store-staging buffers per epilogue set, 0 = one (frees 32 KB for pipeline stages)
     int dense_c;               // N <= 64 and one N block: stage the tile densely and write it with ONE bulk copy
     const float* se;           // A_SCALE: [images][K] gates
 };
@@ -276,7 +277,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int row = q * 32 + lane;
         const bool issuer = q == 0 && lane == 0;
         // staging: 4 x 16 KB; unsplit groups own two buffers (double-buffered), split groups own one
-        const uint32_t my_staging = staging + (uint32_t)(split ? grp : 2 * set) * STAGING_BLOCK_BYTES;
+        const uint32_t my_staging = staging + (uint32_t)(split ? grp : (p.epi_db ? 2 * set : set)) * STAGING_BLOCK_BYTES;
         const int nblk64 = (p.n_pad + 63) >> 6;
         uint32_t blk_count = 0, acc_phase = 0;
         int it = 0;
@@ -298,9 +299,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.n_pad);
             const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
             for (int jb = split ? half : 0; jb < ((p.debug & 16) ? 0 : nblk64); jb += split ? 2 : 1, blk_count++) {
-                const uint32_t buf = my_staging + (split ? 0u : (blk_count & 1u) * STAGING_BLOCK_BYTES);
+                const uint32_t buf = my_staging + ((split || !p.epi_db) ? 0u : (blk_count & 1u) * STAGING_BLOCK_BYTES);
                 if (issuer) {                                      // this buffer's previous store has been read
-                    if (split) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (split || !p.epi_db) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 }
                 set_bar_sync(1 + grp);
@@ -409,15 +410,16 @@ static int make_map(dfd_ctx* ctx, CUtensorMap* m, const void* base, uint64_t row
 
 // generic bf16 tiled map (rank <= 4), 128-byte swizzle, zero OOB fill -- used by mbconv_fused.cu for NHWC patches
 int dfd_tmap_bf16(dfd_ctx* ctx, CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+                  const uint32_t* box, int swizzle_bytes) {
     int rc = get_encode(ctx);
     if (rc) return rc;
     cuuint64_t d[4], s[3];
     cuuint32_t b[4], e[4] = {1, 1, 1, 1};
     for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; }
     for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
+    const CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled (rank " + std::to_string(rank) + ") failed (" + std::to_string((int)r) + ")"; return DFD_ERR_CUDA; }
     return DFD_OK;
 }
@@ -449,7 +451,8 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     p.num_tiles = m_blocks * p.n_blocks;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-    const int staging_bytes = 4 * STAGING_BLOCK_BYTES;       // two 16 KB buffers per epilogue set
+    int staging_bytes = 4 * STAGING_BLOCK_BYTES;             // two 16 KB buffers per epilogue set
+    p.epi_db = 1;
     // W stays resident in shared memory when it fits next to >= 3 A stages: every tile then loads only A
     // (measured: 148 CTAs re-fetching the same few KB of W per tile serialise on one L2 slice, 1-2 us per tile)
     const int b_bytes = num_kb * n_pad * BLOCK_K * 2;
@@ -463,6 +466,15 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     // other phase of a stage and a parity wait could alias with the phase two uses earlier (seen as a rare hang of
     // b7.project with 3 stages).
     if (a_mode != A_TMA) stages &= ~1;
+    if (a_mode != A_TMA && stages < 6 && !getenv("DFD_GEMM_EPI_DB")) {
+        // deep-K layers with a wide, non-resident W: the k-block pipeline, not the epilogue, is the limit; give the
+        // 32 KB of the second store-staging buffers to pipeline stages instead
+        const int sb2 = 2 * STAGING_BLOCK_BYTES;
+        int st2 = (204 * 1024 - sb2 - (p.b_resident ? b_bytes : 0)) / stage_bytes;
+        if (st2 > 8) st2 = 8;
+        st2 &= ~1;
+        if (st2 > stages) { stages = st2; staging_bytes = sb2; p.epi_db = 0; }
+    }
     DFD_REQUIRE(stages >= 2, DFD_ERR_INVALID, "gemm: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes + 1024;
@@ -492,7 +504,7 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
     memset(&p, 0, sizeof p);
     p.M = n_img * hw; p.N = N; p.K = K; p.act = act; p.bias = bias; p.residual = residual;
     p.a_mode = A_IMG; p.A = A; p.se = nullptr; p.hw = hw; p.debug = 0;
-    p.C = C; p.dense_c = (N <= 64 && !g_no_dense) ? 1 : 0;
+    p.C = C; p.dense_c = (N <= 64 && !g_no_dense) ? 1 : 0; p.epi_db = 1;
     p.n_pad = (N + 15) / 16 * 16; p.n_blocks = 1;
     p.tiles_per_img = (hw + BLOCK_M - 1) / BLOCK_M;
     p.num_tiles = n_img * p.tiles_per_img;
@@ -513,17 +525,17 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
     {
         const uint64_t d[3] = {(uint64_t)K, (uint64_t)hw, (uint64_t)n_img}, s[2] = {(uint64_t)K * 2, (uint64_t)hw * K * 2};
         const uint32_t b[3] = {BLOCK_K, BLOCK_M, 1};
-        if ((rc = dfd_tmap_bf16(ctx, &ma, A, 3, d, s, b))) return rc;
+        if ((rc = dfd_tmap_bf16(ctx, &ma, A, 3, d, s, b, 128))) return rc;
     }
     {
         const uint64_t d[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)n_img}, s[2] = {(uint64_t)K * 2, (uint64_t)N * K * 2};
         const uint32_t b[3] = {BLOCK_K, (uint32_t)p.n_pad, 1};
-        if ((rc = dfd_tmap_bf16(ctx, &mb, Wg, 3, d, s, b))) return rc;
+        if ((rc = dfd_tmap_bf16(ctx, &mb, Wg, 3, d, s, b, 128))) return rc;
     }
     {
         const uint64_t d[3] = {(uint64_t)N, (uint64_t)hw, (uint64_t)n_img}, s[2] = {(uint64_t)N * 2, (uint64_t)hw * N * 2};
         const uint32_t b[3] = {BLOCK_K, BLOCK_M, 1};
-        if ((rc = dfd_tmap_bf16(ctx, &mc, C, 3, d, s, b))) return rc;
+        if ((rc = dfd_tmap_bf16(ctx, &mc, C, 3, d, s, b, 128))) return rc;
     }
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
     DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));

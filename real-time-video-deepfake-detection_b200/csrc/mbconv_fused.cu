@@ -30,11 +30,10 @@
 
 #define MF_THREADS 320
 #define MF_CWARPS 8               // consumer warps
-#define MF_NT 4                   // TMEM accumulator ring depth (128-row blocks)
 #define MF_NB 2                   // B ring depth (chunks)
 
 int dfd_tmap_bf16(dfd_ctx* ctx, CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box);
+                  const uint32_t* box, int swizzle_bytes);
 
 struct FrontParams {
     const float* aux;            // packed per chunk: Wd[K*K][CC], 0.5*be[CC], bd[CC]
@@ -98,7 +97,7 @@ __device__ __forceinline__ uint64_t mf_swish2(uint64_t x, uint64_t half_bias) {
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE>
+template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE, int KW, int NT>
 struct MfGeom {
     static constexpr int HOUT = (HIN + S - 1) / S;
     static constexpr int PAD_TOTAL = (HOUT - 1) * S + K - HIN > 0 ? (HOUT - 1) * S + K - HIN : 0;
@@ -106,13 +105,14 @@ struct MfGeom {
     static constexpr int PH = WHOLE ? HIN : (TH - 1) * S + K, PW = WHOLE ? HIN : (TW - 1) * S + K;
     static constexpr int NPIX = PH * PW;                         // patch pixels = MMA rows that carry data
     static constexpr int N_MB = (NPIX + 127) / 128;
-    static constexpr int A_KB_BYTES = (NPIX * 128 + 1023) & ~1023;   // one 64-channel k-block of the A operand (tight)
+    static constexpr int ROWB = KW * 2;                          // bytes per operand row = swizzle width (32 / 64 / 128)
+    static constexpr int A_KB_BYTES = (NPIX * ROWB + 1023) & ~1023;  // one KW-channel k-block of the A operand (tight)
     static constexpr int AUX_FLOATS = (K * K + 2) * CC;          // Wd chunk, be chunk, bd chunk
     static constexpr int AUX_BYTES = (AUX_FLOATS * 4 + 127) & ~127;
     static constexpr int PITCH = CC * 2 + 16;                    // patch bytes per pixel (+16: conflict-free 16-byte stores)
     static constexpr int PATCH_BYTES = (NPIX * PITCH + 127) & ~127;
-    static constexpr int TM_COLS = MF_NT * CC <= 128 ? 128 : 256;
-    static int b_stage_bytes(int num_kb) { return (num_kb * CC * 128 + AUX_BYTES + 1023) & ~1023; }
+    static constexpr int TM_COLS = NT * CC <= 128 ? 128 : 256;
+    static int b_stage_bytes(int num_kb) { return (num_kb * CC * ROWB + AUX_BYTES + 1023) & ~1023; }
     // (the MMA of the last 128-row block reads N_MB*128 rows from each k-block base; the overrun past the tight
     //  A slots lands in the B ring / patch that follow them inside the same allocation: garbage rows, never used)
     static size_t smem_bytes(int num_kb, int na) {
@@ -120,11 +120,12 @@ struct MfGeom {
     }
 };
 
-template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE>
-__global__ void __launch_bounds__(MF_THREADS, 2)
+template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE, int KW, int NT, int MINB>
+__global__ void __launch_bounds__(MF_THREADS, MINB)
 k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FrontParams p) {
-    using G = MfGeom<K, S, TW, TH, CC, HIN, WHOLE>;
-    constexpr int PW = G::PW, NPIX = G::NPIX, N_MB = G::N_MB, PITCH = G::PITCH, PITCH_W = G::PITCH / 4, PAD = G::PAD;
+    using G = MfGeom<K, S, TW, TH, CC, HIN, WHOLE, KW, NT>;
+    constexpr int PW = G::PW, NPIX = G::NPIX, N_MB = G::N_MB, PITCH = G::PITCH, PITCH_W = G::PITCH / 4, PAD = G::PAD, ROWB = G::ROWB;
+    constexpr int MF_NT = NT;
     extern __shared__ __align__(1024) uint8_t smem_mf[];
     __shared__ __align__(8) uint64_t bars[2 + 2 + MF_NB * 2 + MF_NT * 2];
     __shared__ uint32_t tmem_slot;
@@ -133,14 +134,14 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t s0 = smem_u32(smem_mf);
     const uint32_t a_base = (s0 + 1023u) & ~1023u;
     const int a_slot_bytes = p.num_kb * G::A_KB_BYTES;
-    const int b_stage = (p.num_kb * CC * 128 + G::AUX_BYTES + 1023) & ~1023;
+    const int b_stage = (p.num_kb * CC * ROWB + G::AUX_BYTES + 1023) & ~1023;
     const uint32_t b_base = a_base + (uint32_t)(p.na * a_slot_bytes);
     const uint32_t patch_s = b_base + (uint32_t)(MF_NB * b_stage);
     uint8_t* gen = smem_mf + (a_base - s0);
     const uint8_t* b_gen = gen + p.na * a_slot_bytes;
     uint32_t* patch = (uint32_t*)(gen + p.na * a_slot_bytes + MF_NB * b_stage);
     float* spool = (float*)((uint8_t*)patch + G::PATCH_BYTES);           // [MF_CWARPS][CC]
-    const int aux_off = p.num_kb * CC * 128;                              // aux block inside a B stage
+    const int aux_off = p.num_kb * CC * ROWB;                             // aux block inside a B stage
 
     const uint32_t bar0 = smem_u32(&bars[0]);
     const uint32_t a_full = bar0, a_empty = bar0 + 16, b_full = bar0 + 32, b_empty = b_full + 8 * MF_NB;
@@ -176,15 +177,15 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
                 const int iy0 = WHOLE ? 0 : ty * TH * S - PAD, ix0 = WHOLE ? 0 : tx * TW * S - PAD;
                 mbar_wait_backoff(a_empty + 8 * as, aph ^ 1, 256);
-                mbar_expect_tx(a_full + 8 * as, (uint32_t)(p.num_kb * NPIX * 128));
+                mbar_expect_tx(a_full + 8 * as, (uint32_t)(p.num_kb * NPIX * ROWB));
                 for (int kb = 0; kb < p.num_kb; kb++)
-                    tma_load_4d(a_base + as * a_slot_bytes + kb * G::A_KB_BYTES, &map_x, kb * 64, ix0, iy0, b, a_full + 8 * as);
+                    tma_load_4d(a_base + as * a_slot_bytes + kb * G::A_KB_BYTES, &map_x, kb * KW, ix0, iy0, b, a_full + 8 * as);
                 if (++as == p.na) { as = 0; aph ^= 1; }
                 for (int ch = ch_lo; ch < ch_hi; ch++) {
                     mbar_wait_backoff(b_empty + 8 * bs, bph ^ 1, 256);
                     const uint32_t dst = b_base + bs * b_stage;
-                    mbar_expect_tx(b_full + 8 * bs, (uint32_t)(p.num_kb * CC * 128 + G::AUX_FLOATS * 4));
-                    for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(dst + kb * CC * 128, &map_w, kb * 64, ch * CC, b_full + 8 * bs);
+                    mbar_expect_tx(b_full + 8 * bs, (uint32_t)(p.num_kb * CC * ROWB + G::AUX_FLOATS * 4));
+                    for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(dst + kb * CC * ROWB, &map_w, kb * KW, ch * CC, b_full + 8 * bs);
                     bulk_load(dst + aux_off, p.aux + (size_t)ch * G::AUX_FLOATS, G::AUX_FLOATS * 4, b_full + 8 * bs);
                     if (++bs == MF_NB) { bs = 0; bph ^= 1; }
                 }
@@ -211,10 +212,10 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)(ts * CC);
                         for (int kb = 0; kb < p.num_kb; kb++) {
-                            const uint64_t adesc = make_smem_desc(a_slot + kb * G::A_KB_BYTES + mb * 16384);
-                            const uint64_t bdesc = make_smem_desc(bsm + kb * CC * 128);
-                            const int krem = p.cin - kb * 64;
-                            const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
+                            const uint64_t adesc = make_smem_desc_rows<ROWB>(a_slot + kb * G::A_KB_BYTES + mb * 128 * ROWB);
+                            const uint64_t bdesc = make_smem_desc_rows<ROWB>(bsm + kb * CC * ROWB);
+                            const int krem = p.cin - kb * KW;
+                            const int ksteps = krem >= KW ? KW / 16 : (krem + 15) / 16;
                             for (int k = 0; k < ksteps; k++)
                                 tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                         }
@@ -397,22 +398,22 @@ int dfd_front_pack(dfd_ctx* ctx, const float* blob) {
     return DFD_OK;
 }
 
-template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE>
+template <int K, int S, int TW, int TH, int CC, int HIN, bool WHOLE, int KW = 64, int NT = 4, int MINB = 2>
 static int launch_front(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __nv_bfloat16* We, __nv_bfloat16* out, int m,
                         int* n_parts, cudaStream_t st) {
-    using G = MfGeom<K, S, TW, TH, CC, HIN, WHOLE>;
+    using G = MfGeom<K, S, TW, TH, CC, HIN, WHOLE, KW, NT>;
     const EffBlock& b = EFF_BLOCKS[blk];
     DFD_REQUIRE(G::PAD == b.pad && G::HOUT == b.hout && front_cc(blk) == CC, DFD_ERR_INVALID, "mbconv_front: geometry mismatch");
-    const int num_kb = (b.cin + 63) / 64;
-    // two A slots when two CTAs still fit one SM, else one
-    const size_t budget = 112 * 1024;
+    const int num_kb = (b.cin + KW - 1) / KW;
+    // two A slots when MINB CTAs still fit one SM, else one
+    const size_t budget = (size_t)(227 * 1024) / MINB - 1536;
     const int na = G::smem_bytes(num_kb, 2) <= budget ? 2 : 1;
     const size_t smem = G::smem_bytes(num_kb, na);
     static size_t attr_bytes = 0;
     if (smem > attr_bytes) {
-        DFD_CUDA(cudaFuncSetAttribute(k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DFD_CUDA(cudaFuncSetAttribute(k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE, KW, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // two CTAs per SM need the full shared-memory carve-out (the driver's default picks a smaller one)
-        DFD_CUDA(cudaFuncSetAttribute(k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        DFD_CUDA(cudaFuncSetAttribute(k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE, KW, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_bytes = smem;
     }
     CUtensorMap mx, mw;
@@ -420,14 +421,14 @@ static int launch_front(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __n
     {
         const uint64_t dims[4] = {(uint64_t)b.cin, (uint64_t)b.hin, (uint64_t)b.hin, (uint64_t)m};
         const uint64_t str[3] = {(uint64_t)b.cin * 2, (uint64_t)b.hin * b.cin * 2, (uint64_t)b.hin * b.hin * b.cin * 2};
-        const uint32_t box[4] = {64, (uint32_t)G::PW, (uint32_t)G::PH, 1};
-        if ((rc = dfd_tmap_bf16(ctx, &mx, x, 4, dims, str, box))) return rc;
+        const uint32_t box[4] = {(uint32_t)KW, (uint32_t)G::PW, (uint32_t)G::PH, 1};
+        if ((rc = dfd_tmap_bf16(ctx, &mx, x, 4, dims, str, box, G::ROWB))) return rc;
     }
     {
         const uint64_t dims[2] = {(uint64_t)b.cin, (uint64_t)b.cexp};
         const uint64_t str[1] = {(uint64_t)b.cin * 2};
-        const uint32_t box[2] = {64, (uint32_t)CC};
-        if ((rc = dfd_tmap_bf16(ctx, &mw, We, 2, dims, str, box))) return rc;
+        const uint32_t box[2] = {(uint32_t)KW, (uint32_t)CC};
+        if ((rc = dfd_tmap_bf16(ctx, &mw, We, 2, dims, str, box, G::ROWB))) return rc;
     }
     FrontParams p;
     p.aux = ctx->d_front_aux + ctx->front_aux_off[blk];
@@ -438,15 +439,15 @@ static int launch_front(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __n
     p.n_chunks = (b.cexp + CC - 1) / CC;
     // enough items to occupy every CTA slot at small batch: split the chunk loop of an (image, tile) across items
     p.csplit = 1;
-    while (m * p.tiles * p.csplit < 2 * ctx->sm_count && p.csplit < p.n_chunks) p.csplit++;
+    while (m * p.tiles * p.csplit < MINB * ctx->sm_count && p.csplit < p.n_chunks) p.csplit++;
     p.cpi = (p.n_chunks + p.csplit - 1) / p.csplit;
     p.csplit = (p.n_chunks + p.cpi - 1) / p.cpi;              // no empty items
     p.n_items = m * p.tiles * p.csplit;
     *n_parts = p.tiles;
     if ((size_t)p.tiles * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
-    int grid = 2 * ctx->sm_count;
+    int grid = MINB * ctx->sm_count;
     if (grid > p.n_items) grid = p.n_items;
-    DFD_CUDA(dfd_launch(ctx->pdl, k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE>, dim3(grid), dim3(MF_THREADS), smem, st, mx, mw, p));
+    DFD_CUDA(dfd_launch(ctx->pdl, k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE, KW, NT, MINB>, dim3(grid), dim3(MF_THREADS), smem, st, mx, mw, p));
     DFD_LAUNCH_CHECK("k_mbconv_front", st);
     return DFD_OK;
 }
@@ -456,9 +457,9 @@ int dfd_mbconv_front_bf16(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const _
                           int* n_parts, cudaStream_t st) {
     const EffBlock& b = EFF_BLOCKS[blk];
 #define MF_ARGS ctx, blk, x, We, out, m, n_parts, st
-    if (b.k == 3 && b.s == 2 && b.hin == 112) return launch_front<3, 2, 7, 8, 48, 112, false>(MF_ARGS);
-    if (b.k == 3 && b.s == 1 && b.hin == 56) return launch_front<3, 1, 14, 14, 48, 56, false>(MF_ARGS);
-    if (b.k == 5 && b.s == 2 && b.hin == 56) return launch_front<5, 2, 7, 7, 48, 56, false>(MF_ARGS);
+    if (b.k == 3 && b.s == 2 && b.hin == 112) return launch_front<3, 2, 7, 8, 48, 112, false, 16, 2, 3>(MF_ARGS);      // 16 input channels: 32-byte operand rows
+    if (b.k == 3 && b.s == 1 && b.hin == 56) return launch_front<3, 1, 14, 14, 48, 56, false, 32, 4, 2>(MF_ARGS);    // 24 input channels: 64-byte operand rows
+    if (b.k == 5 && b.s == 2 && b.hin == 56) return launch_front<5, 2, 7, 7, 48, 56, false, 32, 4, 2>(MF_ARGS);
     if (b.k == 5 && b.s == 1 && b.hin == 28) return launch_front<5, 1, 14, 14, 48, 28, false>(MF_ARGS);
     if (b.k == 3 && b.s == 2 && b.hin == 28) return launch_front<3, 2, 7, 7, 48, 28, false>(MF_ARGS);
     if (b.k == 3 && b.s == 1 && b.hin == 14) return launch_front<3, 1, 14, 14, 48, 14, true>(MF_ARGS);

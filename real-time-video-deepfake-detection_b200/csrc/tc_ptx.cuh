@@ -21,26 +21,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
 }
-// Same wait for warps that run AHEAD of the data path (TMA producer, MMA issuer): back off between polls so the
-// spinning lane does not take issue slots from the warps doing the math on the same SM sub-partition.
+// Wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or the hint elapses)
+// instead of polling, so waiting warps (TMA producer, MMA issuer, epilogue warps ahead of the data) take no issue slots
+// from the warps doing the math.  `ns` is ignored as a back-off now and kept as the hint.
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
+    (void)ns;
     uint32_t done;
-    for (;;) {
+    do {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(ns);
-    }
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+    } while (!done);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -102,6 +102,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Same for rows of ROWB = 32 / 64 / 128 bytes (SWIZZLE_32B = 6, SWIZZLE_64B = 4, SWIZZLE_128B = 2): SBO = 8 rows * ROWB.
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_smem_desc_rows(uint32_t smem_addr) {
+    constexpr uint64_t LT = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= LT << 61;
     return d;
 }
 
