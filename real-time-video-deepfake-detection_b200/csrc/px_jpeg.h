@@ -88,21 +88,39 @@ DFD_HD void dfd_idct8(int* c, int st, int first) {
     c[3 * st] = dfd_descale(t13 + a0, sh); c[4 * st] = dfd_descale(t13 - a0, sh);
 }
 
-// Full round trip of one 8x8 block held as ints (samples 0..255 in, 0..255 out).
-DFD_HD void dfd_jpeg_block_roundtrip(int* blk, int chroma) {
+// Full round trip of one 8x8 block held as ints (samples 0..255 in, 0..255 out).  Fully unrolled with the component as
+// a template parameter: the block stays in registers and every quantiser is a compile-time constant, so the 64
+// divisions become multiply-shifts.
+#if defined(__CUDACC__)
+#define DFD_UNROLL _Pragma("unroll")
+#else
+#define DFD_UNROLL
+#endif
+template <int CHROMA>
+DFD_HD void dfd_jpeg_block_roundtrip_t(int* blk) {
+    DFD_UNROLL
     for (int i = 0; i < 64; i++) blk[i] -= 128;
+    DFD_UNROLL
     for (int r = 0; r < 8; r++) dfd_fdct8(blk + 8 * r, 1, 1);
+    DFD_UNROLL
     for (int c = 0; c < 8; c++) dfd_fdct8(blk + c, 8, 0);
+    DFD_UNROLL
     for (int i = 0; i < 64; i++) {
-        int q = dfd_jpeg_q90(chroma, i);
+        const int q = dfd_jpeg_q90(CHROMA, i);
         int v = blk[i];
         int a = v < 0 ? -v : v;
         a = (a + 4 * q) / (8 * q);
         blk[i] = (v < 0 ? -a : a) * q;
     }
+    DFD_UNROLL
     for (int c = 0; c < 8; c++) dfd_idct8(blk + c, 8, 1);
+    DFD_UNROLL
     for (int r = 0; r < 8; r++) dfd_idct8(blk + 8 * r, 1, 0);
+    DFD_UNROLL
     for (int i = 0; i < 64; i++) blk[i] = dfd_sat_u8(blk[i] + 128);
+}
+DFD_HD void dfd_jpeg_block_roundtrip(int* blk, int chroma) {
+    if (chroma) dfd_jpeg_block_roundtrip_t<1>(blk); else dfd_jpeg_block_roundtrip_t<0>(blk);
 }
 
 // h2v2 fancy up-sampling of one chroma sample position (jdsample.c).
