@@ -371,15 +371,18 @@ __global__ void __launch_bounds__(1024) k_fft_rows(const uint8_t* __restrict__ g
         s[f][bitrev8(j)] = make_float2((float)g[row0 * T + j], (float)g[(row0 + 1) * T + j]);
     __syncthreads();
     fft256(s[f], tw, t, 0, 0);
-    float2* o = out + (size_t)n * 129 * 256;
+    // the 16 rows of this CTA are 128 contiguous bytes of every output column k: gather them in shared memory and write
+    // full 128-byte segments (a thread writing its own (k, row) pair scatters 8-byte stores 2 KB apart)
+    __shared__ float2 os[129][16];
     for (int k = t; k <= 128; k += 128) {
         float2 zk = s[f][k], zn = s[f][(256 - k) & 255];
         // F1 = (Zk + conj(Zn))/2 ; F2 = (Zk - conj(Zn))/(2i)
-        float2 f1 = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-        float2 f2 = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
-        o[(size_t)k * 256 + row0] = f1;
-        o[(size_t)k * 256 + row0 + 1] = f2;
+        os[k][2 * f] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        os[k][2 * f + 1] = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
     }
+    __syncthreads();
+    float2* o = out + (size_t)n * 129 * 256 + grp * 16;
+    for (int i = threadIdx.x; i < 129 * 16; i += 1024) o[(size_t)(i >> 4) * 256 + (i & 15)] = os[i >> 4][i & 15];
 }
 
 // columns: CTA = 8 half-spectrum columns; grid (17, n).
