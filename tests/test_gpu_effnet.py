@@ -183,3 +183,19 @@ def test_gated_weight_project_matches_gated_activation(setup, blk):
     scale = max(1.0, float(got[1].abs().max()))
     print("gated-w vs gated-a: max", float(d.max()), "mean", float(d.mean()), "scale", scale)
     assert float(d.max()) <= 2.0 ** -5 * scale and float(d.mean()) <= 2.0 ** -9 * scale
+
+
+def test_batch_invariance_bf16_small_batches(setup):
+    """bf16 path: an image's logit does not depend on the batch it is in.  Batches of 1 and 2 take the chunk-split items of
+    the fused MBConv kernel (an (image, tile) is split across CTAs so one image still fills the chip), ragged GEMM tiles
+    and partially filled SE clusters -- all of which must be bit-identical to the batch-24 result."""
+    e, sd, x, ref, taps = setup
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    full = e.effnet_forward(xn).cpu()
+    for i in (0, 5, 23):
+        one = e.effnet_forward(xn[i:i + 1].contiguous()).cpu()
+        assert torch.equal(one, full[i:i + 1]), (i, float(one), float(full[i]))
+    two = e.effnet_forward(xn[7:9].contiguous()).cpu()
+    assert torch.equal(two, full[7:9])
+    seven = e.effnet_forward(xn[10:17].contiguous()).cpu()
+    assert torch.equal(seven, full[10:17])
