@@ -62,6 +62,7 @@ struct GemmParams {
     const __nv_bfloat16* residual;
     const __nv_bfloat16* A;    // A_STEM: NHWC input [B,224,224,3]
     __nv_bfloat16* C;          // output matrix (dense epilogue: the 128 x N tile is one contiguous block of C)
+    int n_acc;                 // TMEM accumulator ring depth (even, 2..8)
     int epi_db;                // staging modes: 1 = two store-staging buffers per epilogue set, 0 = one (frees 32 KB for pipeline stages)
     int dense_c;               // N <= 64 and one N block: stage the tile densely and write it with ONE bulk copy
     const float* se;           // A_SCALE: [images][K] gates
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[3 * 8 + 5];     // full[8], empty[8], raw[8], tmem_full[2], tmem_empty[2], bfull
+    __shared__ __align__(8) uint64_t bars[5 * 8 + 1];     // full[8], empty[8], raw[8], tmem_full[8], tmem_empty[8], bfull
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float sbias[MAX_BIAS];
 
@@ -84,11 +85,15 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t b_region = smem_base + (uint32_t)p.stages * stage_bytes;    // resident W: num_kb x (n_pad x 128 B)
     const uint32_t staging = b_region + (p.b_resident ? (uint32_t)num_kb * b_stage_bytes : 0u);     // 4 x 16 KB
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), raw0 = smem_u32(&bars[16]);
-    const uint32_t tfull0 = smem_u32(&bars[24]), tempty0 = smem_u32(&bars[26]), bfull = smem_u32(&bars[28]);
+    const uint32_t tfull0 = smem_u32(&bars[24]), tempty0 = smem_u32(&bars[32]), bfull = smem_u32(&bars[40]);
     // two accumulators of n_pad columns; the epilogue reads 32 columns at a time, so the last read of the second
     // accumulator may extend to the next multiple of 32 -- it must stay inside the allocation
+    // p.n_acc accumulators of n_pad columns (a ring: the MMA issuer runs up to n_acc tiles ahead of the epilogue, which
+    // hides the commit -> wait -> tcgen05.ld -> arrive round trip of the accumulator hand-over; with only two accumulators
+    // that round trip, ~1 us, capped narrow layers at two tiles per trip).  The epilogue reads 32 columns at a time, so
+    // the last read of the last accumulator may extend to the next multiple of 32 -- it must stay inside the allocation.
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)p.n_pad + (((uint32_t)p.n_pad + 31u) & ~31u)) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(p.n_acc - 1) * (uint32_t)p.n_pad + (((uint32_t)p.n_pad + 31u) & ~31u)) tmem_cols <<= 1;
 
     for (int i = threadIdx.x; i < p.n_pad * p.n_blocks && i < MAX_BIAS; i += GEMM_THREADS) sbias[i] = p.bias[i];
     if (warp == 0 && lane == 0) {
@@ -104,7 +109,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); mbar_init(raw0 + 8 * s, 1);
         }
         // A_TMA: the 8 staging warps double as a second pair of epilogue groups (column halves) -> 8 arrivals
-        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, plain ? 8 : 4); }
+        for (int a = 0; a < p.n_acc; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, plain ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -177,7 +182,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (kb == num_kb - 1) tc_commit(tfull0 + 8 * acc);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 12 && !plain) {
@@ -185,6 +190,63 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         {
             const int g = (warp - 12) >> 2;
             const int t = threadIdx.x - (12 + 4 * g) * 32;         // 0..127
+            if (p.a_mode == A_STEM) {
+                // stem im2col (one k-block per tile): row = output pixel; 3 kernel rows x 9 contiguous bf16 (3 px x 3 ch) -> 27 taps
+                // + 5 zeros.  Software-pipelined: the 15 loads of the group's NEXT tile are in flight while it waits for the
+                // smem slot of the current one and writes it, so the gather latency is paid once, not per tile.
+                auto gather = [&](int tile, uint32_t (&a)[3][5]) {
+                    const int m = tile * BLOCK_M + t;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                        for (int i = 0; i < 5; i++) a[ky][i] = 0;
+                    if (m < p.M) {
+                        const int ox = m % 112, oy = (m / 112) % 112, b = m / (112 * 112);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ky++) {
+                            const int iy = 2 * oy + ky;
+                            if (iy < 224) {
+                                const uint32_t* src = (const uint32_t*)(p.A + (((size_t)b * 224 + iy) * 224 + 2 * ox) * 3);
+                                a[ky][0] = __ldg(src); a[ky][1] = __ldg(src + 1); a[ky][2] = __ldg(src + 2);
+                                if (ox < 111) { a[ky][3] = __ldg(src + 3); a[ky][4] = __ldg(src + 4) & 0xffffu; }   // third pixel is padding at the right edge
+                            }
+                        }
+                    }
+                };
+                uint32_t cur[3][5], nxt[3][5];
+                int it = g;
+                int tile = blockIdx.x + it * (int)gridDim.x;
+                if (tile < p.num_tiles) gather(tile, cur);
+                for (; tile < p.num_tiles; it += 2) {
+                    const int ntile = blockIdx.x + (it + 2) * (int)gridDim.x;
+                    if (ntile < p.num_tiles) gather(ntile, nxt);
+                    const int stage = it % p.stages;
+                    const uint32_t phase = (uint32_t)(it / p.stages) & 1u;
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    uint32_t w[16];
+                    w[0] = cur[0][0]; w[1] = cur[0][1]; w[2] = cur[0][2]; w[3] = cur[0][3];
+                    w[4] = cur[0][4] | (cur[1][0] << 16);
+                    w[5] = (cur[1][0] >> 16) | (cur[1][1] << 16);
+                    w[6] = (cur[1][1] >> 16) | (cur[1][2] << 16);
+                    w[7] = (cur[1][2] >> 16) | (cur[1][3] << 16);
+                    w[8] = (cur[1][3] >> 16) | (cur[1][4] << 16);
+                    w[9] = cur[2][0]; w[10] = cur[2][1]; w[11] = cur[2][2]; w[12] = cur[2][3]; w[13] = cur[2][4];
+                    w[14] = 0; w[15] = 0;
+                    const int row = t;
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        sts128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full0 + 8 * stage);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                        for (int i = 0; i < 5; i++) cur[ky][i] = nxt[ky][i];
+                    tile = ntile;
+                }
+            } else {
             int j = 0;                                             // running k-block index of this CTA (p.stages is even: stage parity == group)
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / p.n_blocks) * BLOCK_M;
@@ -227,43 +289,12 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 }
                             }
                         }
-                    } else {
-                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                        // stem im2col: row = output pixel; 3 kernel rows x 9 contiguous bf16 (3 px x 3 ch) -> 27 taps + 5 zeros
-                        const int row = t, m = m0 + row;
-                        uint32_t w[16];
-#pragma unroll
-                        for (int i = 0; i < 16; i++) w[i] = 0;
-                        if (m < p.M) {
-                            const int ox = m % 112, oy = (m / 112) % 112, b = m / (112 * 112);
-                            uint32_t a[3][5];
-#pragma unroll
-                            for (int ky = 0; ky < 3; ky++) {
-                                const int iy = 2 * oy + ky;
-#pragma unroll
-                                for (int i = 0; i < 5; i++) a[ky][i] = 0;
-                                if (iy < 224) {
-                                    const uint32_t* src = (const uint32_t*)(p.A + (((size_t)b * 224 + iy) * 224 + 2 * ox) * 3);
-                                    a[ky][0] = __ldg(src); a[ky][1] = __ldg(src + 1); a[ky][2] = __ldg(src + 2);
-                                    if (ox < 111) { a[ky][3] = __ldg(src + 3); a[ky][4] = __ldg(src + 4) & 0xffffu; }   // third pixel is padding at the right edge
-                                }
-                            }
-                            w[0] = a[0][0]; w[1] = a[0][1]; w[2] = a[0][2]; w[3] = a[0][3];
-                            w[4] = a[0][4] | (a[1][0] << 16);
-                            w[5] = (a[1][0] >> 16) | (a[1][1] << 16);
-                            w[6] = (a[1][1] >> 16) | (a[1][2] << 16);
-                            w[7] = (a[1][2] >> 16) | (a[1][3] << 16);
-                            w[8] = (a[1][3] >> 16) | (a[1][4] << 16);
-                            w[9] = a[2][0]; w[10] = a[2][1]; w[11] = a[2][2]; w[12] = a[2][3]; w[13] = a[2][4];
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            sts128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
                     }
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full0 + 8 * stage);
                 }
+            }
             }
         }
     } else if (warp >= 4) {
@@ -279,7 +310,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // staging: 4 x 16 KB; unsplit groups own two buffers (double-buffered), split groups own one
         const uint32_t my_staging = staging + (uint32_t)(split ? grp : (p.epi_db ? 2 * set : set)) * STAGING_BLOCK_BYTES;
         const int nblk64 = (p.n_pad + 63) >> 6;
-        uint32_t blk_count = 0, acc_phase = 0;
+        uint32_t blk_count = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
             if ((it & 1) != set) continue;
@@ -293,10 +324,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 m = img * p.hw + m_blk * BLOCK_M + row;
             }
             const int n_base = n_blk * p.n_pad;
-            mbar_wait(tfull0 + 8 * set, acc_phase);
-            acc_phase ^= 1;
+            const int acc = it % p.n_acc;                          // n_acc is even: an accumulator always belongs to the same set
+            mbar_wait(tfull0 + 8 * acc, (uint32_t)(it / p.n_acc) & 1u);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.n_pad);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
             const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
             for (int jb = split ? half : 0; jb < ((p.debug & 16) ? 0 : nblk64); jb += split ? 2 : 1, blk_count++) {
                 const uint32_t buf = my_staging + ((split || !p.epi_db) ? 0u : (blk_count & 1u) * STAGING_BLOCK_BYTES);
@@ -313,7 +344,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (jb + (split ? 2 : 1) >= nblk64 && c32 + 32 >= cols_here) {     // last TMEM read of this group for this tile:
                         tc_fence_before();                                              // hand the accumulator back before the math
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty0 + 8 * set);
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
                     }
 #pragma unroll
                     for (int h = 0; h < 4; h++) {
@@ -366,7 +397,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if ((split && half >= nblk64) || (p.debug & 16)) {     // no column block for this group: still release the accumulator
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * set);
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
             }
         }
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -424,6 +455,13 @@ int dfd_tmap_bf16(dfd_ctx* ctx, CUtensorMap* m, const void* base, int rank, cons
     return DFD_OK;
 }
 
+// accumulator ring depth: as many n_pad-column accumulators as fit 512 TMEM columns (the last one rounded up to 32), even, <= 8
+static int gemm_n_acc(int n_pad) {
+    if (getenv("DFD_GEMM_ACC2")) return 2;
+    int n = 8;
+    while (n > 2 && (n - 1) * n_pad + ((n_pad + 31) & ~31) > 512) n -= 2;
+    return n;
+}
 static bool g_no_dense = getenv("DFD_NO_DENSE_C") != nullptr;     // A/B switch for the dense bulk-store epilogue
 static bool g_enabled = true;
 static int g_debug = 0;
@@ -448,6 +486,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     int nb = (N + 255) / 256;
     int n_pad = nb == 1 ? (N + 15) / 16 * 16 : ((N + nb - 1) / nb + 63) / 64 * 64;
     p.n_pad = n_pad; p.n_blocks = (N + n_pad - 1) / n_pad;
+    p.n_acc = gemm_n_acc(n_pad);
     const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     p.num_tiles = m_blocks * p.n_blocks;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
@@ -506,6 +545,7 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
     p.a_mode = A_IMG; p.A = A; p.se = nullptr; p.hw = hw; p.debug = 0;
     p.C = C; p.dense_c = (N <= 64 && !g_no_dense) ? 1 : 0; p.epi_db = 1;
     p.n_pad = (N + 15) / 16 * 16; p.n_blocks = 1;
+    p.n_acc = gemm_n_acc(p.n_pad);
     p.tiles_per_img = (hw + BLOCK_M - 1) / BLOCK_M;
     p.num_tiles = n_img * p.tiles_per_img;
     p.b_resident = 0;
