@@ -192,6 +192,7 @@ void dfd_destroy(dfd_ctx* ctx) {
                     ctx->d_wbf16, ctx->d_stem_wg, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
                     ctx->d_sescale, ctx->d_se_r, ctx->d_front_aux, ctx->d_wgated, ctx->d_wxt, ctx->d_feat, ctx->d_fc_h1, ctx->d_fc_h2, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& e : ctx->rs_cache) if (e.p) cudaFree(e.p);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

@@ -61,6 +61,8 @@ struct dfd_ctx {
     int64_t launches = 0;
     // tables + state
     DfdColorTables* d_tables = nullptr;
+    struct RsEntry { int h, w; void* p; };
+    std::vector<RsEntry> rs_cache;        // cv2.resize tap tables per frame size (forensics.cu)
     float2* d_twiddle = nullptr;          // 128 twiddles of the 256-point FFT
     DfdStreamState* d_state = nullptr;
     uint8_t* d_prev_gray = nullptr;       // [max_streams][256*256]

@@ -14,6 +14,7 @@
 // The integer stages are bit-exact with cv2 (same px_*.h functions that tests/hostcheck checks on
 // the CPU); float statistics agree to ~1e-6 relative (double accumulation vs NumPy float32 pairwise).
 #include "dfd_internal.cuh"
+#include <stdlib.h>
 #include "px_resize.h"
 #include "px_jpeg.h"
 #include "px_canny.h"
@@ -22,27 +23,77 @@
 #define T 256
 
 // ---------------------------------------------------------------------------------------------
-// CTA = one output row of one frame; a thread reads the 2x2 taps of its pixel straight from the frame (12 byte loads
-// that the L1 merges per sector; staging the two source rows in shared memory with 16-byte loads measured slower).
+// CTA = one output row of one frame.  The fixed-point tap positions / weights depend only on (H, W): they are tabulated on
+// the host once per frame size (dfd_resize_tables), so the kernel has no double-precision math.  When the two horizontal
+// taps are adjacent pixels (always, when down-scaling) their 6 bytes are fetched as three aligned 32-bit words per row
+// instead of six byte loads.  (Staging the source rows in shared memory -- 16-byte loads or cp.async.bulk, 1 or 4 output
+// rows per CTA -- was measured and is not faster: the kernel streams 2 of every 2.8 frame rows at 2.6-2.8 TB/s either way.)
+struct RsTap { int s0, s1, a0, a1; };
+
+__device__ __forceinline__ void rs_fetch6(const uint8_t* row, int byte_off, int* p0, int* p1) {
+    const uint32_t* w = (const uint32_t*)(row + (byte_off & ~3));
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const int sh = (byte_off & 3) * 8;
+    const uint32_t lo = __funnelshift_r(w0, w1, sh);       // bytes 0..3 of the window
+    const uint32_t hi = __funnelshift_r(w1, w2, sh);       // bytes 4..7
+    p0[0] = lo & 255; p0[1] = (lo >> 8) & 255; p0[2] = (lo >> 16) & 255;
+    p1[0] = lo >> 24; p1[1] = hi & 255; p1[2] = (hi >> 8) & 255;
+}
+
 __global__ void __launch_bounds__(256) k_resize256(const uint8_t* __restrict__ frames, int H, int W, size_t fstride,
-                                                   int pitch, uint8_t* __restrict__ tile, uint8_t* __restrict__ gray) {
+                                                   int pitch, const RsTap* __restrict__ tab, int wide_ok,
+                                                   uint8_t* __restrict__ tile, uint8_t* __restrict__ gray) {
     const int n = blockIdx.y, y = blockIdx.x, x = threadIdx.x;
-    int sy0, sy1, b0, b1, sx0, sx1, a0, a1;
-    dfd_cvresize_coef(y, H, T, 0, &sy0, &sy1, &b0, &b1);
-    dfd_cvresize_coef(x, W, T, 1, &sx0, &sx1, &a0, &a1);
+    const RsTap ty = tab[y], tx = tab[T + x];
     const uint8_t* f = frames + (size_t)n * fstride;
-    const uint8_t* r0 = f + (size_t)sy0 * pitch;
-    const uint8_t* r1 = f + (size_t)sy1 * pitch;
+    const uint8_t* r0 = f + (size_t)ty.s0 * pitch;
+    const uint8_t* r1 = f + (size_t)ty.s1 * pitch;
+    int p00[3], p01[3], p10[3], p11[3];
+    // the 12-byte window of rs_fetch6 must stay inside the row (last pixels: byte loads)
+    if (wide_ok && tx.s1 == tx.s0 + 1 && ((tx.s0 * 3) & ~3) + 12 <= W * 3) {
+        rs_fetch6(r0, tx.s0 * 3, p00, p01);
+        rs_fetch6(r1, tx.s0 * 3, p10, p11);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            p00[c] = __ldg(r0 + tx.s0 * 3 + c); p01[c] = __ldg(r0 + tx.s1 * 3 + c);
+            p10[c] = __ldg(r1 + tx.s0 * 3 + c); p11[c] = __ldg(r1 + tx.s1 * 3 + c);
+        }
+    }
     int px[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++)
-        px[c] = dfd_cvresize_px(__ldg(r0 + sx0 * 3 + c), __ldg(r0 + sx1 * 3 + c), __ldg(r1 + sx0 * 3 + c),
-                                __ldg(r1 + sx1 * 3 + c), a0, a1, b0, b1);
+    for (int c = 0; c < 3; c++) px[c] = dfd_cvresize_px(p00[c], p01[c], p10[c], p11[c], tx.a0, tx.a1, ty.a0, ty.a1);
     size_t o = ((size_t)n * T + y) * T + x;
     tile[o * 3 + 0] = (uint8_t)px[0];
     tile[o * 3 + 1] = (uint8_t)px[1];
     tile[o * 3 + 2] = (uint8_t)px[2];
     gray[o] = (uint8_t)dfd_bgr2gray(px[0], px[1], px[2]);
+}
+
+// host: tap table for an H x W frame, [0..255] vertical, [256..511] horizontal.  Tables are cached per frame size and never
+// rewritten while cached (a kernel of an earlier call may still be reading one); the first call with a new size uploads
+// synchronously, so CUDA-graph capture needs one warm-up call per frame size (Engine.capture_step does that).
+static int dfd_resize_tables(dfd_ctx* ctx, int H, int W, const RsTap** out) {
+    for (auto& e : ctx->rs_cache)
+        if (e.h == H && e.w == W) { *out = (const RsTap*)e.p; return DFD_OK; }
+    RsTap h[2 * T];
+    for (int i = 0; i < T; i++) {
+        dfd_cvresize_coef(i, H, T, 0, &h[i].s0, &h[i].s1, &h[i].a0, &h[i].a1);
+        dfd_cvresize_coef(i, W, T, 1, &h[T + i].s0, &h[T + i].s1, &h[T + i].a0, &h[T + i].a1);
+    }
+    dfd_ctx::RsEntry e;
+    e.h = H; e.w = W; e.p = nullptr;
+    if (ctx->rs_cache.size() >= 32) {                       // recycle the oldest table once nothing can be using it
+        DFD_CUDA(cudaDeviceSynchronize());
+        e.p = ctx->rs_cache.front().p;
+        ctx->rs_cache.erase(ctx->rs_cache.begin());
+    } else {
+        DFD_CUDA(cudaMalloc(&e.p, sizeof h));
+    }
+    DFD_CUDA(cudaMemcpy(e.p, h, sizeof h, cudaMemcpyHostToDevice));
+    ctx->rs_cache.push_back(e);
+    *out = (const RsTap*)e.p;
+    return DFD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -563,7 +614,11 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
                          const int32_t* stream_ids, const uint8_t* full, dfd_forensic_result* results, cudaStream_t st) {
     DFD_REQUIRE(n > 0 && n <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "forensics: batch exceeds max_batch");
     DFD_REQUIRE(H >= 1 && W >= 1 && row_pitch >= 3 * W, DFD_ERR_INVALID, "forensics: bad frame geometry");
-    k_resize256<<<dim3(T, n), 256, 0, st>>>(frames, H, W, frame_stride, row_pitch, ctx->d_tile, ctx->d_gray);
+    const RsTap* rs_tab = nullptr;
+    { int rc = dfd_resize_tables(ctx, H, W, &rs_tab); if (rc) return rc; }
+    // aligned 32-bit tap loads need 4-byte aligned rows
+    const int wide_ok = ((uintptr_t)frames % 4 == 0) && (frame_stride % 4 == 0) && (row_pitch % 4 == 0);
+    k_resize256<<<dim3(T, n), 256, 0, st>>>(frames, H, W, frame_stride, row_pitch, rs_tab, wide_ok, ctx->d_tile, ctx->d_gray);
     DFD_LAUNCH_CHECK("k_resize256", st);
     k_tile_stats<<<dim3(DFD_NBLK, n), 256, 0, st>>>(ctx->d_tile, ctx->d_gray, stream_ids, full, ctx->d_tables, ctx->d_state,
                                                      ctx->d_prev_gray, ctx->d_part);
