@@ -391,6 +391,53 @@ def main():
         except Exception as e:                                   # never let the extra measurement break the contract line
             latency = {"error": str(e)[:200]}
 
+    # ---- the other BASELINE.json configurations that fit one GPU, as side measurements (rank 0, N=1) ----
+    side = None
+    if rank == 0 and world == 1:
+        try:
+            side = {}
+
+            def graph_time(fn, reps):
+                st = torch.cuda.Stream(dev)
+                with torch.cuda.stream(st):
+                    fn(); fn()
+                st.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for _ in range(3):
+                    g.replay()
+                a.record()
+                for _ in range(reps):
+                    flush.zero_()                      # cold L2 between replays (the 256 MB memset is inside the timing: subtracted below)
+                    g.replay()
+                b.record()
+                torch.cuda.synchronize()
+                t_all = a.elapsed_time(b)
+                a.record()
+                for _ in range(reps):
+                    flush.zero_()
+                b.record()
+                torch.cuda.synchronize()
+                return (t_all - a.elapsed_time(b)) / reps
+
+            # config 2: EfficientNet-B0 classifier only, 224x224 bf16, batch 256
+            crops = eng.face_prep_batch(dev_frames[0], dev_boxes[0], box_frame, dtype="bf16")
+            ms2 = graph_time(lambda: eng.effnet_forward(crops), 10)
+            side["config2_classifier_bf16_b256"] = {"crops_per_sec": S / ms2 * 1e3, "ms": ms2,
+                                                    "hbm_layer_granular_bound_crops_per_sec": hbm * 1e9 / 27.42e6}
+            # config 3: six forensic signals on 1080p frames, batch 64 (all frames "full")
+            f1080 = torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, device=dev)
+            sid64 = torch.arange(64, dtype=torch.int32, device=dev)
+            full64 = torch.ones(64, dtype=torch.uint8, device=dev)
+            ms3 = graph_time(lambda: eng.forensics_batch(f1080, sid64, full64), 10)
+            side["config3_forensics_1080p_b64"] = {"frames_per_sec": 64 / ms3 * 1e3, "ms": ms3}
+            del f1080
+        except Exception as e:
+            side = {"error": str(e)[:200]}
+
     # ---- CPU baseline (rank 0, N=1): the oracle port on a bounded sample of the same workload ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -419,7 +466,7 @@ def main():
                     "note": "pinned host frames, H2D double-buffered on a copy stream; bound by the PCIe Gen5 x16 link "
                             "(2.76 MB of raw frame per frame), not by the kernels"},
             "gpu_launches": int(launches), "crops_per_sec": value, "clocks": clocks, "roofline": roof,
-            "cpu_baseline": cpu, "latency": latency, "top_kernels": functions[:6],
+            "cpu_baseline": cpu, "latency": latency, "other_configs": side, "top_kernels": functions[:6],
         }
         print(json.dumps(out))
     if world > 1:
