@@ -392,74 +392,125 @@ __global__ void __launch_bounds__(512) k_ela(const uint8_t* __restrict__ tile, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// 256-point radix-2 DIT FFT on shared memory; 128 threads cooperate on one transform.
-__device__ __forceinline__ int bitrev8(int v) { return (int)(__brev((unsigned)v) >> 24); }
+// 256-point FFT as 16 x 16 (Cooley-Tukey, decimation in time) by 16 threads: a thread owns 16 points in registers, runs a
+// 16-point DFT (4 x 4, constant twiddles), applies the W256 twiddles, the 16 threads transpose through shared memory
+// (one __syncwarp -- they are half a warp) and run the second 16-point DFT.  Output index k = k1 + 16 * k2.
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmuli_neg(float2 a) { return make_float2(a.y, -a.x); }          // a * (-i)
 
-__device__ __forceinline__ void fft256(float2* s, const float2* __restrict__ tw, int t, int barrier_id, int nthreads) {
-#pragma unroll
-    for (int st = 1; st <= 8; st++) {
-        int half = 1 << (st - 1);
-        int grp = t >> (st - 1), idx = t & (half - 1);
-        int i0 = (grp << st) + idx, i1 = i0 + half;
-        float2 w = tw[idx << (8 - st)];
-        float2 a = s[i0], b = s[i1];
-        float2 wb = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
-        s[i0] = make_float2(a.x + wb.x, a.y + wb.y);
-        s[i1] = make_float2(a.x - wb.x, a.y - wb.y);
-        __syncthreads();
-    }
+// 4-point forward DFT of (a0..a3) -> (y0..y3)
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = cmuli_neg(csub(a1, a3));
+    a0 = cadd(s02, s13); a2 = csub(s02, s13); a1 = cadd(d02, d13); a3 = csub(d02, d13);
 }
 
-// rows: CTA = 8 row-pairs (16 rows); grid (16, n).  Output half-spectrum, transposed: fft[n][k][row].
-__global__ void __launch_bounds__(1024) k_fft_rows(const uint8_t* __restrict__ gray, const float2* __restrict__ tw,
-                                                   float2* __restrict__ out) {
-    __shared__ float2 s[8][256];
+// 16-point forward DFT in place: v[n] (n = 4*n1 + n2) -> v[k] (k = k1 + 4*k2), natural order in and out
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R = 0.70710678118654752f;
+    // step A: for each n2, 4-point DFT over n1 of v[4*n1 + n2]  -> a[n2][k1] stored at v[4*k1 + n2]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    // step B: twiddle a[n2][k1] *= W16^(n2*k1)
+    v[4 + 1] = cmulf(v[4 + 1], make_float2(C1, -S1));      // k1=1,n2=1 : W^1
+    v[4 + 2] = cmulf(v[4 + 2], make_float2(R, -R));        // W^2
+    v[4 + 3] = cmulf(v[4 + 3], make_float2(S1, -C1));      // W^3
+    v[8 + 1] = cmulf(v[8 + 1], make_float2(R, -R));        // k1=2,n2=1 : W^2
+    v[8 + 2] = cmuli_neg(v[8 + 2]);                        // W^4 = -i
+    v[8 + 3] = cmulf(v[8 + 3], make_float2(-R, -R));       // W^6
+    v[12 + 1] = cmulf(v[12 + 1], make_float2(S1, -C1));    // k1=3,n2=1 : W^3
+    v[12 + 2] = cmulf(v[12 + 2], make_float2(-R, -R));     // W^6
+    v[12 + 3] = cmulf(v[12 + 3], make_float2(-C1, S1));    // W^9
+    // step C: for each k1, 4-point DFT over n2 of v[4*k1 + n2] -> X[k1 + 4*k2] stored at v[4*k1 + k2]
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+    // reorder: X[k1 + 4*k2] sits at v[4*k1 + k2]  ->  natural order
+    float2 t[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++)
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) t[k1 + 4 * k2] = v[4 * k1 + k2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = t[i];
+}
+
+// x[16*n1 + t] in v[n1] on entry (t = lane within the 16-thread group); on exit v[k2] = X[t + 16*k2].
+// S: this group's shared scratch, 16 x 17 float2.
+__device__ __forceinline__ void fft256_16x16(float2 (&v)[16], float2* S, const float2* __restrict__ tw, int t, unsigned gmask) {
+    dft16(v);                                              // v[k1] = sum_n1 x[16 n1 + t] W16^(n1 k1)
+#pragma unroll
+    for (int k1 = 1; k1 < 16; k1++) {                      // * W256^(t * k1)
+        const int j = t * k1;                              // < 226
+        float2 w = tw[j & 127];
+        if (j & 128) { w.x = -w.x; w.y = -w.y; }
+        v[k1] = cmulf(v[k1], w);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) S[k1 * 17 + t] = v[k1];
+    __syncwarp(gmask);
+#pragma unroll
+    for (int n2 = 0; n2 < 16; n2++) v[n2] = S[t * 17 + n2];     // now t plays k1: v[n2] = A[n2][k1 = t]
+    __syncwarp(gmask);
+    dft16(v);                                              // v[k2] = X[t + 16 k2]
+}
+
+// rows: a 16-thread group transforms one row PAIR (real-pair trick); CTA = 8 groups = 16 rows; grid (16, n).
+// Output half-spectrum, transposed: fft[n][k][row].
+__global__ void __launch_bounds__(128) k_fft_rows(const uint8_t* __restrict__ gray, const float2* __restrict__ tw,
+                                                  float2* __restrict__ out) {
+    __shared__ float2 S[8][16 * 17];                       // transpose scratch, then the group's spectrum Z[256]
+    __shared__ float2 os[129][16];
     const int n = blockIdx.y, grp = blockIdx.x;
-    const int f = threadIdx.x >> 7, t = threadIdx.x & 127;
+    const int f = threadIdx.x >> 4, t = threadIdx.x & 15;
+    const unsigned gmask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
     const int row0 = grp * 16 + 2 * f;
     const uint8_t* g = gray + (size_t)n * T * T;
-    for (int j = t; j < 256; j += 128)
-        s[f][bitrev8(j)] = make_float2((float)g[row0 * T + j], (float)g[(row0 + 1) * T + j]);
-    __syncthreads();
-    fft256(s[f], tw, t, 0, 0);
-    // the 16 rows of this CTA are 128 contiguous bytes of every output column k: gather them in shared memory and write
-    // full 128-byte segments (a thread writing its own (k, row) pair scatters 8-byte stores 2 KB apart)
-    __shared__ float2 os[129][16];
-    for (int k = t; k <= 128; k += 128) {
-        float2 zk = s[f][k], zn = s[f][(256 - k) & 255];
+    float2 v[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) v[n1] = make_float2((float)g[row0 * T + 16 * n1 + t], (float)g[(row0 + 1) * T + 16 * n1 + t]);
+    fft256_16x16(v, S[f], tw, t, gmask);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) S[f][t + 16 * k2] = v[k2];     // (fft256_16x16 ended with a group barrier after its last read of S)
+    __syncwarp(gmask);
+    for (int k = t; k <= 128; k += 16) {
+        const float2 zk = S[f][k], zn = S[f][(256 - k) & 255];
         // F1 = (Zk + conj(Zn))/2 ; F2 = (Zk - conj(Zn))/(2i)
         os[k][2 * f] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         os[k][2 * f + 1] = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
     }
     __syncthreads();
+    // the 16 rows of this CTA are 128 contiguous bytes of every output column k: write full 128-byte segments
     float2* o = out + (size_t)n * 129 * 256 + grp * 16;
-    for (int i = threadIdx.x; i < 129 * 16; i += 1024) o[(size_t)(i >> 4) * 256 + (i & 15)] = os[i >> 4][i & 15];
+    for (int i = threadIdx.x; i < 129 * 16; i += 128) o[(size_t)(i >> 4) * 256 + (i & 15)] = os[i >> 4][i & 15];
 }
 
-// columns: CTA = 8 half-spectrum columns; grid (17, n).
-__global__ void __launch_bounds__(1024) k_fft_cols(const float2* __restrict__ in, const float2* __restrict__ tw,
-                                                   DfdFramePartials* __restrict__ part) {
-    __shared__ float2 s[8][256];
-    __shared__ double red[32][7];
+// columns: a 16-thread group transforms one half-spectrum column; CTA = 8 columns; grid (17, n).
+__global__ void __launch_bounds__(128) k_fft_cols(const float2* __restrict__ in, const float2* __restrict__ tw,
+                                                  DfdFramePartials* __restrict__ part) {
+    __shared__ float2 S[8][16 * 17];
+    __shared__ double red[4][7];
     const int n = blockIdx.y, grp = blockIdx.x;
-    const int f = threadIdx.x >> 7, t = threadIdx.x & 127;
+    const int f = threadIdx.x >> 4, t = threadIdx.x & 15;
+    const unsigned gmask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
     const int k = grp * 8 + f;
     const bool active = k <= 128;
-    if (active) {
-        const float2* c = in + ((size_t)n * 129 + k) * 256;
-        for (int j = t; j < 256; j += 128) s[f][bitrev8(j)] = c[j];
-    }
-    __syncthreads();
-    fft256(s[f], tw, t, 0, 0);      // inactive columns transform garbage; results unused
+    float2 v[16];
+    const float2* c = in + ((size_t)n * 129 + (active ? k : 0)) * 256;
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) v[n1] = c[16 * n1 + t];
+    fft256_16x16(v, S[f], tw, t, gmask);                  // inactive columns transform column 0 again; results unused
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     if (active) {
         const int fv = k < 128 ? k : -128;
         const double wgt = (k == 0 || k == 128) ? 1.0 : 2.0;
-        for (int u = t; u < 256; u += 128) {
-            int fu = u < 128 ? u : u - 256;
-            int d2 = fu * fu + fv * fv;
-            float2 z = s[f][u];
-            double m = (double)log1pf(hypotf(z.x, z.y));
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) {
+            const int u = t + 16 * k2;
+            const int fu = u < 128 ? u : u - 256;
+            const int d2 = fu * fu + fv * fv;
+            const float2 z = v[k2];
+            const double m = (double)log1pf(hypotf(z.x, z.y));
             if (d2 <= 32 * 32) { acc[0] += wgt * m; acc[4] += wgt; }
             else if (d2 <= 64 * 64) { acc[1] += wgt * m; acc[2] += wgt * m * m; acc[5] += wgt; }
             else if (d2 <= 128 * 128) { acc[3] += wgt * m; acc[6] += wgt; }
@@ -472,7 +523,7 @@ __global__ void __launch_bounds__(1024) k_fft_cols(const float2* __restrict__ in
     __syncthreads();
     if (threadIdx.x < 7) {
         double r = 0;
-        for (int w = 0; w < 32; w++) r += red[w][threadIdx.x];
+        for (int w = 0; w < 4; w++) r += red[w][threadIdx.x];
         part[n].fft[grp][threadIdx.x] = r;
     }
 }
@@ -627,9 +678,9 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
     DFD_LAUNCH_CHECK("k_canny", st);
     k_ela<<<n, 512, T * T + 2 * 128 * 128, st>>>(ctx->d_tile, full, ctx->d_part, nullptr);
     DFD_LAUNCH_CHECK("k_ela", st);
-    k_fft_rows<<<dim3(16, n), 1024, 0, st>>>(ctx->d_gray, ctx->d_twiddle, ctx->d_fft);
+    k_fft_rows<<<dim3(16, n), 128, 0, st>>>(ctx->d_gray, ctx->d_twiddle, ctx->d_fft);
     DFD_LAUNCH_CHECK("k_fft_rows", st);
-    k_fft_cols<<<dim3(DFD_FFT_GROUPS, n), 1024, 0, st>>>(ctx->d_fft, ctx->d_twiddle, ctx->d_part);
+    k_fft_cols<<<dim3(DFD_FFT_GROUPS, n), 128, 0, st>>>(ctx->d_fft, ctx->d_twiddle, ctx->d_part);
     DFD_LAUNCH_CHECK("k_fft_cols", st);
     k_finalize<<<(n + 63) / 64, 64, 0, st>>>(n, stream_ids, full, ctx->d_part, ctx->d_state, results);
     DFD_LAUNCH_CHECK("k_finalize", st);
