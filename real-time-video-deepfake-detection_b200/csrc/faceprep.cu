@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ f
 // in shared memory, then Pillow's horizontal resampling pass of that row to 160 pixels.  The colour tables and the
 // box's 64 CLAHE LUTs are staged in shared memory once per CTA (11 table gathers + 4 LUT gathers per pixel).
 #define HP_ROWS 16
+#define DFD_PIL_KMAX_STAGED 15      // Pillow tap counts up to 15 (crops up to 1120 px) are staged in shared memory
 __global__ void __launch_bounds__(256) k_clahe_hpass(const uint8_t* __restrict__ frames, size_t fstride, int pitch,
                                                      const int32_t* __restrict__ boxes, const int32_t* __restrict__ frame_idx,
                                                      const DfdColorTables* __restrict__ tab, const uint8_t* __restrict__ luts,
@@ -87,28 +88,60 @@ __global__ void __launch_bounds__(256) k_clahe_hpass(const uint8_t* __restrict__
     extern __shared__ __align__(16) uint8_t hp_smem[];
     DfdColorTables* s_tab = (DfdColorTables*)hp_smem;                               // sizeof is a multiple of 16
     uint8_t* s_lut = hp_smem + sizeof(DfdColorTables);                              // [64][256]
-    uint8_t* s_rows = s_lut + 64 * 256;                                             // [8 warps][max_crop * 3]
+    int* s_pc = (int*)(s_lut + 64 * 256);                                           // [160][2 + ksize] Pillow horizontal taps of this box
+    uint8_t* s_rows = (uint8_t*)(s_pc + 160 * (2 + DFD_PIL_KMAX_STAGED));           // [8 warps][row_stride]
     const int m = blockIdx.y, y0 = blockIdx.x * rows_per_cta;
     const int bx = boxes[m * 4], by = boxes[m * 4 + 1], bw = boxes[m * 4 + 2], bh = boxes[m * 4 + 3];
     if (y0 >= bh) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < (int)(sizeof(DfdColorTables) / 16); i += 256) ((uint4*)s_tab)[i] = ((const uint4*)tab)[i];
     for (int i = threadIdx.x; i < 64 * 256 / 16; i += 256) ((uint4*)s_lut)[i] = ((const uint4*)(luts + (size_t)m * 64 * 256))[i];
+    // Pillow's horizontal coefficients (the same for every row of the box) are read ~7 times per output value: keep them in
+    // shared memory, compacted to the box's real tap count
+    const int* pg = pil + ((size_t)m * 2 + 0) * 160 * PIL_STRIDE;
+    const int ks_real = dfd_pil_ksize(bw, 160);
+    const bool staged = ks_real <= DFD_PIL_KMAX_STAGED;    // very large crops (> 1120 px wide) read the table from global memory
+    const int pcs = 2 + (staged ? ks_real : 0);
+    if (staged) {
+        for (int i = threadIdx.x; i < 160 * pcs; i += 256) {
+            const int xx = i / pcs, j = i - xx * pcs;
+            s_pc[i] = pg[xx * PIL_STRIDE + j];
+        }
+    }
     __syncthreads();
     const DfdClaheGeom g = dfd_clahe_geom(bw, bh);
-    uint8_t* row = s_rows + (size_t)warp * max_crop * 3;
-    const int* pc = pil + ((size_t)m * 2 + 0) * 160 * PIL_STRIDE;
+    const bool words_ok = ((uintptr_t)frames % 4 == 0) && (fstride % 4 == 0) && (pitch % 4 == 0);
+    const int row_stride = (max_crop * 3 + 8 + 15) & ~15;
+    uint8_t* row = s_rows + (size_t)warp * row_stride;
     for (int y = y0 + warp; y < y0 + rows_per_cta && y < bh; y += 8) {
         const uint8_t* f = frames + (size_t)frame_idx[m] * fstride + (size_t)(by + y) * pitch + (size_t)bx * 3;
-        for (int x = lane; x < bw; x += 32) {
-            int L, A, B, ob, og, orr;
-            dfd_bgr2lab(s_tab, f[x * 3], f[x * 3 + 1], f[x * 3 + 2], &L, &A, &B);
-            L = dfd_clahe_apply(s_lut, g, x, y, L);
-            dfd_lab2bgr(s_tab, L, A, B, &ob, &og, &orr);
-            row[x * 3] = (uint8_t)orr; row[x * 3 + 1] = (uint8_t)og; row[x * 3 + 2] = (uint8_t)ob;   // RGB order (:376)
-            if (dbg_clahe && m == dbg_box) {
-                uint8_t* d = dbg_clahe + ((size_t)y * bw + x) * 3;
-                d[0] = (uint8_t)ob; d[1] = (uint8_t)og; d[2] = (uint8_t)orr;
+        // the crop row is fetched with aligned, coalesced 32-bit loads into the row buffer and converted in place (the three
+        // byte loads per pixel straight from the frame were the kernel's main stall: 55 % long-scoreboard)
+        int off = 0;
+        const uint8_t* src = f;
+        if (words_ok) {
+            off = (int)((uintptr_t)f & 3);
+            const uint32_t* fw = (const uint32_t*)(f - off);
+            const int nwords = (off + bw * 3 + 3) >> 2;
+            for (int i = lane; i < nwords; i += 32) ((uint32_t*)row)[i] = __ldg(fw + i);
+            __syncwarp();
+            src = row + off;
+        }
+        for (int x0 = 0; x0 < bw; x0 += 32) {
+            const int x = x0 + lane;
+            int L = 0, A = 0, B = 0, ob = 0, og = 0, orr = 0;
+            if (x < bw) {
+                dfd_bgr2lab(s_tab, src[x * 3], src[x * 3 + 1], src[x * 3 + 2], &L, &A, &B);
+                L = dfd_clahe_apply(s_lut, g, x, y, L);
+                dfd_lab2bgr(s_tab, L, A, B, &ob, &og, &orr);
+            }
+            __syncwarp();                                    // every lane has read its pixel before anyone overwrites the buffer
+            if (x < bw) {
+                row[x * 3] = (uint8_t)orr; row[x * 3 + 1] = (uint8_t)og; row[x * 3 + 2] = (uint8_t)ob;   // RGB order (:376)
+                if (dbg_clahe && m == dbg_box) {
+                    uint8_t* d = dbg_clahe + ((size_t)y * bw + x) * 3;
+                    d[0] = (uint8_t)ob; d[1] = (uint8_t)og; d[2] = (uint8_t)orr;
+                }
             }
         }
         __syncwarp();
@@ -116,7 +149,7 @@ __global__ void __launch_bounds__(256) k_clahe_hpass(const uint8_t* __restrict__
             uint8_t* out = hpass + (((size_t)m * max_crop + y) * 160) * 3;
             for (int o = lane; o < 480; o += 32) {
                 const int xx = o / 3, c = o - xx * 3;
-                const int* k = pc + xx * PIL_STRIDE;
+                const int* k = staged ? s_pc + xx * pcs : pg + xx * PIL_STRIDE;
                 const int xmin = k[0], cnt = k[1];
                 int acc = 1 << (DFD_PIL_PRECISION - 1);
                 for (int t = 0; t < cnt; t++) acc += row[(xmin + t) * 3 + c] * k[2 + t];
@@ -202,7 +235,7 @@ int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H
     const int lut_warps = m >= 16 ? 8 : 2;
     k_clahe_lut<<<dim3(64 / lut_warps, m), 32 * lut_warps, 0, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables, ctx->d_luts);
     DFD_LAUNCH_CHECK("k_clahe_lut", st);
-    const size_t hp_smem = sizeof(DfdColorTables) + 64 * 256 + (size_t)8 * mc * 3;
+    const size_t hp_smem = sizeof(DfdColorTables) + 64 * 256 + 160 * (2 + DFD_PIL_KMAX_STAGED) * sizeof(int) + (size_t)8 * ((mc * 3 + 8 + 15) & ~15);
     static size_t hp_attr = 0;
     if (hp_smem > hp_attr) {
         DFD_CUDA(cudaFuncSetAttribute(k_clahe_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem));
@@ -226,7 +259,7 @@ int dfd_dbg_clahe_launch(dfd_ctx* ctx, const uint8_t* frames, size_t frame_strid
                          const int32_t* frame_idx, int i, uint8_t* out, cudaStream_t st) {
     // luts of the last dfd_face_prep_batch call are reused; only box i is written
     const int mc = ctx->cfg.max_crop;
-    const size_t hp_smem = sizeof(DfdColorTables) + 64 * 256 + (size_t)8 * mc * 3;
+    const size_t hp_smem = sizeof(DfdColorTables) + 64 * 256 + 160 * (2 + DFD_PIL_KMAX_STAGED) * sizeof(int) + (size_t)8 * ((mc * 3 + 8 + 15) & ~15);
     DFD_CUDA(cudaFuncSetAttribute(k_clahe_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem));
     k_clahe_hpass<<<dim3((mc + HP_ROWS - 1) / HP_ROWS, i + 1), 256, hp_smem, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx,
                                                                                    ctx->d_tables, ctx->d_luts, ctx->d_pil, nullptr, mc, out, i, HP_ROWS);
