@@ -147,13 +147,20 @@ __global__ void __launch_bounds__(256) k_clahe_hpass(const uint8_t* __restrict__
         __syncwarp();
         if (hpass) {
             uint8_t* out = hpass + (((size_t)m * max_crop + y) * 160) * 3;
-            for (int o = lane; o < 480; o += 32) {
-                const int xx = o / 3, c = o - xx * 3;
+            // a lane resamples one output pixel (3 channels share the tap positions and weights)
+            for (int xx = lane; xx < 160; xx += 32) {
                 const int* k = staged ? s_pc + xx * pcs : pg + xx * PIL_STRIDE;
                 const int xmin = k[0], cnt = k[1];
-                int acc = 1 << (DFD_PIL_PRECISION - 1);
-                for (int t = 0; t < cnt; t++) acc += row[(xmin + t) * 3 + c] * k[2 + t];
-                out[o] = (uint8_t)dfd_pil_clip8(acc);
+                int a0 = 1 << (DFD_PIL_PRECISION - 1), a1 = a0, a2 = a0;
+                const uint8_t* rp = row + xmin * 3;
+                for (int t = 0; t < cnt; t++) {
+                    const int w = k[2 + t];
+                    a0 += rp[0] * w; a1 += rp[1] * w; a2 += rp[2] * w;
+                    rp += 3;
+                }
+                out[xx * 3] = (uint8_t)dfd_pil_clip8(a0);
+                out[xx * 3 + 1] = (uint8_t)dfd_pil_clip8(a1);
+                out[xx * 3 + 2] = (uint8_t)dfd_pil_clip8(a2);
             }
         }
         __syncwarp();
@@ -180,7 +187,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict__ boxes, const int* __restrict__ pil,
                                                        const uint8_t* __restrict__ hpass, int max_crop,
                                                        uint8_t* __restrict__ face160, OutT* __restrict__ out) {
-    __shared__ uint8_t s160[44][480];
+    __shared__ __align__(16) uint8_t s160[44][480];
     const int m = blockIdx.y, band = blockIdx.x;           // 4 bands of 56 output rows
     int r_first, r_last, t0, t1; float l0, l1;
     dfd_torch_bilinear_coef(band * 56, 160, 224, &r_first, &t1, &l0, &l1);
@@ -188,15 +195,22 @@ __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict
     const int nrows = r_last - r_first + 1;                // <= 42
     const int* pc = pil + ((size_t)m * 2 + 1) * 160 * PIL_STRIDE;
     const uint8_t* hp = hpass + (size_t)m * max_crop * 480;
-    for (int o = threadIdx.x; o < nrows * 480; o += 512) {
-        int r = o / 480, xc = o % 480;
+    // a thread resamples 4 consecutive bytes of an output row: one 32-bit load of the h-pass image per tap
+    for (int o = threadIdx.x; o < nrows * 120; o += 512) {
+        const int r = o / 120, xw = o - r * 120;
         const int* k = pc + (r_first + r) * PIL_STRIDE;
-        int ymin = k[0], cnt = k[1];
-        int acc = 1 << (DFD_PIL_PRECISION - 1);
-        for (int t = 0; t < cnt; t++) acc += hp[(size_t)(ymin + t) * 480 + xc] * k[2 + t];
-        uint8_t v = (uint8_t)dfd_pil_clip8(acc);
-        s160[r][xc] = v;
-        if (face160) face160[((size_t)m * 160 + r_first + r) * 480 + xc] = v;
+        const int ymin = k[0], cnt = k[1];
+        int a0 = 1 << (DFD_PIL_PRECISION - 1), a1 = a0, a2 = a0, a3 = a0;
+        const uint32_t* src = (const uint32_t*)(hp + (size_t)ymin * 480) + xw;
+        for (int t = 0; t < cnt; t++) {
+            const int w = k[2 + t];
+            const uint32_t v = src[(size_t)t * 120];
+            a0 += (int)(v & 255u) * w; a1 += (int)((v >> 8) & 255u) * w; a2 += (int)((v >> 16) & 255u) * w; a3 += (int)(v >> 24) * w;
+        }
+        const uint32_t pk = (uint32_t)dfd_pil_clip8(a0) | ((uint32_t)dfd_pil_clip8(a1) << 8) | ((uint32_t)dfd_pil_clip8(a2) << 16) |
+                            ((uint32_t)dfd_pil_clip8(a3) << 24);
+        *(uint32_t*)&s160[r][xw * 4] = pk;
+        if (face160) *(uint32_t*)(face160 + ((size_t)m * 160 + r_first + r) * 480 + xw * 4) = pk;
     }
     __syncthreads();
     const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
