@@ -133,6 +133,10 @@ __global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ 
     __shared__ uint8_t sg[36][40];
     __shared__ int wpart[8][12];
     __shared__ unsigned int shue[6];
+    __shared__ __align__(16) int s_hsv[512];                // sdiv[256], hdiv180[256]: the first 2 KB of DfdColorTables
+    if (is_full)
+        for (int i = threadIdx.x; i < 128; i += 256) ((uint4*)s_hsv)[i] = ((const uint4*)tab)[i];
+    const DfdColorTables* stab = (const DfdColorTables*)s_hsv;     // dfd_bgr2hsv touches sdiv / hdiv180 only
     const uint8_t* g = gray + (size_t)n * T * T;
     for (int i = threadIdx.x; i < 36 * 36; i += 256) {
         int ly = i / 36, lx = i - ly * 36;
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ 
             const unsigned x2 = (unsigned)(x * x);  // < 2^32
             nsxx_lo += x2 & 0xffffu; nsxx_hi += x2 >> 16;
             int h, sv, v;
-            dfd_bgr2hsv(tab, t3[k][0], t3[k][1], t3[k][2], &h, &sv, &v);
+            dfd_bgr2hsv(stab, t3[k][0], t3[k][1], t3[k][2], &h, &sv, &v);
             ss += sv; sss += sv * sv; vs += v; vss += v * v;
             atomicOr(&shue[h >> 5], 1u << (h & 31));
         }
