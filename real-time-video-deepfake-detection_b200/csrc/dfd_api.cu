@@ -147,6 +147,8 @@ static int create_impl(dfd_ctx* ctx) {
     DFD_CUDA(cudaMalloc(&ctx->d_sescale, nb * 1152 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_se_r, nb * 64 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_wgated, nb * 40 * 240 * sizeof(__nv_bfloat16)));
+    DFD_CUDA(cudaMalloc(&ctx->d_wgated_fold, nb * 32 * 64 * sizeof(__nv_bfloat16)));
+    DFD_CUDA(cudaMemset(ctx->d_wgated_fold, 0, nb * 32 * 64 * sizeof(__nv_bfloat16)));
     DFD_CUDA(cudaMalloc(&ctx->d_feat, nb * 1280 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_fc_h1, nb * 512 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_fc_h2, nb * 256 * sizeof(float)));
@@ -178,6 +180,7 @@ int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
     ctx->no_fuse = getenv("DFD_NO_FUSE") != nullptr;
     ctx->pdl = getenv("DFD_NO_PDL") == nullptr;
     ctx->no_gated_w = getenv("DFD_NO_GATED_W") != nullptr;
+    ctx->no_fold = getenv("DFD_NO_FOLD") != nullptr;
     if (getenv("DFD_SE_MODE")) ctx->se_mode = atoi(getenv("DFD_SE_MODE"));
     int rc = create_impl(ctx);
     if (rc) { g_create_err = ctx->err; dfd_destroy(ctx); *out = nullptr; return rc; }
@@ -190,7 +193,7 @@ void dfd_destroy(dfd_ctx* ctx) {
     void* ptrs[] = {ctx->d_tables, ctx->d_twiddle, ctx->d_state, ctx->d_prev_gray, ctx->d_tile, ctx->d_gray, ctx->d_fft,
                     ctx->d_part, ctx->d_fres, ctx->d_luts, ctx->d_pil, ctx->d_hpass, ctx->d_face160, ctx->d_wf32,
                     ctx->d_wbf16, ctx->d_stem_wg, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
-                    ctx->d_sescale, ctx->d_se_r, ctx->d_front_aux, ctx->d_wgated, ctx->d_wxt, ctx->d_feat, ctx->d_fc_h1, ctx->d_fc_h2, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
+                    ctx->d_sescale, ctx->d_se_r, ctx->d_front_aux, ctx->d_wgated, ctx->d_wgated_fold, ctx->d_bias_fold, ctx->d_wxt, ctx->d_feat, ctx->d_fc_h1, ctx->d_fc_h2, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : ctx->rs_cache) if (e.p) cudaFree(e.p);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
@@ -356,6 +359,7 @@ int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value) {
     if (n == "no_fuse") ctx->no_fuse = value != 0;
     else if (n == "pdl") ctx->pdl = value != 0;
     else if (n == "no_gated_w") ctx->no_gated_w = value != 0;
+    else if (n == "no_fold") ctx->no_fold = value != 0;
     else if (n == "se_mode") ctx->se_mode = value;
     else if (n == "no_overlap") ctx->no_overlap = value != 0;
     else { ctx->err = "dbg_set_option: unknown option " + n; return DFD_ERR_INVALID; }

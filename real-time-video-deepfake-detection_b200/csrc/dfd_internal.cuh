@@ -88,6 +88,9 @@ struct dfd_ctx {
     float* d_pool = nullptr;              // [m][n_parts][C] SE squeeze partial sums (<= DFD_POOL_FLOATS per image)
     float* d_sescale = nullptr;           // [m][1152]
     __nv_bfloat16* d_wgated = nullptr;    // [m][40][240] per-image SE-gated project weights of blocks 0-4
+    __nv_bfloat16* d_wgated_fold = nullptr;   // [m][32][64] block 0: block-diagonal weights of the 2-pixel folded GEMM (off-diagonal zeros)
+    float* d_bias_fold = nullptr;         // [32] block 0 project bias, repeated
+    bool no_fold = false;                 // "no_fold": block 0 project GEMM with one pixel per row
     float* d_front_aux = nullptr;         // mbconv_fused.cu: per block / chunk packed depthwise weights + biases
     size_t front_aux_off[16] = {0};
     float* d_se_r = nullptr;              // [m][64] squeezed activations between the two SE kernels

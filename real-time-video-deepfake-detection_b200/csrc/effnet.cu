@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(SE_X_THREADS) k_se_excite(const float* __restr
 __global__ void __cluster_dims__(SE_CL, 1, 1) __launch_bounds__(256)
 k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restrict__ Wr, const float* __restrict__ br,
              const float* __restrict__ WxT, const float* __restrict__ bx, float* __restrict__ scale, int C, int se,
-             float inv_hw, int m, const float* __restrict__ Wp, __nv_bfloat16* __restrict__ Wg, int N) {
+             float inv_hw, int m, const float* __restrict__ Wp, __nv_bfloat16* __restrict__ Wg, int N, int fold) {
     __shared__ __align__(16) float mean[SE_CL][1152];
     __shared__ float r[SE_CL][64];
     __shared__ float gsm[SE_CL][144];                           // this CTA's gates (8 images x channel slice)
@@ -512,7 +512,13 @@ k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restric
             const int cl = idx % Cs, t = idx / Cs, n = t % N, i = t / N;
             if (b0 + i < m) {
                 const int k = rank * Cs + cl;
-                Wg[((size_t)(b0 + i) * N + n) * C + k] = __float2bfloat16_rn(Wp[(size_t)n * C + k] * gsm[i][cl]);
+                const __nv_bfloat16 w = __float2bfloat16_rn(Wp[(size_t)n * C + k] * gsm[i][cl]);
+                // fold > 1: `fold` consecutive pixels form one GEMM row (K' = fold * C, N' = fold * N) and the weight matrix is
+                // block-diagonal: copy f of W sits at rows f*N.., columns f*C.. (the off-diagonal blocks were zeroed once)
+                if (fold <= 1) Wg[((size_t)(b0 + i) * N + n) * C + k] = w;
+                else
+                    for (int fd = 0; fd < fold; fd++)
+                        Wg[((size_t)(b0 + i) * fold * N + fd * N + n) * (fold * C) + fd * C + k] = w;
             }
         }
     }
@@ -624,6 +630,12 @@ int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n) {
         for (int k = 0; k < 32; k++) wg[n * 32 + k] = __float2bfloat16_rn(k < 27 ? blob[o.stem_w + (size_t)k * 32 + n] : 0.f);
     DFD_CUDA(cudaMemcpy(ctx->d_stem_wg, wg.data(), wg.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     { int rc = dfd_front_pack(ctx, blob); if (rc) return rc; }
+    {   // block 0 project bias repeated for the 2-pixel folded GEMM rows
+        float hb[32];
+        for (int j = 0; j < 32; j++) hb[j] = blob[o.blk[0].bp + (j % 16)];
+        if (!ctx->d_bias_fold) DFD_CUDA(cudaMalloc(&ctx->d_bias_fold, sizeof hb));
+        DFD_CUDA(cudaMemcpy(ctx->d_bias_fold, hb, sizeof hb, cudaMemcpyHostToDevice));
+    }
     ctx->w_floats = o.total;
     ctx->has_weights = true;
     return DFD_OK;
@@ -755,13 +767,16 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         ctx->label = L_SE[i];
         // blocks 0-4 (>= 784 rows per image): the SE gate is folded into per-image project weights by the SE kernel
         const bool gated_w = BF && tc && i <= 4 && ctx->se_mode == 2 && !ctx->no_gated_w;
+        // block 0 (K = 32): two pixels per GEMM row, so the TMA moves full 128-byte rows (its row rate, not bytes, is the limit)
+        const int fold = (gated_w && i == 0 && !ctx->no_fold) ? 2 : 1;
+        __nv_bfloat16* wg_buf = fold > 1 ? ctx->d_wgated_fold : ctx->d_wgated;
         if (BF && ctx->se_mode == 3) {
             // timing experiment only (DFD_SE_MODE=3): no SE excite at all, gates stay whatever they were
         } else if (BF && ctx->se_mode == 2) {
             DFD_CUDA(dfd_launch(ctx->pdl, k_se_cluster, dim3((m + SE_CL - 1) / SE_CL * SE_CL), dim3(256), 0, st, (const float*)ctx->d_pool, n_parts,
                                 (const float*)(Wf + f.wr), (const float*)(Wf + f.br), (const float*)(ctx->d_wxt + wxt_off[i]),
                                 (const float*)(Wf + f.bx), ctx->d_sescale, b.cexp, b.se, 1.0f / (float)(b.hout * b.hout), m,
-                                (const float*)(gated_w ? Wf + f.wp : nullptr), gated_w ? ctx->d_wgated : (__nv_bfloat16*)nullptr, b.cout));
+                                (const float*)(gated_w ? Wf + f.wp : nullptr), gated_w ? wg_buf : (__nv_bfloat16*)nullptr, b.cout, fold));
             DFD_LAUNCH_CHECK("k_se_cluster", st);
         } else if (BF && ctx->se_mode != 0) {
             k_se_excite<<<(m + SE_X_IPC - 1) / SE_X_IPC, SE_X_THREADS, 0, st>>>(ctx->d_pool, n_parts, Wf + f.wr, Wf + f.br, ctx->d_wxt + wxt_off[i],
@@ -781,8 +796,9 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         T* outp = (dw_out == y) ? x : y;       // block 0 wrote dw into y; its project output goes to x (input is dead, no skip)
         ctx->label = L_PROJ[i];
         if (gated_w) {
-            if ((rc = dfd_gemm_bf16_img(ctx, (const __nv_bfloat16*)dw_out, ctx->d_wgated, Wf + f.bp, (const __nv_bfloat16*)(skip ? x : nullptr),
-                                        (__nv_bfloat16*)outp, m, b.hout * b.hout, b.cout, b.cexp, 0, st))) return rc;
+            if ((rc = dfd_gemm_bf16_img(ctx, (const __nv_bfloat16*)dw_out, wg_buf, fold > 1 ? ctx->d_bias_fold : Wf + f.bp,
+                                        (const __nv_bfloat16*)(skip ? x : nullptr), (__nv_bfloat16*)outp, m, b.hout * b.hout / fold,
+                                        b.cout * fold, b.cexp * fold, 0, st))) return rc;
         } else if (tc) {      // the SE gate is applied while the A tile is staged (A_SCALE)
             if ((rc = dfd_gemm_bf16_ex(ctx, 1, (const __nv_bfloat16*)dw_out, ctx->d_sescale, b.hout * b.hout,
                                        ctx->d_wbf16 + f.wp, Wf + f.bp, (const __nv_bfloat16*)(skip ? x : nullptr),
