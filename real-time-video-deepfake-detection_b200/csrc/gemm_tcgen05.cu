@@ -355,8 +355,23 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const float4 b0 = *(const float4*)(sbias + n), b1 = *(const float4*)(sbias + n + 4);
                             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                             if (p.act && !(p.debug & 2)) {
+                                // swish on pairs with packed fp32 math: h = 0.5*(acc + b) as ONE fma (scaling by 0.5 is exact, so this
+                                // rounds exactly like (acc + b) * 0.5), y = h + h * tanh(h): 2 FFMA2 + 2 MUFU per pair
 #pragma unroll
-                                for (int jj = 0; jj < 8; jj++) v[jj] = swish_fast(__uint_as_float(r[h * 8 + jj]) + bb[jj]);
+                                for (int jj = 0; jj < 4; jj++) {
+                                    uint64_t x2, hb2, half2, h2, t2, y2;
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "r"(r[h * 8 + 2 * jj]), "r"(r[h * 8 + 2 * jj + 1]));
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(hb2) : "f"(0.5f * bb[2 * jj]), "f"(0.5f * bb[2 * jj + 1]));
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(half2) : "f"(0.5f), "f"(0.5f));
+                                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(h2) : "l"(x2), "l"(half2), "l"(hb2));
+                                    float h0, h1, t0, t1;
+                                    asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(h2));
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
+                                    asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(y2) : "l"(h2), "l"(t2));
+                                    asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2 * jj]), "=f"(v[2 * jj + 1]) : "l"(y2));
+                                }
                             } else {
 #pragma unroll
                                 for (int jj = 0; jj < 8; jj++) v[jj] = __uint_as_float(r[h * 8 + jj]) + bb[jj];
