@@ -102,12 +102,22 @@ __global__ void k_vote(int n, const int32_t* __restrict__ stream_ids, const doub
 __global__ void k_select_vote(int n, int m, const int32_t* __restrict__ box_frame, const double* __restrict__ face_prob,
                               const dfd_forensic_result* __restrict__ fres, const int32_t* __restrict__ stream_ids,
                               DfdStreamState* __restrict__ state, VoteCfg cfg, dfd_vote_record* __restrict__ rec) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // first box of every frame of this CTA (faces[0], backend_server.py:160): all threads sweep the box list once and
+    // keep the smallest box index per frame in shared memory (a per-thread scan of all m boxes was O(m) dependent loads)
+    __shared__ int s_first[256];
+    const int base = blockIdx.x * blockDim.x;
+    s_first[threadIdx.x] = 0x7fffffff;
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const int f = box_frame[j] - base;
+        if (f >= 0 && f < (int)blockDim.x) atomicMin(&s_first[f], j);
+    }
+    __syncthreads();
+    int i = base + threadIdx.x;
     if (i >= n) return;
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
     double fp = NaN;
-    for (int j = 0; j < m; j++)
-        if (box_frame[j] == i) { fp = face_prob[j]; break; }       // faces[0] (backend_server.py:160)
+    if (s_first[threadIdx.x] != 0x7fffffff) fp = face_prob[s_first[threadIdx.x]];
     double forensic = fres[i].fake_probability;
     double p;
     if (fp == fp) p = cfg.blend_mode == DFD_BLEND_README ? cfg.face_w * fp + cfg.forensic_w * forensic : fp;
