@@ -110,9 +110,18 @@ k_dw_tile(const __nv_bfloat16* __restrict__ in, const float* __restrict__ W, con
 #pragma unroll
         for (int i = 0; i < TW; i++) {
             if (ox0 + i < hout && ch_ok) {
+                // swish on the pair with packed fp32 math (h = 0.5 x exactly, y = h + h * tanh(h): same values as dw_swish)
+                uint64_t h2 = 0, y2;
+                ffma2(h2, acc[i], pack2(0.5f, 0.5f));
+                float h0, h1;
+                unpack2(h2, h0, h1);
+                float t0, t1;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                y2 = h2;
+                ffma2(y2, h2, pack2(t0, t1));
                 float y0, y1;
-                unpack2(acc[i], y0, y1);
-                y0 = dw_swish(y0); y1 = dw_swish(y1);
+                unpack2(y2, y0, y1);
                 ps0 += y0; ps1 += y1;
                 *(__nv_bfloat162*)(orow + (size_t)i * C) = __floats2bfloat162_rn(y0, y1);
             }
