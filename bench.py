@@ -443,6 +443,21 @@ def main():
             ms3 = graph_time(lambda: eng.forensics_batch(f1080, sid64, full64), 10)
             side["config3_forensics_1080p_b64"] = {"frames_per_sec": 64 / ms3 * 1e3, "ms": ms3}
             del f1080
+            # config 5: 4K frames with 8 variable-size face boxes each, fp32 accuracy mode (8 frames = 64 crops per step)
+            eng5 = Engine(device=local, max_streams=8, max_batch=64, max_crop=1200, detection_threshold=0.55)
+            try:
+                eng5.load_state_dict(sd)
+                rng5 = np.random.RandomState(77)
+                f4k = torch.randint(0, 256, (8, 2160, 3840, 3), dtype=torch.uint8, device=dev)
+                bx5 = torch.from_numpy(np.concatenate([synth.make_boxes(8, 2160, 3840, rng5, lo=48, hi=1200) for _ in range(8)])).to(dev)
+                bf5 = torch.arange(8, dtype=torch.int32, device=dev).repeat_interleave(8)
+                sid5 = torch.arange(8, dtype=torch.int32, device=dev)
+                full5 = torch.ones(8, dtype=torch.uint8, device=dev)
+                rec5 = torch.empty(8 * RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+                ms5 = graph_time(lambda: eng5.analyze_batch(f4k, sid5, full5, bx5, bf5, dtype="fp32", records_out=rec5), 5)
+                side["config5_4k_8boxes_fp32"] = {"frames_per_sec": 8 / ms5 * 1e3, "crops_per_sec": 64 / ms5 * 1e3, "ms": ms5}
+            finally:
+                eng5.close()
         except Exception as e:
             side = {"error": str(e)[:200]}
 
