@@ -83,47 +83,128 @@ __global__ void __launch_bounds__(128) k_stem(const T* __restrict__ in, const fl
 }
 
 // ---------------------------------------------------------------------------------------------
-// C[M,N] = act(A[M,K] (* se[img][k]) . W[N,K]^T + bias[n]) (+ residual[M,N]); 64x64x16 tiles, 4x4 per thread.
-template <typename T>
-__global__ void __launch_bounds__(256) k_pw(const T* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
-                                            const float* __restrict__ se, int hw, const T* __restrict__ residual,
-                                            T* __restrict__ C, int M, int N, int K, int act) {
-    __shared__ float sa[16][64 + 4];
+// C[M,N] = act(A[M,K] (* se[img][k]) . W[N,K]^T + bias[n]) (+ residual[M,N]).  BM x 64 x 16 tiles, 4x4 outputs per thread.
+// fp32 path (T = float): 16-byte global loads along K, the SE gate applied as the A tile is loaded (image index per row
+// computed once, no division in the loop), and the next k-block's loads issued before the current block's FMAs.
+// BM = 32 (128 threads) when the 64-row grid would not fill the chip (7x7 / 14x14 stages at small batch).
+template <typename T, int BM>
+__global__ void __launch_bounds__(BM * 4) k_pw(const T* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                                               const float* __restrict__ se, int hw, const T* __restrict__ residual,
+                                               T* __restrict__ C, int M, int N, int K, int act) {
+    constexpr int NT = BM * 4;                                // threads: (BM / 4) x 16
+    __shared__ float sa[16][BM + 4];
     __shared__ float sb[16][64 + 4];
-    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * 64;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int e = threadIdx.x; e < 64 * 16; e += 256) {
-            int r = e >> 4, kk = e & 15;
-            int m = m0 + r, k = k0 + kk;
-            float v = 0.f;
-            if (m < M && k < K) {
-                v = ld1<T>(A + (size_t)m * K + k);
-                if (se) v *= se[(size_t)(m / hw) * K + k];
+    if constexpr (std::is_same<T, float>::value) {
+        // loader mapping: one float4 (4 consecutive k) of one row per thread and tile
+        const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;          // A: rows 0..BM-1
+        const int am = m0 + lr;
+        const bool a_ok = am < M;
+        const float* a_row = A + (size_t)(a_ok ? am : 0) * K;
+        const float* g_row = se ? se + (size_t)((a_ok ? am : 0) / hw) * K : nullptr;
+        constexpr int BPT = 64 * 4 / NT;                                        // W float4 per thread: 1 (BM = 64) or 2 (BM = 32)
+        const float* w_row[BPT];
+        bool w_ok[BPT];
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            const int n = n0 + lr + q * (NT / 4);
+            w_ok[q] = n < N;
+            w_row[q] = W + (size_t)(w_ok[q] ? n : 0) * K;
+        }
+        const bool k4 = (K & 3) == 0;
+        auto load_a = [&](int k0) -> float4 {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int k = k0 + lk;
+            if (a_ok && k < K) {
+                if (k4) {
+                    v = *(const float4*)(a_row + k);
+                    if (g_row) { const float4 g = __ldg((const float4*)(g_row + k)); v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w; }
+                } else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int j = 0; j < 4 && k + j < K; j++) t[j] = a_row[k + j] * (g_row ? g_row[k + j] : 1.0f);
+                    v = make_float4(t[0], t[1], t[2], t[3]);
+                }
             }
-            sa[kk][r] = v;
-            int n = n0 + r;
-            sb[kk][r] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+            return v;
+        };
+        auto load_b = [&](int q, int k0) -> float4 {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int k = k0 + lk;
+            if (w_ok[q] && k < K) {
+                if (k4) v = __ldg((const float4*)(w_row[q] + k));
+                else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int j = 0; j < 4 && k + j < K; j++) t[j] = w_row[q][k + j];
+                    v = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
+            return v;
+        };
+        float4 ra = load_a(0), rb[BPT];
+#pragma unroll
+        for (int q = 0; q < BPT; q++) rb[q] = load_b(q, 0);
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            sa[lk][lr] = ra.x; sa[lk + 1][lr] = ra.y; sa[lk + 2][lr] = ra.z; sa[lk + 3][lr] = ra.w;
+#pragma unroll
+            for (int q = 0; q < BPT; q++) {
+                const int r = lr + q * (NT / 4);
+                sb[lk][r] = rb[q].x; sb[lk + 1][r] = rb[q].y; sb[lk + 2][r] = rb[q].z; sb[lk + 3][r] = rb[q].w;
+            }
+            __syncthreads();
+            if (k0 + 16 < K) {                                                  // next block's loads fly during the FMAs
+                ra = load_a(k0 + 16);
+#pragma unroll
+                for (int q = 0; q < BPT; q++) rb[q] = load_b(q, k0 + 16);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 16; kk++) {
+                const float4 a4 = *(const float4*)&sa[kk][ty * 4];
+                const float4 b4 = *(const float4*)&sb[kk][tx * 4];
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
+    } else {
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            for (int e = threadIdx.x; e < 64 * 16; e += NT) {
+                int r = e >> 4, kk = e & 15;
+                int m = m0 + r, k = k0 + kk;
+                if (r < BM) {
+                    float v = 0.f;
+                    if (m < M && k < K) {
+                        v = ld1<T>(A + (size_t)m * K + k);
+                        if (se) v *= se[(size_t)(m / hw) * K + k];
+                    }
+                    sa[kk][r] = v;
+                }
+                int n = n0 + r;
+                sb[kk][r] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+            }
+            __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; kk++) {
-            float a[4], b[4];
+            for (int kk = 0; kk < 16; kk++) {
+                float a[4], bq[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = sa[kk][ty * 4 + i];
+                for (int i = 0; i < 4; i++) a[i] = sa[kk][ty * 4 + i];
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = sb[kk][tx * 4 + j];
+                for (int j = 0; j < 4; j++) bq[j] = sb[kk][tx * 4 + j];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -717,7 +798,11 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             return dfd_gemm_bf16(ctx, (const __nv_bfloat16*)A, ctx->d_wbf16 + w_off, Wf + b_off, (const __nv_bfloat16*)res,
                                  (__nv_bfloat16*)C, M, N, K, act, st);
         }
-        k_pw<T><<<dim3((M + 63) / 64, (N + 63) / 64), 256, 0, st>>>(A, Wf + w_off, Wf + b_off, se, hw, res, C, M, N, K, act);
+        // 32-row tiles when 64-row tiles would leave SMs idle
+        if ((size_t)((M + 63) / 64) * ((N + 63) / 64) < (size_t)2 * ctx->sm_count)
+            k_pw<T, 32><<<dim3((M + 31) / 32, (N + 63) / 64), 128, 0, st>>>(A, Wf + w_off, Wf + b_off, se, hw, res, C, M, N, K, act);
+        else
+            k_pw<T, 64><<<dim3((M + 63) / 64, (N + 63) / 64), 256, 0, st>>>(A, Wf + w_off, Wf + b_off, se, hw, res, C, M, N, K, act);
         DFD_LAUNCH_CHECK("k_pw", st);
         return DFD_OK;
     };
