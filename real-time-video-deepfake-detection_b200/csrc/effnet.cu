@@ -631,15 +631,18 @@ __global__ void k_pool(const T* __restrict__ x, float* __restrict__ feat, int hw
 }
 
 // One layer of the custom classifier (model.py:50-61, BatchNorm1d folded, Dropout = identity in eval):
-//   out[b][j] = act(W[j] . in[b] + bias[j]);  CTA = 8 outputs (one per warp) x FC_IPC images, so a weight row is
-// fetched once per FC_IPC images with coalesced 16-byte loads and every lane keeps FC_IPC accumulators.
+//   out[b][j] = act(W[j] . in[b] + bias[j]);  CTA = IPC images x 8 * JR outputs; a warp computes JR outputs at once for all
+// IPC images, so an input float4 read from shared memory feeds JR FMAs x 4 (with JR = 1 the layer is bound by shared-memory
+// bandwidth: every (image, output) pair streams the whole input vector) and a weight row is fetched once per IPC images.
+// Large batches use <16, 4>, small ones <8, 1> (more CTAs, lower latency).  The per-image summation order does not depend
+// on IPC / JR (batch invariance).
 #define FC_IPC 8
-template <int IN>
+template <int IN, int IPC, int JR>
 __global__ void __launch_bounds__(256) k_fc_layer(const float* __restrict__ in, const float* __restrict__ W,
                                                   const float* __restrict__ bias, float* __restrict__ out, int J, int m, int relu) {
-    extern __shared__ __align__(16) float s_in[];           // [FC_IPC][IN]
-    const int b0 = blockIdx.y * FC_IPC;
-    for (int e = threadIdx.x; e < FC_IPC * (IN / 4); e += 256) {
+    extern __shared__ __align__(16) float s_in[];           // [IPC][IN]
+    const int b0 = blockIdx.y * IPC;
+    for (int e = threadIdx.x; e < IPC * (IN / 4); e += 256) {
         const int i = e / (IN / 4), c4 = e - i * (IN / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b0 + i < m) v = *(const float4*)(in + (size_t)(b0 + i) * IN + c4 * 4);
@@ -647,28 +650,59 @@ __global__ void __launch_bounds__(256) k_fc_layer(const float* __restrict__ in, 
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * 8 + warp;
-    if (j >= J) return;
-    float a[FC_IPC];
+    const int j0 = (blockIdx.x * 8 + warp) * JR;
+    if (j0 >= J) return;
+    float a[JR][IPC];
 #pragma unroll
-    for (int i = 0; i < FC_IPC; i++) a[i] = 0.f;
-    const float4* w4 = (const float4*)(W + (size_t)j * IN);
-#pragma unroll 2
+    for (int q = 0; q < JR; q++)
+#pragma unroll
+        for (int i = 0; i < IPC; i++) a[q][i] = 0.f;
+    const float4* w4[JR];
+#pragma unroll
+    for (int q = 0; q < JR; q++) w4[q] = (const float4*)(W + (size_t)min(j0 + q, J - 1) * IN);
+    float4 wn[JR];                                          // next iteration's weights, in flight during the FMAs
+#pragma unroll
+    for (int q = 0; q < JR; q++) wn[q] = __ldg(w4[q] + lane);
+#pragma unroll 1
     for (int c4 = lane; c4 < IN / 4; c4 += 32) {
-        const float4 w = __ldg(w4 + c4);
+        float4 w[JR];
 #pragma unroll
-        for (int i = 0; i < FC_IPC; i++) {
+        for (int q = 0; q < JR; q++) w[q] = wn[q];
+        if (c4 + 32 < IN / 4) {
+#pragma unroll
+            for (int q = 0; q < JR; q++) wn[q] = __ldg(w4[q] + c4 + 32);
+        }
+#pragma unroll
+        for (int i = 0; i < IPC; i++) {
             const float4 x = *(const float4*)(s_in + i * IN + c4 * 4);
-            a[i] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, a[i]))));
+#pragma unroll
+            for (int q = 0; q < JR; q++)
+                a[q][i] = fmaf(w[q].x, x.x, fmaf(w[q].y, x.y, fmaf(w[q].z, x.z, fmaf(w[q].w, x.w, a[q][i]))));
         }
     }
-    const float bj = bias[j];
 #pragma unroll
-    for (int i = 0; i < FC_IPC; i++) {
+    for (int q = 0; q < JR; q++) {
+        if (j0 + q >= J) break;
+        const float bj = bias[j0 + q];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
-        if (lane == 0 && b0 + i < m) { const float v = a[i] + bj; out[(size_t)(b0 + i) * J + j] = relu ? fmaxf(v, 0.f) : v; }
+        for (int i = 0; i < IPC; i++) {
+            float v = a[q][i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && b0 + i < m) { v += bj; out[(size_t)(b0 + i) * J + j0 + q] = relu ? fmaxf(v, 0.f) : v; }
+        }
     }
+}
+
+template <int IN, int IPC, int JR>
+static int fc_launch(const float* in, const float* W, const float* bias, float* out, int J, int m, int relu, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_fc_layer<IN, IPC, JR>, cudaFuncAttributeMaxDynamicSharedMemorySize, IPC * IN * 4) != cudaSuccess) return DFD_ERR_CUDA;
+        attr = true;
+    }
+    k_fc_layer<IN, IPC, JR><<<dim3((J + 8 * JR - 1) / (8 * JR), (m + IPC - 1) / IPC), 256, IPC * IN * 4, st>>>(in, W, bias, out, J, m, relu);
+    return DFD_OK;
 }
 
 template <typename T>
@@ -908,17 +942,17 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         }
         ctx->label = "fc";
         {
-            const int mg = (m + FC_IPC - 1) / FC_IPC;
-            static bool attr = false;
-            if (!attr) {
-                DFD_CUDA(cudaFuncSetAttribute(k_fc_layer<1280>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_IPC * 1280 * 4));
-                attr = true;
+            if (m >= 64) {
+                if ((rc = fc_launch<1280, 16, 4>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, ctx->d_fc_h1, 512, m, 1, st))) return rc;
+                DFD_LAUNCH_CHECK("k_fc", st);
+                if ((rc = fc_launch<512, 16, 4>(ctx->d_fc_h1, Wf + o.fc2_w, Wf + o.fc2_b, ctx->d_fc_h2, 256, m, 1, st))) return rc;
+            } else {
+                if ((rc = fc_launch<1280, FC_IPC, 1>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, ctx->d_fc_h1, 512, m, 1, st))) return rc;
+                DFD_LAUNCH_CHECK("k_fc", st);
+                if ((rc = fc_launch<512, FC_IPC, 1>(ctx->d_fc_h1, Wf + o.fc2_w, Wf + o.fc2_b, ctx->d_fc_h2, 256, m, 1, st))) return rc;
             }
-            k_fc_layer<1280><<<dim3(512 / 8, mg), 256, FC_IPC * 1280 * 4, st>>>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, ctx->d_fc_h1, 512, m, 1);
             DFD_LAUNCH_CHECK("k_fc", st);
-            k_fc_layer<512><<<dim3(256 / 8, mg), 256, FC_IPC * 512 * 4, st>>>(ctx->d_fc_h1, Wf + o.fc2_w, Wf + o.fc2_b, ctx->d_fc_h2, 256, m, 1);
-            DFD_LAUNCH_CHECK("k_fc", st);
-            k_fc_layer<256><<<dim3(1, mg), 256, FC_IPC * 256 * 4, st>>>(ctx->d_fc_h2, Wf + o.fc3_w, Wf + o.fc3_b, logits, 1, m, 0);
+            if ((rc = fc_launch<256, FC_IPC, 1>(ctx->d_fc_h2, Wf + o.fc3_w, Wf + o.fc3_b, logits, 1, m, 0, st))) return rc;
         }
         DFD_LAUNCH_CHECK("k_fc", st);
         ctx->label = "";

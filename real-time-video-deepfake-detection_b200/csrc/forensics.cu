@@ -240,44 +240,56 @@ __global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Canny: one CTA per frame.  smem: gray 64 KB + candidate bits 8 KB + strong bits 8 KB.
-__device__ __forceinline__ int sob_mag(const uint8_t* g, int x, int y, int* dxo, int* dyo) {
-    int dx, dy;
-    dfd_sobel3(g, T, T, x, y, &dx, &dy);
-    if (dxo) { *dxo = dx; *dyo = dy; }
-    return dfd_absi(dx) + dfd_absi(dy);
-}
+// Canny: one CTA per frame, two CTAs per SM.  smem: gray 64 KB + candidate bits 8 KB + strong bits 8 KB + one band of packed
+// (magnitude | direction) codes.  The frame is processed in bands of CN_BR rows: phase A computes the Sobel magnitude and the
+// gradient direction class of every pixel of the band (+ one row above and below) ONCE into the band buffer, phase B does the
+// non-maximum suppression from the codes (own code + the two neighbours along the gradient).  The buffer carries a zero column
+// on either side and zero rows outside the frame: cv2 treats the magnitude outside the image as 0.
+#define CN_BR 32
+#define CN_PITCH (T + 2)
+#define CN_SMEM (T * T + 2 * 2048 * 4 + (CN_BR + 2) * CN_PITCH * 2)
 
-struct MagAt {
-    const uint8_t* g;
-    __device__ __forceinline__ int operator()(int x, int y) const {
-        if (x < 0 || y < 0 || x >= T || y >= T) return 0;
-        return sob_mag(g, x, y, nullptr, nullptr);
-    }
-};
-
-__global__ void __launch_bounds__(1024) k_canny(const uint8_t* __restrict__ gray, int* __restrict__ count_out,
-                                                size_t count_stride_bytes, uint8_t* __restrict__ edges_out) {
+__global__ void __launch_bounds__(1024, 2) k_canny(const uint8_t* __restrict__ gray, int* __restrict__ count_out,
+                                                   size_t count_stride_bytes, uint8_t* __restrict__ edges_out) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* sg = smem;
     uint32_t* W = (uint32_t*)(smem + T * T);
     uint32_t* S = W + 2048;
+    uint16_t* mb = (uint16_t*)(S + 2048);
     const int n = blockIdx.x;
     const uint4* src = (const uint4*)(gray + (size_t)n * T * T);
     for (int i = threadIdx.x; i < T * T / 16; i += 1024) ((uint4*)sg)[i] = src[i];
+    if (threadIdx.x < 2 * (CN_BR + 2)) mb[(threadIdx.x >> 1) * CN_PITCH + (threadIdx.x & 1) * (T + 1)] = 0;   // guard columns
     __syncthreads();
-    MagAt mag{sg};
-    for (int it = 0; it < 64; it++) {
-        int p = it * 1024 + threadIdx.x;
-        int y = p >> 8, x = p & 255;
-        int dx, dy;
-        int m = sob_mag(sg, x, y, &dx, &dy);
-        int st = dfd_canny_nms(dx, dy, m, x, y, mag);
-        uint32_t wb = __ballot_sync(0xffffffffu, st >= 1);
-        uint32_t sb = __ballot_sync(0xffffffffu, st == 2);
-        if ((threadIdx.x & 31) == 0) { W[p >> 5] = wb; S[p >> 5] = sb; }
+    for (int y0 = 0; y0 < T; y0 += CN_BR) {
+        for (int i = threadIdx.x; i < (CN_BR + 2) * T; i += 1024) {
+            const int r = i >> 8, x = i & 255, y = y0 - 1 + r;
+            unsigned c = 0;
+            if (y >= 0 && y < T) {
+                int dx, dy;
+                dfd_sobel3(sg, T, T, x, y, &dx, &dy);
+                c = dfd_canny_pack(dx, dy);
+            }
+            mb[r * CN_PITCH + x + 1] = (uint16_t)c;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int i = threadIdx.x; i < CN_BR * T; i += 1024) {
+            const int r = i >> 8, x = i & 255;
+            const uint16_t* q = mb + (r + 1) * CN_PITCH + x + 1;
+            const unsigned c = *q;
+            int st = 0;
+            if ((c & 2047u) > DFD_CANNY_LOW) {
+                const int off = dfd_canny_first_off(c >> 11, CN_PITCH);
+                st = dfd_canny_nms_packed(c, q[off] & 2047, q[-off] & 2047);
+            }
+            const uint32_t wb = __ballot_sync(0xffffffffu, st >= 1);
+            const uint32_t sb = __ballot_sync(0xffffffffu, st == 2);
+            const int p = (y0 + r) * T + x;
+            if ((threadIdx.x & 31) == 0) { W[p >> 5] = wb; S[p >> 5] = sb; }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // hysteresis: S <- W & dilate3x3(S) until stable (monotone, in place)
     while (true) {
         int changed = 0;
@@ -678,7 +690,7 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
     k_tile_stats<<<dim3(DFD_NBLK, n), 256, 0, st>>>(ctx->d_tile, ctx->d_gray, stream_ids, full, ctx->d_tables, ctx->d_state,
                                                      ctx->d_prev_gray, ctx->d_part);
     DFD_LAUNCH_CHECK("k_tile_stats", st);
-    k_canny<<<n, 1024, T * T + 2 * 2048 * 4, st>>>(ctx->d_gray, &ctx->d_part[0].canny_count, sizeof(DfdFramePartials), nullptr);
+    k_canny<<<n, 1024, CN_SMEM, st>>>(ctx->d_gray, &ctx->d_part[0].canny_count, sizeof(DfdFramePartials), nullptr);
     DFD_LAUNCH_CHECK("k_canny", st);
     k_ela<<<n, 512, T * T + 2 * 128 * 128, st>>>(ctx->d_tile, full, ctx->d_part, nullptr);
     DFD_LAUNCH_CHECK("k_ela", st);
@@ -692,7 +704,7 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
 }
 
 int dfd_forensics_init(dfd_ctx* ctx) {
-    DFD_CUDA(cudaFuncSetAttribute(k_canny, cudaFuncAttributeMaxDynamicSharedMemorySize, T * T + 2 * 2048 * 4));
+    DFD_CUDA(cudaFuncSetAttribute(k_canny, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_SMEM));
     DFD_CUDA(cudaFuncSetAttribute(k_ela, cudaFuncAttributeMaxDynamicSharedMemorySize, T * T + 2 * 128 * 128));
     return DFD_OK;
 }
@@ -704,7 +716,7 @@ int dfd_dbg_jpeg_launch(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n,
 }
 
 int dfd_dbg_canny_launch(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, cudaStream_t st) {
-    k_canny<<<n, 1024, T * T + 2 * 2048 * 4, st>>>(gray, nullptr, 0, edges);
+    k_canny<<<n, 1024, CN_SMEM, st>>>(gray, nullptr, 0, edges);
     DFD_LAUNCH_CHECK("k_canny", st);
     return DFD_OK;
 }

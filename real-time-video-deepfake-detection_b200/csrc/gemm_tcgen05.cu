@@ -75,6 +75,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __shared__ __align__(8) uint64_t bars[5 * 8 + 1];     // full[8], empty[8], raw[8], tmem_full[8], tmem_empty[8], bfull
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float sbias[MAX_BIAS];
+    __shared__ __align__(16) float sgate[8][4][64];       // A_SCALE: per staging warp, the current k-block's gates of the tile's <= 4 images
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool plain = p.a_mode == A_TMA || p.a_mode == A_IMG;     // A goes from TMA straight to the MMA
@@ -247,54 +248,88 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tile = ntile;
                 }
             } else {
-            int j = 0;                                             // running k-block index of this CTA (p.stages is even: stage parity == group)
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_blocks) * BLOCK_M;
-                for (int kb = 0; kb < num_kb; kb++, j++) {
-                    if ((j & 1) != g) continue;
+                // A_SCALE.  The gates of a k-block (at most 4 images x 64 channels for one 128-row tile, hw >= 49) are fetched one
+                // k-block AHEAD into registers (lane = image x 8-channel chunk), then published to the warp through a 1 KB
+                // shared-memory table, so the L2 latency of the gate loads is not paid between "raw tile landed" and
+                // "tile ready for the tensor core" (it was: twice per k-block, and it bounded the deep-K 7x7 / 14x14 layers).
+                // The multiply itself is two packed bf16 instructions per pair: g = hi + lo (both bf16, |lo| <= 2^-9 |g|), and
+                // v * g = fma(v, hi, v * lo) -- the inner product is a 2^-9-relative correction term, the fma rounds once, so
+                // the result is the correctly rounded bf16 of v * g up to ~2^-17 relative (unpack / fp32 multiply / re-pack was
+                // 5 instructions per pair and made this fix-up, not the tensor core or the loads, the pace of the layer).
+                uint4* wg_hi = (uint4*)&sgate[warp - 12][0][0];       // [4 images][8 chunks] x 8 bf16
+                uint4* wg_lo = wg_hi + 32;
+                const int c = t & 7;
+                const int gl_img = lane >> 3, gl_c = lane & 7;
+                const int n_img = (p.M + p.hw - 1) / p.hw;
+                int tile = blockIdx.x, kb = g;                        // this group's next k-block (p.stages is even: stage parity == group)
+                auto norm = [&]() { while (kb >= num_kb && tile < p.num_tiles) { kb -= num_kb; tile += gridDim.x; } };
+                norm();
+                float4 q0, q1;
+                auto prefetch = [&]() {
+                    q0 = make_float4(0.f, 0.f, 0.f, 0.f); q1 = q0;
+                    if (tile < p.num_tiles) {
+                        int img = ((tile / p.n_blocks) * BLOCK_M) / p.hw + gl_img;
+                        if (img > n_img - 1) img = n_img - 1;
+                        const int k = kb * BLOCK_K + gl_c * 8;
+                        if (k < p.K) {
+                            const float* sp = p.se + (size_t)img * p.K + k;
+                            q0 = __ldg((const float4*)sp); q1 = __ldg((const float4*)(sp + 4));
+                        }
+                    }
+                };
+                auto split = [](float a, float b, uint32_t& hi, uint32_t& lo) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                    const float2 hf = __bfloat1622float2(h);
+                    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                    hi = *(const uint32_t*)&h; lo = *(const uint32_t*)&l;
+                };
+                prefetch();
+                for (int j = g; tile < p.num_tiles; j += 2) {
+                    const int m0 = (tile / p.n_blocks) * BLOCK_M;
                     const int stage = j % p.stages;
                     const uint32_t phase = (uint32_t)(j / p.stages) & 1u;
                     const uint32_t sa = smem_base + stage * stage_bytes;
-                    if (p.a_mode == A_SCALE) {
-                        mbar_wait(raw0 + 8 * stage, phase);        // raw A (and W) tile landed
-                        const int c = t & 7;
-                        const int k = kb * BLOCK_K + c * 8;
-                        if (k < p.K) {
-                            // image of a row without a division per row: one division per tile, then the (at most 3, hw >= 49)
-                            // image boundaries inside the 128-row tile by comparison
-                            const int img0 = m0 / p.hw, rem0 = m0 - img0 * p.hw;
-                            const int last = p.M - 1 - m0;                         // rows beyond M are clamped to the last row
+                    {
+                        uint4 h, l;
+                        split(q0.x, q0.y, h.x, l.x); split(q0.z, q0.w, h.y, l.y);
+                        split(q1.x, q1.y, h.z, l.z); split(q1.z, q1.w, h.w, l.w);
+                        wg_hi[gl_img * 8 + gl_c] = h; wg_lo[gl_img * 8 + gl_c] = l;
+                    }
+                    __syncwarp();
+                    const int k = kb * BLOCK_K + c * 8;
+                    kb += 2;
+                    norm();
+                    prefetch();                                    // next k-block's gates fly during the wait and the fix-up
+                    mbar_wait(raw0 + 8 * stage, phase);            // raw A (and W) tile landed
+                    if (k < p.K) {
+                        // image of a row without a division per row: one division per tile, then the (at most 3, hw >= 49)
+                        // image boundaries inside the 128-row tile by comparison
+                        const int img0 = m0 / p.hw, rem0 = m0 - img0 * p.hw;
+                        const int last = p.M - 1 - m0;                         // rows beyond M are clamped to the last row
+                        uint4 v[8];
 #pragma unroll
-                            for (int hb = 0; hb < 2; hb++) {
-                                uint4 v[4]; float4 s0[4], s1[4];
+                        for (int i = 0; i < 8; i++) {
+                            const int row = i * 16 + (t >> 3);
+                            v[i] = lds128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)));
+                        }
 #pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    const int row = (hb * 4 + i) * 16 + (t >> 3);
-                                    const int rr = rem0 + (row < last ? row : last);
-                                    const int img = img0 + (rr >= p.hw) + (rr >= 2 * p.hw) + (rr >= 3 * p.hw);
-                                    const float* sp = p.se + (size_t)img * p.K + k;
-                                    s0[i] = __ldg((const float4*)sp); s1[i] = __ldg((const float4*)(sp + 4));
-                                    v[i] = lds128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)));
-                                }
+                        for (int i = 0; i < 8; i++) {
+                            const int row = i * 16 + (t >> 3);
+                            const int rr = rem0 + (row < last ? row : last);
+                            const int rel = (rr >= p.hw) + (rr >= 2 * p.hw) + (rr >= 3 * p.hw);
+                            const uint4 gh = wg_hi[rel * 8 + c], gl = wg_lo[rel * 8 + c];
+                            __nv_bfloat162* h = (__nv_bfloat162*)&v[i];
+                            const __nv_bfloat162* ph = (const __nv_bfloat162*)&gh;
+                            const __nv_bfloat162* pl = (const __nv_bfloat162*)&gl;
 #pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    const int row = (hb * 4 + i) * 16 + (t >> 3);
-                                    __nv_bfloat162* h = (__nv_bfloat162*)&v[i];
-                                    float2 f;
-                                    f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * s0[i].x, f.y * s0[i].y);
-                                    f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * s0[i].z, f.y * s0[i].w);
-                                    f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * s1[i].x, f.y * s1[i].y);
-                                    f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * s1[i].z, f.y * s1[i].w);
-                                    sts128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)), v[i]);
-                                }
-                            }
+                            for (int e = 0; e < 4; e++) h[e] = __hfma2(h[e], ph[e], __hmul2(h[e], pl[e]));
+                            sts128(sa + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)), v[i]);
                         }
                     }
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full0 + 8 * stage);
                 }
-            }
             }
         }
     } else if (warp >= 4) {
@@ -325,10 +360,21 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             const int n_base = n_blk * p.n_pad;
             const int acc = it % p.n_acc;                          // n_acc is even: an accumulator always belongs to the same set
+            const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
+            // residual: the 32 columns of a TMEM read are fetched one read AHEAD (the first before the accumulator is even
+            // complete), so the L2 round trip of these row-strided loads is not paid once per 32 columns
+            uint4 rnx[4];
+            auto load_res = [&](int jb_, int c32_) {
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const int col = jb_ * 64 + c32_ + h * 8, n = n_base + col;
+                    rnx[h] = (rrow && col < p.n_pad && n + 8 <= p.N) ? __ldg((const uint4*)(rrow + n)) : make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            if (p.residual) load_res(split ? half : 0, 0);
             mbar_wait(tfull0 + 8 * acc, (uint32_t)(it / p.n_acc) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
-            const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
             for (int jb = split ? half : 0; jb < ((p.debug & 16) ? 0 : nblk64); jb += split ? 2 : 1, blk_count++) {
                 const uint32_t buf = my_staging + ((split || !p.epi_db) ? 0u : (blk_count & 1u) * STAGING_BLOCK_BYTES);
                 if (issuer) {                                      // this buffer's previous store has been read
@@ -340,6 +386,13 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int c32 = 0; c32 < cols_here; c32 += 32) {
                     uint32_t r[32];
                     tc_ld32(taddr + jb * 64 + c32, r);            // columns beyond n_pad read the other accumulator's TMEM: ignored below
+                    uint4 rcur[4];
+#pragma unroll
+                    for (int h = 0; h < 4; h++) rcur[h] = rnx[h];
+                    if (p.residual) {                              // next read's residual columns (next 32 columns or next 64-column block)
+                        if (c32 + 32 < cols_here) load_res(jb, c32 + 32);
+                        else load_res(jb + (split ? 2 : 1), 0);
+                    }
                     tc_ld_wait();
                     if (jb + (split ? 2 : 1) >= nblk64 && c32 + 32 >= cols_here) {     // last TMEM read of this group for this tile:
                         tc_fence_before();                                              // hand the accumulator back before the math
@@ -377,8 +430,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 for (int jj = 0; jj < 8; jj++) v[jj] = __uint_as_float(r[h * 8 + jj]) + bb[jj];
                             }
                             if (rrow && n + 8 <= p.N) {
-                                const uint4 rv = __ldg((const uint4*)(rrow + n));
-                                const __nv_bfloat162* rh = (const __nv_bfloat162*)&rv;
+                                const __nv_bfloat162* rh = (const __nv_bfloat162*)&rcur[h];
 #pragma unroll
                                 for (int jj = 0; jj < 4; jj++) { float2 f = __bfloat1622float2(rh[jj]); v[2 * jj] += f.x; v[2 * jj + 1] += f.y; }
                             }

@@ -42,6 +42,31 @@ DFD_HD int dfd_canny_nms(int dxv, int dyv, int m, int x, int y, MagFn mag) {
     return m > DFD_CANNY_HIGH ? 2 : 1;
 }
 
+// Packed form of the same rule for kernels that compute every magnitude once: code = magnitude (<= 2040, 11 bits)
+// | direction << 11, direction 0 = horizontal, 1 = vertical, 2 = diagonal with s = +1, 3 = diagonal with s = -1.
+DFD_HD unsigned dfd_canny_pack(int dxv, int dyv) {
+    const int TG22 = 13573;
+    int ax = dfd_absi(dxv), ayv = dfd_absi(dyv), ay = ayv << 15;
+    int tg22x = ax * TG22;
+    unsigned dir;
+    if (ay < tg22x) dir = 0;
+    else if (ay > tg22x + (ax << 16)) dir = 1;
+    else dir = (dxv ^ dyv) < 0 ? 3 : 2;
+    return (unsigned)(ax + ayv) | (dir << 11);
+}
+// offset of the FIRST neighbour of direction `dir` in a magnitude plane of the given pitch (the second is its negation)
+DFD_HD int dfd_canny_first_off(unsigned dir, int pitch) {
+    return dir == 0 ? -1 : dir == 1 ? -pitch : dir == 2 ? -pitch - 1 : -pitch + 1;
+}
+// c = this pixel's code, a / b = magnitudes of the first / second neighbour (0 outside the image)
+DFD_HD int dfd_canny_nms_packed(unsigned c, int a, int b) {
+    const int m = (int)(c & 2047u);
+    if (m <= DFD_CANNY_LOW) return 0;
+    const bool keep = m > a && ((c >> 11) < 2 ? m >= b : m > b);
+    if (!keep) return 0;
+    return m > DFD_CANNY_HIGH ? 2 : 1;
+}
+
 // Laplacian ksize=1: [0 1 0; 1 -4 1; 0 1 0], BORDER_REFLECT_101.
 DFD_HD int dfd_laplacian(const uint8_t* g, int w, int h, int x, int y) {
     int xm = dfd_reflect101(x - 1, w), xp = dfd_reflect101(x + 1, w);

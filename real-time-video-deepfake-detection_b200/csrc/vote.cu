@@ -18,14 +18,16 @@ struct TrackerParams { int window_size, voting_window; double threshold; };
 // Neumaier-compensated (hi, lo) pair; the first item that is not an exact float (np.float64, which is
 // what np.clip returns in apply_heuristics, deepfake_detection.py:502) collapses the pair and every
 // later addition is a plain double add.  is_np[k] != 0 marks such items.
-struct ScoreRing {
-    const double* v; const uint8_t* is_np; int head, n, cap;
-    __device__ double val(int k) const { return v[(head + k) % cap]; }
-    __device__ bool np(int k) const { return is_np[(head + k) % cap] != 0; }
+// The serial arithmetic runs on a copy of the score deque in shared memory, in deque order (ScoreList), which the
+// stream's warp stages with coalesced loads: walking the ring in global memory costs one dependent L2 round trip per item.
+struct ScoreList {
+    const double* v; const uint8_t* is_np;
+    __device__ double val(int k) const { return v[k]; }
+    __device__ bool np(int k) const { return is_np[k] != 0; }
 };
 
 template <class Item>
-__device__ double py_sum(int n, Item item, bool any_np_forces_plain, const ScoreRing& R) {
+__device__ double py_sum(int n, Item item, bool any_np_forces_plain, const ScoreList& R) {
     if (n == 0) return 0.0;
     double hi = item(0), lo = 0.0;
     int k = 1;
@@ -45,79 +47,107 @@ __device__ double py_sum(int n, Item item, bool any_np_forces_plain, const Score
     return hi;
 }
 
-__device__ void tracker_update(DfdStreamState& S, const VoteCfg&, double p, int p_is_np, dfd_vote_record& r) {
+#define VOTE_WARPS 8                                 // streams per CTA: one warp each
+
+// Warp-cooperative TemporalTracker.update + statistics: every lane of the stream's warp calls; lane 0 owns the state
+// updates and the order-sensitive double arithmetic, all lanes stage the score deque.  sv / snp: this warp's
+// DFD_MAX_SCORES-entry staging arrays in shared memory.  r is meaningful in lane 0.
+__device__ void tracker_update(DfdStreamState& S, const VoteCfg&, double p, int p_is_np, dfd_vote_record& r,
+                               double* sv, uint8_t* snp) {
+    const int lane = threadIdx.x & 31;
     TrackerParams c{S.window_size, S.voting_window, S.threshold};
-    r.last_vote = -1; r.reserved = 0;
-    if (p == p) {                                   // update(None) is ignored (:123-124)
-        int slot = S.score_n < c.window_size ? (S.score_head + S.score_n) % c.window_size : S.score_head;
-        S.scores[slot] = p; S.score_is_np[slot] = (uint8_t)(p_is_np != 0);
-        if (S.score_n < c.window_size) S.score_n++; else S.score_head = (S.score_head + 1) % c.window_size;
-        uint8_t cls = p > c.threshold ? 1 : 0;      // strict > (:135)
-        r.last_vote = cls;
-        if (S.vote_n < c.voting_window) { S.votes[(S.vote_head + S.vote_n) % c.voting_window] = cls; S.vote_n++; }
-        else { S.votes[S.vote_head] = cls; S.vote_head = (S.vote_head + 1) % c.voting_window; }
+    if (lane == 0) {
+        r.last_vote = -1; r.reserved = 0;
+        if (p == p) {                                   // update(None) is ignored (:123-124)
+            int slot = S.score_n < c.window_size ? (S.score_head + S.score_n) % c.window_size : S.score_head;
+            S.scores[slot] = p; S.score_is_np[slot] = (uint8_t)(p_is_np != 0);
+            if (S.score_n < c.window_size) S.score_n++; else S.score_head = (S.score_head + 1) % c.window_size;
+            uint8_t cls = p > c.threshold ? 1 : 0;      // strict > (:135)
+            r.last_vote = cls;
+            if (S.vote_n < c.voting_window) { S.votes[(S.vote_head + S.vote_n) % c.voting_window] = cls; S.vote_n++; }
+            else { S.votes[S.vote_head] = cls; S.vote_head = (S.vote_head + 1) % c.voting_window; }
+            int fake = 0;
+            for (int k = 0; k < S.vote_n; k++) fake += S.votes[k];
+            if (S.vote_n < c.voting_window) S.verdict = DFD_UNCERTAIN;          // :158-160
+            else S.verdict = fake > S.vote_n - fake ? DFD_FAKE : DFD_REAL;      // tie -> REAL (:175-178)
+        }
         int fake = 0;
         for (int k = 0; k < S.vote_n; k++) fake += S.votes[k];
-        if (S.vote_n < c.voting_window) S.verdict = DFD_UNCERTAIN;          // :158-160
-        else S.verdict = fake > S.vote_n - fake ? DFD_FAKE : DFD_REAL;      // tie -> REAL (:175-178)
+        r.verdict = S.verdict;
+        r.fake_count = fake;
+        r.real_count = S.vote_n - fake;
+        r.history_len = S.score_n;
+        r.frame_count = S.detector_frames;
+        r.vote_input = p;
     }
-    int fake = 0;
-    for (int k = 0; k < S.vote_n; k++) fake += S.votes[k];
-    r.verdict = S.verdict;
-    r.fake_count = fake;
-    r.real_count = S.vote_n - fake;
-    r.history_len = S.score_n;
-    r.frame_count = S.detector_frames;
-    r.vote_input = p;
-    ScoreRing R{S.scores, S.score_is_np, S.score_head, S.score_n, c.window_size};
+    __syncwarp();                                       // lane 0's ring insertion is visible to the warp
+    const int n = S.score_n, head = S.score_head;
+    for (int k = lane; k < n; k += 32) {
+        const int idx = (head + k) % c.window_size;
+        sv[k] = S.scores[idx];
+        snp[k] = S.score_is_np[idx];
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    ScoreList R{sv, snp};
     bool any_np = false;
-    for (int k = 0; k < S.score_n; k++) any_np |= R.np(k);
-    double sum = py_sum(S.score_n, [&](int k) { return R.val(k); }, false, R);            // sum(deque)/len (:198-202)
-    r.temporal_average = S.score_n ? __ddiv_rn(sum, (double)S.score_n) : 0.0;
-    if (S.score_n < 10) r.stability_score = 0.0;    // :214-221
+    for (int k = 0; k < n; k++) any_np |= R.np(k);
+    double sum = py_sum(n, [&](int k) { return R.val(k); }, false, R);                    // sum(deque)/len (:198-202)
+    r.temporal_average = n ? __ddiv_rn(sum, (double)n) : 0.0;
+    if (n < 10) r.stability_score = 0.0;            // :214-221
     else {
         const double mean = r.temporal_average;
         // (x - mean) ** 2 items are np.float64 as soon as the mean is (any np score) -> plain summation
-        double v = py_sum(S.score_n, [&](int k) { double d = __dsub_rn(R.val(k), mean); return __dmul_rn(d, d); }, any_np, R);
-        v = __ddiv_rn(v, (double)S.score_n);
+        double v = py_sum(n, [&](int k) { double d = __dsub_rn(R.val(k), mean); return __dmul_rn(d, d); }, any_np, R);
+        v = __ddiv_rn(v, (double)n);
         double m4 = __dmul_rn(v, 4.0);
         r.stability_score = __dsub_rn(1.0, m4 < 1.0 ? m4 : 1.0);
     }
 }
 
-__global__ void k_vote(int n, const int32_t* __restrict__ stream_ids, const double* __restrict__ vote_input,
-                       const uint8_t* __restrict__ np_flags, DfdStreamState* __restrict__ state, VoteCfg cfg,
-                       dfd_vote_record* __restrict__ rec) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// CTA = VOTE_WARPS streams, one warp per stream.
+__global__ void __launch_bounds__(32 * VOTE_WARPS)
+k_vote(int n, const int32_t* __restrict__ stream_ids, const double* __restrict__ vote_input,
+       const uint8_t* __restrict__ np_flags, DfdStreamState* __restrict__ state, VoteCfg cfg,
+       dfd_vote_record* __restrict__ rec) {
+    __shared__ double s_v[VOTE_WARPS][DFD_MAX_SCORES];
+    __shared__ uint8_t s_np[VOTE_WARPS][DFD_MAX_SCORES];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * VOTE_WARPS + w;
     if (i >= n) return;
     dfd_vote_record r;
     r.stream_id = stream_ids[i];
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
     r.face_probability = NaN; r.forensic_probability = NaN;
-    tracker_update(state[r.stream_id], cfg, vote_input[i], np_flags ? np_flags[i] : 0, r);
-    rec[i] = r;
+    tracker_update(state[r.stream_id], cfg, vote_input[i], np_flags ? np_flags[i] : 0, r, s_v[w], s_np[w]);
+    if (lane == 0) rec[i] = r;
 }
 
 // analyze_batch tail: choose the vote input per frame, bump detector.frame_count, update the tracker.
-__global__ void k_select_vote(int n, int m, const int32_t* __restrict__ box_frame, const double* __restrict__ face_prob,
-                              const dfd_forensic_result* __restrict__ fres, const int32_t* __restrict__ stream_ids,
-                              DfdStreamState* __restrict__ state, VoteCfg cfg, dfd_vote_record* __restrict__ rec) {
+// CTA = VOTE_WARPS frames, one warp per frame (= per stream).
+__global__ void __launch_bounds__(32 * VOTE_WARPS)
+k_select_vote(int n, int m, const int32_t* __restrict__ box_frame, const double* __restrict__ face_prob,
+              const dfd_forensic_result* __restrict__ fres, const int32_t* __restrict__ stream_ids,
+              DfdStreamState* __restrict__ state, VoteCfg cfg, dfd_vote_record* __restrict__ rec) {
     // first box of every frame of this CTA (faces[0], backend_server.py:160): all threads sweep the box list once and
     // keep the smallest box index per frame in shared memory (a per-thread scan of all m boxes was O(m) dependent loads)
-    __shared__ int s_first[256];
-    const int base = blockIdx.x * blockDim.x;
-    s_first[threadIdx.x] = 0x7fffffff;
+    __shared__ int s_first[VOTE_WARPS];
+    __shared__ double s_v[VOTE_WARPS][DFD_MAX_SCORES];
+    __shared__ uint8_t s_np[VOTE_WARPS][DFD_MAX_SCORES];
+    const int base = blockIdx.x * VOTE_WARPS;
+    if (threadIdx.x < VOTE_WARPS) s_first[threadIdx.x] = 0x7fffffff;
     __syncthreads();
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         const int f = box_frame[j] - base;
-        if (f >= 0 && f < (int)blockDim.x) atomicMin(&s_first[f], j);
+        if (f >= 0 && f < VOTE_WARPS) atomicMin(&s_first[f], j);
     }
     __syncthreads();
-    int i = base + threadIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = base + w;
     if (i >= n) return;
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
     double fp = NaN;
-    if (s_first[threadIdx.x] != 0x7fffffff) fp = face_prob[s_first[threadIdx.x]];
+    if (s_first[w] != 0x7fffffff) fp = face_prob[s_first[w]];
     double forensic = fres[i].fake_probability;
     double p;
     if (fp == fp) p = cfg.blend_mode == DFD_BLEND_README ? cfg.face_w * fp + cfg.forensic_w * forensic : fp;
@@ -125,11 +155,11 @@ __global__ void k_select_vote(int n, int m, const int32_t* __restrict__ box_fram
     dfd_vote_record r;
     r.stream_id = stream_ids[i];
     DfdStreamState& S = state[r.stream_id];
-    S.detector_frames += 1;                                          // backend_server.py:156
+    if (lane == 0) S.detector_frames += 1;                           // backend_server.py:156
     r.face_probability = fp;
     r.forensic_probability = forensic;
-    tracker_update(S, cfg, p, (fp == fp) ? 1 : 0, r);   // face prob is np.float64 (np.clip), forensic prob a Python float
-    rec[i] = r;
+    tracker_update(S, cfg, p, (fp == fp) ? 1 : 0, r, s_v[w], s_np[w]);   // face prob is np.float64 (np.clip), forensic prob a Python float
+    if (lane == 0) rec[i] = r;
 }
 
 // sigmoid + apply_heuristics (deepfake_detection.py:398,489-502)
@@ -175,7 +205,7 @@ int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes,
 
 int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
                     dfd_vote_record* rec, cudaStream_t st) {
-    k_vote<<<(n + 63) / 64, 64, 0, st>>>(n, stream_ids, vote_input, np_flags, ctx->d_state, make_cfg(ctx), rec);
+    k_vote<<<(n + VOTE_WARPS - 1) / VOTE_WARPS, 32 * VOTE_WARPS, 0, st>>>(n, stream_ids, vote_input, np_flags, ctx->d_state, make_cfg(ctx), rec);
     DFD_LAUNCH_CHECK("k_vote", st);
     return DFD_OK;
 }
@@ -183,7 +213,7 @@ int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_
 int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame, const double* face_prob,
                            const dfd_forensic_result* fres, const int32_t* stream_ids, dfd_vote_record* rec,
                            cudaStream_t st) {
-    k_select_vote<<<(n + 63) / 64, 64, 0, st>>>(n, m, box_frame, face_prob, fres, stream_ids, ctx->d_state, make_cfg(ctx), rec);
+    k_select_vote<<<(n + VOTE_WARPS - 1) / VOTE_WARPS, 32 * VOTE_WARPS, 0, st>>>(n, m, box_frame, face_prob, fres, stream_ids, ctx->d_state, make_cfg(ctx), rec);
     DFD_LAUNCH_CHECK("k_select_vote", st);
     return DFD_OK;
 }

@@ -172,6 +172,11 @@ void hc_canny(const uint8_t* g, int h, int w, uint8_t* dst) {
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             st[y * w + x] = dfd_canny_nms(dxs[y * w + x], dys[y * w + x], mag[y * w + x], x, y, M);
+            // the packed form the CUDA kernel uses must give the same state
+            const unsigned c = dfd_canny_pack(dxs[y * w + x], dys[y * w + x]);
+            const int off = dfd_canny_first_off(c >> 11, w);
+            const int ox = off == -1 ? -1 : off == -w ? 0 : off == -w - 1 ? -1 : 1, oy = off == -1 ? 0 : -1;
+            if (st[y * w + x] != dfd_canny_nms_packed(c, M(x + ox, y + oy), M(x - ox, y - oy))) st[y * w + x] = 77;
             if (st[y * w + x] == 2) stack.push_back(y * w + x);
         }
     while (!stack.empty()) {
