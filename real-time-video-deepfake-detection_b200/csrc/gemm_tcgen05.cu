@@ -68,6 +68,9 @@ struct GemmParams {
     const float* se;           // A_SCALE: [images][K] gates
 };
 
+// RES: the layer has a residual input (its epilogue prefetches the residual one TMEM read ahead; layers without one keep the
+// shorter epilogue -- the narrow early layers are bound by per-tile epilogue latency and pay for every extra instruction)
+template <bool RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
@@ -360,7 +363,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             const int n_base = n_blk * p.n_pad;
             const int acc = it % p.n_acc;                          // n_acc is even: an accumulator always belongs to the same set
-            const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
+            const __nv_bfloat16* rrow = (RES && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
             // residual: the 32 columns of a TMEM read are fetched one read AHEAD (the first before the accumulator is even
             // complete), so the L2 round trip of these row-strided loads is not paid once per 32 columns
             uint4 rnx[4];
@@ -371,7 +374,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     rnx[h] = (rrow && col < p.n_pad && n + 8 <= p.N) ? __ldg((const uint4*)(rrow + n)) : make_uint4(0u, 0u, 0u, 0u);
                 }
             };
-            if (p.residual) load_res(split ? half : 0, 0);
+            if (RES) load_res(split ? half : 0, 0);
             mbar_wait(tfull0 + 8 * acc, (uint32_t)(it / p.n_acc) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
@@ -387,9 +390,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     uint32_t r[32];
                     tc_ld32(taddr + jb * 64 + c32, r);            // columns beyond n_pad read the other accumulator's TMEM: ignored below
                     uint4 rcur[4];
+                    if (RES) {                                     // next read's residual columns (next 32 columns or next 64-column block)
 #pragma unroll
-                    for (int h = 0; h < 4; h++) rcur[h] = rnx[h];
-                    if (p.residual) {                              // next read's residual columns (next 32 columns or next 64-column block)
+                        for (int h = 0; h < 4; h++) rcur[h] = rnx[h];
                         if (c32 + 32 < cols_here) load_res(jb, c32 + 32);
                         else load_res(jb + (split ? 2 : 1), 0);
                     }
@@ -429,7 +432,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                                 for (int jj = 0; jj < 8; jj++) v[jj] = __uint_as_float(r[h * 8 + jj]) + bb[jj];
                             }
-                            if (rrow && n + 8 <= p.N) {
+                            if (RES && rrow && n + 8 <= p.N) {
                                 const __nv_bfloat162* rh = (const __nv_bfloat162*)&rcur[h];
 #pragma unroll
                                 for (int jj = 0; jj < 4; jj++) { float2 f = __bfloat1622float2(rh[jj]); v[2 * jj] += f.x; v[2 * jj + 1] += f.y; }
@@ -586,7 +589,8 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     const size_t smem = (size_t)stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr_set = true;
     }
     CUtensorMap ma, mb, mc;
@@ -595,7 +599,8 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     if ((rc = make_map(ctx, &mb, W, (uint64_t)N, (uint64_t)K, (uint32_t)n_pad))) return rc;
     if ((rc = make_map(ctx, &mc, C, (uint64_t)M, (uint64_t)N, BLOCK_M))) return rc;
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
+    if (p.residual) DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05<true>, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
+    else DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05<false>, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
     DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);
     return DFD_OK;
 }
@@ -625,7 +630,8 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
     const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr_set = true;
     }
     CUtensorMap ma, mb, mc;
@@ -645,7 +651,8 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
         if ((rc = dfd_tmap_bf16(ctx, &mc, C, 3, d, s, b, 128))) return rc;
     }
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
+    if (p.residual) DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05<true>, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
+    else DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05<false>, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
     DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);
     return DFD_OK;
 }
