@@ -70,7 +70,8 @@ struct GemmParams {
 
 // RES: the layer has a residual input (its epilogue prefetches the residual one TMEM read ahead; layers without one keep the
 // shorter epilogue -- the narrow early layers are bound by per-tile epilogue latency and pay for every extra instruction)
-template <bool RES>
+// ACT / DENSE: swish epilogue / dense bulk-store epilogue (p.act, p.dense_c) resolved at compile time for the same reason.
+template <bool RES, bool ACT, bool DENSE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
@@ -410,7 +411,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             float v[8];
                             const float4 b0 = *(const float4*)(sbias + n), b1 = *(const float4*)(sbias + n + 4);
                             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                            if (p.act && !(p.debug & 2)) {
+                            if (ACT && !(p.debug & 2)) {
                                 // swish on pairs with packed fp32 math: h = 0.5*(acc + b) as ONE fma (scaling by 0.5 is exact, so this
                                 // rounds exactly like (acc + b) * 0.5), y = h + h * tanh(h): 2 FFMA2 + 2 MUFU per pair
 #pragma unroll
@@ -441,7 +442,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             __nv_bfloat162* oh = (__nv_bfloat162*)&o;
 #pragma unroll
                             for (int jj = 0; jj < 4; jj++) oh[jj] = __floats2bfloat162_rn(v[2 * jj], v[2 * jj + 1]);
-                            if (p.dense_c) { if (col < p.N) sts128(buf + (uint32_t)(row * (p.N * 2) + (col >> 3) * 16), o); }
+                            if (DENSE) { if (col < p.N) sts128(buf + (uint32_t)(row * (p.N * 2) + (col >> 3) * 16), o); }
                             else sts128(buf + (uint32_t)(row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4)), o);
                         }
                     }
@@ -450,7 +451,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 set_bar_sync(1 + grp);
                 if (issuer) {
                     if (n_base + jb * 64 < p.N && !(p.debug & 1)) {
-                        if (p.dense_c) {
+                        if (DENSE) {
                             // rows of a narrow C tile are 32-128 bytes: 128 separate row writes through the tensor path cost
                             // more than the tile's math; the tile is contiguous in C, so it goes out as ONE bulk copy
                             const int lim = p.a_mode == A_IMG ? p.hw : p.M;
@@ -532,6 +533,33 @@ static int gemm_n_acc(int n_pad) {
     while (n > 2 && (n - 1) * n_pad + ((n_pad + 31) & ~31) > 512) n -= 2;
     return n;
 }
+typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+static GemmKernel gemm_kernel(const GemmParams& p) {
+    const int sel = (p.residual ? 4 : 0) | (p.act ? 2 : 0) | (p.dense_c ? 1 : 0);
+    switch (sel) {
+        case 0: return k_gemm_tcgen05<false, false, false>;
+        case 1: return k_gemm_tcgen05<false, false, true>;
+        case 2: return k_gemm_tcgen05<false, true, false>;
+        case 3: return k_gemm_tcgen05<false, true, true>;
+        case 4: return k_gemm_tcgen05<true, false, false>;
+        case 5: return k_gemm_tcgen05<true, false, true>;
+        case 6: return k_gemm_tcgen05<true, true, false>;
+        default: return k_gemm_tcgen05<true, true, true>;
+    }
+}
+static int gemm_set_attrs(dfd_ctx* ctx) {
+    static bool done = false;
+    if (done) return DFD_OK;
+    GemmParams q;
+    memset(&q, 0, sizeof q);
+    for (int sel = 0; sel < 8; sel++) {
+        q.residual = (sel & 4) ? (const __nv_bfloat16*)1 : nullptr; q.act = (sel & 2) ? 1 : 0; q.dense_c = sel & 1;
+        DFD_CUDA(cudaFuncSetAttribute(gemm_kernel(q), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    }
+    done = true;
+    return DFD_OK;
+}
+
 static bool g_no_dense = getenv("DFD_NO_DENSE_C") != nullptr;     // A/B switch for the dense bulk-store epilogue
 static bool g_enabled = true;
 static int g_debug = 0;
@@ -589,8 +617,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     const size_t smem = (size_t)stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        if ((rc = gemm_set_attrs(ctx))) return rc;
         attr_set = true;
     }
     CUtensorMap ma, mb, mc;
@@ -599,8 +626,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     if ((rc = make_map(ctx, &mb, W, (uint64_t)N, (uint64_t)K, (uint32_t)n_pad))) return rc;
     if ((rc = make_map(ctx, &mc, C, (uint64_t)M, (uint64_t)N, BLOCK_M))) return rc;
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    if (p.residual) DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05<true>, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
-    else DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05<false>, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
+    DFD_CUDA(dfd_launch(ctx->pdl, gemm_kernel(p), dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
     DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);
     return DFD_OK;
 }
@@ -630,8 +656,7 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
     const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        DFD_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        if ((rc = gemm_set_attrs(ctx))) return rc;
         attr_set = true;
     }
     CUtensorMap ma, mb, mc;
@@ -651,8 +676,7 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
         if ((rc = dfd_tmap_bf16(ctx, &mc, C, 3, d, s, b, 128))) return rc;
     }
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    if (p.residual) DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05<true>, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
-    else DFD_CUDA(dfd_launch(ctx->pdl, k_gemm_tcgen05<false>, dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
+    DFD_CUDA(dfd_launch(ctx->pdl, gemm_kernel(p), dim3(grid), dim3(GEMM_THREADS), smem, st, ma, mb, mc, p));
     DFD_LAUNCH_CHECK("k_gemm_tcgen05", st);
     return DFD_OK;
 }

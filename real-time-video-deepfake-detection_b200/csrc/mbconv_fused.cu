@@ -363,8 +363,13 @@ k_mbconv_front(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// chunk width per block: 48 divides every expanded width (96 .. 672) exactly; 1152 = 18 x 64
-static int front_cc(int blk) { return EFF_BLOCKS[blk].cexp == 1152 ? 64 : 48; }
+// chunk width per block: 48 divides every expanded width (96 .. 672) exactly, but fills only 24 of the 32 lanes of the
+// depthwise stage (lane = channel pair).  64-wide chunks where the padding of the last chunk costs less than that:
+// 240 = 3.75 x 64, 480 = 7.5 x 64, 1152 = 18 x 64 (96, 144 and 672 stay at 48: 672 does not fit two CTAs per SM at 64).
+static int front_cc(int blk) {
+    const int c = EFF_BLOCKS[blk].cexp;
+    return (c == 1152 || c == 480 || c == 240) ? 64 : 48;
+}
 
 // Packs, per block and per chunk, the depthwise weights and both biases into one contiguous bulk-copy source.
 int dfd_front_pack(dfd_ctx* ctx, const float* blob) {
@@ -460,9 +465,12 @@ int dfd_mbconv_front_bf16(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const _
     if (b.k == 3 && b.s == 2 && b.hin == 112) return launch_front<3, 2, 7, 8, 48, 112, false, 16, 2, 3>(MF_ARGS);      // 16 input channels: 32-byte operand rows
     if (b.k == 3 && b.s == 1 && b.hin == 56) return launch_front<3, 1, 14, 14, 48, 56, false, 32, 4, 2>(MF_ARGS);    // 24 input channels: 64-byte operand rows
     if (b.k == 5 && b.s == 2 && b.hin == 56) return launch_front<5, 2, 7, 7, 48, 56, false, 32, 4, 2>(MF_ARGS);
-    if (b.k == 5 && b.s == 1 && b.hin == 28) return launch_front<5, 1, 14, 14, 48, 28, false>(MF_ARGS);
-    if (b.k == 3 && b.s == 2 && b.hin == 28) return launch_front<3, 2, 7, 7, 48, 28, false>(MF_ARGS);
-    if (b.k == 3 && b.s == 1 && b.hin == 14) return launch_front<3, 1, 14, 14, 48, 14, true>(MF_ARGS);
+    // 64-wide chunks with 32-byte operand rows (40 / 80 input channels = 3 / 5 exact 16-channel k-blocks: no zero-filled
+    // operand columns, which is what makes the wider patch fit two CTAs per SM)
+    if (b.k == 5 && b.s == 1 && b.hin == 28) return launch_front<5, 1, 14, 14, 64, 28, false, 16>(MF_ARGS);
+    if (b.k == 3 && b.s == 2 && b.hin == 28) return launch_front<3, 2, 7, 7, 64, 28, false, 16>(MF_ARGS);
+    if (b.k == 3 && b.s == 1 && b.hin == 14) return launch_front<3, 1, 14, 14, 64, 14, true, 16>(MF_ARGS);
+    if (b.k == 5 && b.s == 1 && b.hin == 14 && b.cexp == 480) return launch_front<5, 1, 14, 14, 64, 14, true, 16>(MF_ARGS);
     if (b.k == 5 && b.s == 1 && b.hin == 14) return launch_front<5, 1, 14, 14, 48, 14, true>(MF_ARGS);
     if (b.k == 5 && b.s == 2 && b.hin == 14) return launch_front<5, 2, 7, 7, 48, 14, true>(MF_ARGS);
     if (b.k == 5 && b.s == 1 && b.hin == 7) return launch_front<5, 1, 7, 7, 64, 7, true>(MF_ARGS);
