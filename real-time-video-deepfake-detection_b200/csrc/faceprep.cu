@@ -52,23 +52,35 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ f
     const int area = g.tw * g.th;
     const unsigned magic = g.tw > 1 ? 0xffffffffu / (unsigned)g.tw + 1u : 0u;   // p / tw == umulhi(p, magic) for p * tw < 2^32
     int* h = hist[warp];
-    for (int p0 = 0; p0 < area; p0 += 32) {
-        const int p = p0 + lane;
-        const bool ok = p < area;
-        int L = 0;
-        if (ok) {
-            const int yy = g.tw > 1 ? (int)__umulhi((unsigned)p, magic) : p, xx = p - yy * g.tw;
-            int y = ty * g.th + yy, x = tx * g.tw + xx;
-            if (x >= bw) x = dfd_reflect101(x, bw);
-            if (y >= bh) y = dfd_reflect101(y, bh);
-            const uint8_t* px = f + (size_t)(by + y) * pitch + (size_t)(bx + x) * 3;
-            L = dfd_bgr2lab_L(s_gamma, s_cbrt, px[0], px[1], px[2]);
+    // four pixels per lane per trip: the 12 byte loads of a trip are issued before the first conversion, so a warp has four
+    // DRAM round trips in flight instead of one (the crop is read here for the first time: the loop was latency-bound)
+    for (int p0 = 0; p0 < area; p0 += 128) {
+        int b[4], gq[4], r[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = p0 + u * 32 + lane;
+            ok[u] = p < area;
+            b[u] = gq[u] = r[u] = 0;
+            if (ok[u]) {
+                const int yy = g.tw > 1 ? (int)__umulhi((unsigned)p, magic) : p, xx = p - yy * g.tw;
+                int y = ty * g.th + yy, x = tx * g.tw + xx;
+                if (x >= bw) x = dfd_reflect101(x, bw);
+                if (y >= bh) y = dfd_reflect101(y, bh);
+                const uint8_t* px = f + (size_t)(by + y) * pitch + (size_t)(bx + x) * 3;
+                b[u] = __ldg(px); gq[u] = __ldg(px + 1); r[u] = __ldg(px + 2);
+            }
         }
-        // warp-aggregated histogram update: one shared atomic per distinct value
-        const unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            const unsigned peers = __match_any_sync(act, L);
-            if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&h[L], __popc(peers));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (p0 + u * 32 >= area) break;                     // warp-uniform
+            const int L = ok[u] ? dfd_bgr2lab_L(s_gamma, s_cbrt, b[u], gq[u], r[u]) : 0;
+            // warp-aggregated histogram update: one shared atomic per distinct value
+            const unsigned act = __ballot_sync(0xffffffffu, ok[u]);
+            if (ok[u]) {
+                const unsigned peers = __match_any_sync(act, L);
+                if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&h[L], __popc(peers));
+            }
         }
     }
     __syncwarp();
@@ -212,8 +224,18 @@ __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict
         *(uint32_t*)&s160[r][xw * 4] = pk;
         if (face160) *(uint32_t*)(face160 + ((size_t)m * 160 + r_first + r) * 480 + xw * 4) = pk;
     }
+    // bilinear source columns / weights of the 224 output columns: computed once per CTA instead of once per output value
+    __shared__ float s_xw[224][2];
+    __shared__ uint16_t s_xi[224][2];
+    for (int x = threadIdx.x; x < 224; x += 512) {
+        int x0, x1; float w0, w1;
+        dfd_torch_bilinear_coef(x, 160, 224, &x0, &x1, &w0, &w1);
+        s_xi[x][0] = (uint16_t)(x0 * 3); s_xi[x][1] = (uint16_t)(x1 * 3);
+        s_xw[x][0] = w0; s_xw[x][1] = w1;
+    }
     __syncthreads();
-    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    // (x / 255 - mean) / std with both divisions as exact 3-instruction constant divisions (dfd_div_const)
+    constexpr float R255 = 1.0f / 255.0f;
     // a thread produces 8 consecutive values of an output row (672 = 84 x 8 per row) and stores them as 16-byte vectors
     for (int o = threadIdx.x; o < 56 * 84; o += 512) {
         const int yr = o / 84, v8 = o - yr * 84;
@@ -223,16 +245,23 @@ __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict
         const uint8_t* r0 = s160[y0 - r_first];
         const uint8_t* r1 = s160[y1 - r_first];
         float v[8];
-        int xprev = -1, x0 = 0, x1 = 0; float w0 = 0.f, w1 = 0.f;
+        const int e0 = v8 * 8, xb = e0 / 3;
+        int c = e0 - xb * 3, x = xb;
+        int i0 = s_xi[x][0], i1 = s_xi[x][1]; float w0 = s_xw[x][0], w1 = s_xw[x][1];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int e = v8 * 8 + j, x = e / 3, c = e - x * 3;
-            if (x != xprev) { dfd_torch_bilinear_coef(x, 160, 224, &x0, &x1, &w0, &w1); xprev = x; }
-            const float p00 = r0[x0 * 3 + c], p01 = r0[x1 * 3 + c], p10 = r1[x0 * 3 + c], p11 = r1[x1 * 3 + c];
+            const float p00 = r0[i0 + c], p01 = r0[i1 + c], p10 = r1[i0 + c], p11 = r1[i1 + c];
             float t = DFD_FADD(DFD_FMUL(h0, DFD_FADD(DFD_FMUL(w0, p00), DFD_FMUL(w1, p01))),
                                DFD_FMUL(h1, DFD_FADD(DFD_FMUL(w0, p10), DFD_FMUL(w1, p11))));
-            t = DFD_FDIV(t, 255.0f);
-            v[j] = DFD_FDIV(DFD_FSUB(t, c == 0 ? mean[0] : (c == 1 ? mean[1] : mean[2])), c == 0 ? stdv[0] : (c == 1 ? stdv[1] : stdv[2]));
+            t = dfd_div_const(t, 255.0f, R255);
+            const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+            const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+            const float rs = c == 0 ? 1.0f / 0.229f : (c == 1 ? 1.0f / 0.224f : 1.0f / 0.225f);
+            v[j] = dfd_div_const(DFD_FSUB(t, mean), sd, rs);
+            if (++c == 3) {
+                c = 0; ++x;
+                if (j < 7) { i0 = s_xi[x][0]; i1 = s_xi[x][1]; w0 = s_xw[x][0]; w1 = s_xw[x][1]; }
+            }
         }
         store8<OutT>(out + (((size_t)m * 224 + y) * 224) * 3 + v8 * 8, v);
     }

@@ -48,3 +48,11 @@ DFD_HD int dfd_reflect101(int p, int n) {          // cv::BORDER_REFLECT_101
     while (p < 0 || p >= n) { if (p < 0) p = -p; else p = 2 * n - 2 - p; }
     return p;
 }
+
+// t / d for a compile-time constant d, correctly rounded, in three instructions: q = t * r, q' = fma(fma(-d, q, t), r, q)
+// with r = RN(1 / d).  Proven equal to the IEEE quotient by exhaustion for the operand ranges of the face-prep
+// normalisation (tests/hostcheck/divconst_check.c); NOT valid for denormal quotients.
+DFD_HD float dfd_div_const(float t, float d, float r) {
+    const float q = DFD_FMUL(t, r);
+    return DFD_FFMA(DFD_FFMA(-d, q, t), r, q);
+}
