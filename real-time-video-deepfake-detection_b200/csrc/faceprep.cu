@@ -87,10 +87,10 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ f
     dfd_clahe_lut_warp(h, g.clip, g.lut_scale, luts + ((size_t)m * 64 + ty * 8 + tx) * 256, lane);
 }
 
-// CTA = HP_ROWS consecutive crop rows of one box, warp = one row at a time: BGR -> LAB -> CLAHE(L) -> LAB2BGR -> RGB row
+// CTA = HP_ROWS consecutive crop rows of one box (32: staging the 34 KB of tables costs more than 16 rows of pixels), warp = one row at a time: BGR -> LAB -> CLAHE(L) -> LAB2BGR -> RGB row
 // in shared memory, then Pillow's horizontal resampling pass of that row to 160 pixels.  The colour tables and the
 // box's 64 CLAHE LUTs are staged in shared memory once per CTA (11 table gathers + 4 LUT gathers per pixel).
-#define HP_ROWS 16
+#define HP_ROWS 32
 #define DFD_PIL_KMAX_STAGED 15      // Pillow tap counts up to 15 (crops up to 1120 px) are staged in shared memory
 __global__ void __launch_bounds__(256) k_clahe_hpass(const uint8_t* __restrict__ frames, size_t fstride, int pitch,
                                                      const int32_t* __restrict__ boxes, const int32_t* __restrict__ frame_idx,
@@ -214,10 +214,20 @@ __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict
         const int ymin = k[0], cnt = k[1];
         int a0 = 1 << (DFD_PIL_PRECISION - 1), a1 = a0, a2 = a0, a3 = a0;
         const uint32_t* src = (const uint32_t*)(hp + (size_t)ymin * 480) + xw;
-        for (int t = 0; t < cnt; t++) {
-            const int w = k[2 + t];
-            const uint32_t v = src[(size_t)t * 120];
-            a0 += (int)(v & 255u) * w; a1 += (int)((v >> 8) & 255u) * w; a2 += (int)((v >> 16) & 255u) * w; a3 += (int)(v >> 24) * w;
+        // four taps per trip, loads first: the h-pass image comes from L2 and a one-tap loop pays that latency per tap
+        for (int t = 0; t < cnt; t += 4) {
+            int w[4]; uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const bool ok = t + u < cnt;
+                w[u] = ok ? k[2 + t + u] : 0;
+                v[u] = ok ? src[(size_t)(t + u) * 120] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                a0 += (int)(v[u] & 255u) * w[u]; a1 += (int)((v[u] >> 8) & 255u) * w[u];
+                a2 += (int)((v[u] >> 16) & 255u) * w[u]; a3 += (int)(v[u] >> 24) * w[u];
+            }
         }
         const uint32_t pk = (uint32_t)dfd_pil_clip8(a0) | ((uint32_t)dfd_pil_clip8(a1) << 8) | ((uint32_t)dfd_pil_clip8(a2) << 16) |
                             ((uint32_t)dfd_pil_clip8(a3) << 24);

@@ -121,7 +121,7 @@ __device__ __forceinline__ V block_sum_256(V v, V* sh /* [8] */) {
 // separably on an 8x5 register window (40 shared loads for 4 pixels instead of 100) and the Laplacian reads the same
 // registers.  Every sum is an exact integer: warp sums use redux.sync on 32-bit pieces (the one 64-bit quantity, the sum
 // of squared noise residuals, is reduced as 16-bit halves), one barrier, then 11 threads add the 8 warp partials.
-__global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ tile, const uint8_t* __restrict__ gray,
+__global__ void __launch_bounds__(256, 6) k_tile_stats(const uint8_t* __restrict__ tile, const uint8_t* __restrict__ gray,
                                                     const int32_t* __restrict__ stream_ids,
                                                     const uint8_t* __restrict__ full, const DfdColorTables* __restrict__ tab,
                                                     const DfdStreamState* __restrict__ state, uint8_t* __restrict__ prev_gray,
@@ -137,16 +137,41 @@ __global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ 
     if (is_full)
         for (int i = threadIdx.x; i < 128; i += 256) ((uint4*)s_hsv)[i] = ((const uint4*)tab)[i];
     const DfdColorTables* stab = (const DfdColorTables*)s_hsv;     // dfd_bgr2hsv touches sdiv / hdiv180 only
+    // The CTA's work is a few hundred instructions; what it costs is its chain of dependent global round trips.  Every
+    // global load of the thread (halo bytes, previous gray, colour pixels) is therefore issued up front, before the first
+    // shared-memory store and the barrier: {full, stream id} -> {halo, prev, tile} -> compute, two round trips instead of four.
     const uint8_t* g = gray + (size_t)n * T * T;
-    for (int i = threadIdx.x; i < 36 * 36; i += 256) {
-        int ly = i / 36, lx = i - ly * 36;
-        int gy = dfd_reflect101(by * 32 + ly - 2, T), gx = dfd_reflect101(bx * 32 + lx - 2, T);
-        sg[ly][lx] = g[gy * T + gx];
+    uint8_t* prev = prev_gray + (size_t)sid * T * T;
+    const int lx = threadIdx.x & 31, ly0 = (threadIdx.x >> 5) * 4, warp = threadIdx.x >> 5;
+    const size_t g0 = (size_t)(by * 32 + ly0) * T + bx * 32 + lx;
+    uint8_t hv[6];
+#pragma unroll
+    for (int u = 0; u < 6; u++) {
+        const int i = threadIdx.x + u * 256;
+        hv[u] = 0;
+        if (i < 36 * 36) {
+            const int hy = i / 36, hx = i - hy * 36;
+            const int gy = dfd_reflect101(by * 32 + hy - 2, T), gx = dfd_reflect101(bx * 32 + hx - 2, T);
+            hv[u] = g[gy * T + gx];
+        }
+    }
+    int pv[4]; uint8_t t3[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        pv[k] = prev[g0 + (size_t)k * T];
+        t3[k][0] = t3[k][1] = t3[k][2] = 0;
+        if (is_full) {
+            const uint8_t* tp = tile + ((size_t)n * T * T + g0 + (size_t)k * T) * 3;
+            t3[k][0] = tp[0]; t3[k][1] = tp[1]; t3[k][2] = tp[2];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 6; u++) {
+        const int i = threadIdx.x + u * 256;
+        if (i < 36 * 36) (&sg[0][0])[(i / 36) * 40 + (i % 36)] = hv[u];
     }
     if (threadIdx.x < 6) shue[threadIdx.x] = 0;
     __syncthreads();
-    uint8_t* prev = prev_gray + (size_t)sid * T * T;
-    const int lx = threadIdx.x & 31, ly0 = (threadIdx.x >> 5) * 4, warp = threadIdx.x >> 5;
     int ls = 0, lss = 0, td = 0, nsx = 0, ss = 0, sss = 0, vs = 0, vss = 0;
     unsigned nsxx_lo = 0, nsxx_hi = 0;
     if (is_full) {
@@ -157,14 +182,6 @@ __global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ 
             const int a0 = sg[ly0 + j][lx], a1 = sg[ly0 + j][lx + 1], a2 = sg[ly0 + j][lx + 2], a3 = sg[ly0 + j][lx + 3], a4 = sg[ly0 + j][lx + 4];
             ctr[j][0] = a1; ctr[j][1] = a2; ctr[j][2] = a3;
             hrow[j] = a0 + 4 * a1 + 6 * a2 + 4 * a3 + a4;
-        }
-        const size_t g0 = (size_t)(by * 32 + ly0) * T + bx * 32 + lx;
-        int pv[4]; uint8_t t3[4][3];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {                // every global load of the thread is issued before the first use
-            pv[k] = prev[g0 + (size_t)k * T];
-            const uint8_t* tp = tile + ((size_t)n * T * T + g0 + (size_t)k * T) * 3;
-            t3[k][0] = tp[0]; t3[k][1] = tp[1]; t3[k][2] = tp[2];
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -184,10 +201,6 @@ __global__ void __launch_bounds__(256) k_tile_stats(const uint8_t* __restrict__ 
             atomicOr(&shue[h >> 5], 1u << (h & 31));
         }
     } else {
-        const size_t g0 = (size_t)(by * 32 + ly0) * T + bx * 32 + lx;
-        int pv[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) pv[k] = prev[g0 + (size_t)k * T];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int ly = ly0 + k;
