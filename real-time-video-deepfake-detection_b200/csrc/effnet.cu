@@ -493,6 +493,28 @@ k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restric
     const int b0 = (blockIdx.x / SE_CL) * SE_CL;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Cs = C / SE_CL;                                   // every expanded width is a multiple of 8
+    // The FC weights are static: this warp's reduce-FC row and this thread's first 16 expand-FC weights are fetched BEFORE the
+    // programmatic-dependent-launch wait, i.e. while the producer of the squeeze partials is still running, which takes two of
+    // the kernel's dependent L2 round trips off its critical path.
+    float4 wr_pre[9];
+    {
+        const int j = rank + SE_CL * warp;
+        const float4* w4 = (const float4*)(Wr + (size_t)(j < se ? j : 0) * C);
+        const int n4 = C >> 2;
+#pragma unroll
+        for (int u = 0; u < 9; u++) { const int c4 = lane + 32 * u; wr_pre[u] = (j < se && c4 < n4) ? __ldg(w4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+    float wx_pre[16];
+    float bx_pre = 0.f;
+    if (tid < 2 * Cs) {
+        const int half = tid / Cs, c = rank * Cs + (tid - half * Cs);
+#pragma unroll
+        for (int u = 0; u < 16; u++) wx_pre[u] = u < se ? __ldg(WxT + (size_t)u * C + c) : 0.f;
+        bx_pre = bx[c];
+    } else {
+#pragma unroll
+        for (int u = 0; u < 16; u++) wx_pre[u] = 0.f;
+    }
     pdl_trigger();
     pdl_wait();
     float* mean_rem[SE_CL];
@@ -527,11 +549,8 @@ k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restric
     {
         const int j = rank + SE_CL * warp;
         if (j < se) {
-            const float4* w4 = (const float4*)(Wr + (size_t)j * C);
             const int n4 = C >> 2;
-            float4 w[9];
-#pragma unroll
-            for (int u = 0; u < 9; u++) { const int c4 = lane + 32 * u; w[u] = c4 < n4 ? __ldg(w4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f); }
+            const float4 (&w)[9] = wr_pre;
             float a[SE_CL];
 #pragma unroll
             for (int i = 0; i < SE_CL; i++) a[i] = 0.f;
@@ -563,13 +582,18 @@ k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restric
     for (int e = tid; e < 2 * Cs; e += 256) {                   // two threads per channel: images 0-3 / 4-7
         const int half = e / Cs, c = rank * Cs + (e - half * Cs);
         float a[4];
-        const float bc = bx[c];
+        const float bc = e == tid ? bx_pre : bx[c];
 #pragma unroll
         for (int i = 0; i < 4; i++) a[i] = bc;
         for (int j0 = 0; j0 < se; j0 += 16) {
             float w[16];
+            if (e == tid && j0 == 0) {
 #pragma unroll
-            for (int u = 0; u < 16; u++) w[u] = j0 + u < se ? __ldg(WxT + (size_t)(j0 + u) * C + c) : 0.f;
+                for (int u = 0; u < 16; u++) w[u] = wx_pre[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 16; u++) w[u] = j0 + u < se ? __ldg(WxT + (size_t)(j0 + u) * C + c) : 0.f;
+            }
 #pragma unroll
             for (int u = 0; u < 16; u++) {
                 if (j0 + u < se) {

@@ -235,45 +235,45 @@ __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict
         if (face160) *(uint32_t*)(face160 + ((size_t)m * 160 + r_first + r) * 480 + xw * 4) = pk;
     }
     // bilinear source columns / weights of the 224 output columns: computed once per CTA instead of once per output value
-    __shared__ float s_xw[224][2];
-    __shared__ uint16_t s_xi[224][2];
+    // (entry of column x at [(x % 8) * 28 + x / 8]: the lanes of a warp read column 8 * lane + px, i.e. consecutive entries)
+    __shared__ __align__(16) float4 s_xc[224];             // {w0, w1, bits(x0 * 3), bits(x1 * 3)}
     for (int x = threadIdx.x; x < 224; x += 512) {
         int x0, x1; float w0, w1;
         dfd_torch_bilinear_coef(x, 160, 224, &x0, &x1, &w0, &w1);
-        s_xi[x][0] = (uint16_t)(x0 * 3); s_xi[x][1] = (uint16_t)(x1 * 3);
-        s_xw[x][0] = w0; s_xw[x][1] = w1;
+        s_xc[(x & 7) * 28 + (x >> 3)] = make_float4(w0, w1, __int_as_float(x0 * 3), __int_as_float(x1 * 3));
     }
     __syncthreads();
-    // (x / 255 - mean) / std with both divisions as exact 3-instruction constant divisions (dfd_div_const)
+    // (x / 255 - mean) / std with both divisions as exact 3-instruction constant divisions (dfd_div_const).
+    // A thread produces 8 consecutive pixels of an output row (24 values: the channel of every value is a compile-time
+    // constant, so the normalisation constants are immediates) and stores them as 16-byte vectors.
     constexpr float R255 = 1.0f / 255.0f;
-    // a thread produces 8 consecutive values of an output row (672 = 84 x 8 per row) and stores them as 16-byte vectors
-    for (int o = threadIdx.x; o < 56 * 84; o += 512) {
-        const int yr = o / 84, v8 = o - yr * 84;
+    for (int o = threadIdx.x; o < 56 * 28; o += 512) {
+        const int yr = o / 28, g8 = o - yr * 28;
         const int y = band * 56 + yr;
         int y0, y1; float h0, h1;
         dfd_torch_bilinear_coef(y, 160, 224, &y0, &y1, &h0, &h1);
         const uint8_t* r0 = s160[y0 - r_first];
         const uint8_t* r1 = s160[y1 - r_first];
-        float v[8];
-        const int e0 = v8 * 8, xb = e0 / 3;
-        int c = e0 - xb * 3, x = xb;
-        int i0 = s_xi[x][0], i1 = s_xi[x][1]; float w0 = s_xw[x][0], w1 = s_xw[x][1];
+        OutT* dst = out + (((size_t)m * 224 + y) * 224 + g8 * 8) * 3;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float p00 = r0[i0 + c], p01 = r0[i1 + c], p10 = r1[i0 + c], p11 = r1[i1 + c];
-            float t = DFD_FADD(DFD_FMUL(h0, DFD_FADD(DFD_FMUL(w0, p00), DFD_FMUL(w1, p01))),
-                               DFD_FMUL(h1, DFD_FADD(DFD_FMUL(w0, p10), DFD_FMUL(w1, p11))));
-            t = dfd_div_const(t, 255.0f, R255);
-            const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
-            const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-            const float rs = c == 0 ? 1.0f / 0.229f : (c == 1 ? 1.0f / 0.224f : 1.0f / 0.225f);
-            v[j] = dfd_div_const(DFD_FSUB(t, mean), sd, rs);
-            if (++c == 3) {
-                c = 0; ++x;
-                if (j < 7) { i0 = s_xi[x][0]; i1 = s_xi[x][1]; w0 = s_xw[x][0]; w1 = s_xw[x][1]; }
+        for (int q = 0; q < 3; q++) {                      // 3 x 8 values
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = q * 8 + j, px = e / 3, c = e - px * 3;      // compile-time after unrolling
+                const float4 xc = s_xc[px * 28 + g8];
+                const int i0 = __float_as_int(xc.z) + c, i1 = __float_as_int(xc.w) + c;
+                const float p00 = r0[i0], p01 = r0[i1], p10 = r1[i0], p11 = r1[i1];
+                float t = DFD_FADD(DFD_FMUL(h0, DFD_FADD(DFD_FMUL(xc.x, p00), DFD_FMUL(xc.y, p01))),
+                                   DFD_FMUL(h1, DFD_FADD(DFD_FMUL(xc.x, p10), DFD_FMUL(xc.y, p11))));
+                t = dfd_div_const(t, 255.0f, R255);
+                const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+                const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+                const float rs = c == 0 ? 1.0f / 0.229f : (c == 1 ? 1.0f / 0.224f : 1.0f / 0.225f);
+                v[j] = dfd_div_const(DFD_FSUB(t, mean), sd, rs);
             }
+            store8<OutT>(dst + q * 8, v);
         }
-        store8<OutT>(out + (((size_t)m * 224 + y) * 224) * 3 + v8 * 8, v);
     }
 }
 
