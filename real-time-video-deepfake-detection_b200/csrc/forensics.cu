@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(1024, 2) k_canny(const uint8_t* __restrict__ g
 
 // ---------------------------------------------------------------------------------------------
 // ELA: JPEG Q90 4:2:0 round trip in shared memory; one CTA (512 threads) per frame.
-__global__ void __launch_bounds__(512) k_ela(const uint8_t* __restrict__ tile, const uint8_t* __restrict__ full,
+__global__ void __launch_bounds__(512, 2) k_ela(const uint8_t* __restrict__ tile, const uint8_t* __restrict__ full,
                                              DfdFramePartials* __restrict__ part, uint8_t* __restrict__ recon_out) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* Y = smem;                  // 256 x 256

@@ -381,11 +381,15 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
             for (int jb = split ? half : 0; jb < ((p.debug & 16) ? 0 : nblk64); jb += split ? 2 : 1, blk_count++) {
                 const uint32_t buf = my_staging + ((split || !p.epi_db) ? 0u : (blk_count & 1u) * STAGING_BLOCK_BYTES);
-                if (issuer) {                                      // this buffer's previous store has been read
-                    if (split || !p.epi_db) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                // One staging buffer: its previous store must have been read before anyone writes -> wait + barrier here.
+                // Two buffers (dbl): the issuer instead confirms, just BEFORE the barrier that ends a block, that the store issued
+                // one block earlier has been read; every thread that writes buffer b in block k has passed the barrier of block
+                // k - 1, which followed that confirmation for store k - 2 (the last user of b).  One barrier per block, not two.
+                const bool dbl = !split && p.epi_db;
+                if (!dbl) {
+                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    set_bar_sync(1 + grp);
                 }
-                set_bar_sync(1 + grp);
                 const int cols_here = min(64, p.n_pad - jb * 64);
                 for (int c32 = 0; c32 < cols_here; c32 += 32) {
                     uint32_t r[32];
@@ -448,6 +452,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
                 fence_async_smem();
+                if (dbl && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 set_bar_sync(1 + grp);
                 if (issuer) {
                     if (n_base + jb * 64 < p.N && !(p.debug & 1)) {
