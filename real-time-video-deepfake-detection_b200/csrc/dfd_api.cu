@@ -146,7 +146,7 @@ static int create_impl(dfd_ctx* ctx) {
     DFD_CUDA(cudaMalloc(&ctx->d_pool, nb * DFD_POOL_FLOATS * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_sescale, nb * 1152 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_se_r, nb * 64 * sizeof(float)));
-    DFD_CUDA(cudaMalloc(&ctx->d_wgated, nb * 40 * 240 * sizeof(__nv_bfloat16)));
+    DFD_CUDA(cudaMalloc(&ctx->d_wgated, nb * 112 * 672 * sizeof(__nv_bfloat16)));
     DFD_CUDA(cudaMalloc(&ctx->d_wgated_fold, nb * 32 * 64 * sizeof(__nv_bfloat16)));
     DFD_CUDA(cudaMemset(ctx->d_wgated_fold, 0, nb * 32 * 64 * sizeof(__nv_bfloat16)));
     DFD_CUDA(cudaMalloc(&ctx->d_feat, nb * 1280 * sizeof(float)));
@@ -180,6 +180,7 @@ int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
     ctx->no_fuse = getenv("DFD_NO_FUSE") != nullptr;
     ctx->pdl = getenv("DFD_NO_PDL") == nullptr;
     ctx->no_gated_w = getenv("DFD_NO_GATED_W") != nullptr;
+    if (const char* e = getenv("DFD_GATED_W_MAX")) { ctx->gated_w_max = atoi(e); if (ctx->gated_w_max > 10) ctx->gated_w_max = 10; }
     ctx->no_fold = getenv("DFD_NO_FOLD") != nullptr;
     if (getenv("DFD_SE_MODE")) ctx->se_mode = atoi(getenv("DFD_SE_MODE"));
     int rc = create_impl(ctx);

@@ -87,7 +87,7 @@ struct dfd_ctx {
     DfdBuf face_in;                       // prepared crops for analyze_batch
     float* d_pool = nullptr;              // [m][n_parts][C] SE squeeze partial sums (<= DFD_POOL_FLOATS per image)
     float* d_sescale = nullptr;           // [m][1152]
-    __nv_bfloat16* d_wgated = nullptr;    // [m][40][240] per-image SE-gated project weights of blocks 0-4
+    __nv_bfloat16* d_wgated = nullptr;    // [m][112][672] (sized for block 10) per-image SE-gated project weights of blocks 0-4
     __nv_bfloat16* d_wgated_fold = nullptr;   // [m][32][64] block 0: block-diagonal weights of the 2-pixel folded GEMM (off-diagonal zeros)
     float* d_bias_fold = nullptr;         // [32] block 0 project bias, repeated
     bool no_fold = false;                 // "no_fold": block 0 project GEMM with one pixel per row
@@ -119,6 +119,7 @@ struct dfd_ctx {
     bool trace = false;                   // DFD_TRACE=1: synchronise after every launch and log it (debugging)
     int se_mode = 2;                      // bf16 SE excite: 0 = k_se_reduce + k_se_expand, 1 = k_se_excite (CTA per 4 images), 2 = k_se_cluster (8-CTA clusters, DSMEM)
     bool pdl = true;                      // programmatic dependent launch between the tcgen05 / SE kernels (DFD_NO_PDL=1 or "pdl" option = 0 disables)
+    int gated_w_max = 4;                  // last block whose project conv uses per-image gated weights (DFD_GATED_W_MAX)
     bool no_gated_w = false;              // "no_gated_w": blocks 0-4 apply the SE gate to the A operand (A_SCALE) instead of per-image weights
     bool no_fuse = false;                 // DFD_NO_FUSE=1: expand GEMM + depthwise as two kernels (A/B testing of mbconv_fused.cu)
     bool no_overlap = false;              // DFD_NO_OVERLAP=1: run the forensic kernels on the caller's stream

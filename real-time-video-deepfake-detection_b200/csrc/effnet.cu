@@ -909,7 +909,8 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
         // blocks 0-4 (>= 784 rows per image): the SE gate is folded into per-image project weights by the SE kernel
-        const bool gated_w = BF && tc && i <= 4 && ctx->se_mode == 2 && !ctx->no_gated_w;
+        // (ctx->gated_w_max: last block that does so; 4 = the >= 784-row blocks, 10 = also the 14x14 stage)
+        const bool gated_w = BF && tc && i <= ctx->gated_w_max && ctx->se_mode == 2 && !ctx->no_gated_w;
         // block 0 (K = 32): two pixels per GEMM row, so the TMA moves full 128-byte rows (its row rate, not bytes, is the limit)
         const int fold = (gated_w && i == 0 && !ctx->no_fold) ? 2 : 1;
         __nv_bfloat16* wg_buf = fold > 1 ? ctx->d_wgated_fold : ctx->d_wgated;
