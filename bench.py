@@ -147,7 +147,7 @@ def run_reference(args):
         n += cpu_pipeline(fn[k % 3:k % 3 + 1], boxes[k % 3:k % 3 + 1], sd, cores)
     dt = time.perf_counter() - t0
     v = n / dt
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -159,7 +159,23 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def _emit(line):
+    """The ONE JSON line goes to the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries may print to file descriptor 1 (NCCL prints its version banner there when NCCL_DEBUG=VERSION is set in the
+    # environment): keep the real stdout for the JSON line and send everything else written to fd 1 to stderr.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -491,7 +507,7 @@ def main():
             "gpu_launches": int(launches), "crops_per_sec": value, "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu, "latency": latency, "other_configs": side, "top_kernels": functions[:6],
         }
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     eng.close()
