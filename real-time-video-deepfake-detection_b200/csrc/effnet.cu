@@ -613,17 +613,24 @@ k_se_cluster(const float* __restrict__ pool, int n_parts, const float* __restric
     // Wg[b][n][k] = bf16(Wp[n][k] * g[b][k]), so the project GEMM needs no pass over its A operand (gemm A_IMG)
     if (Wg) {
         __syncthreads();
-        for (int idx = tid; idx < SE_CL * N * Cs; idx += 256) {
-            const int cl = idx % Cs, t = idx / Cs, n = t % N, i = t / N;
-            if (b0 + i < m) {
-                const int k = rank * Cs + cl;
-                const __nv_bfloat16 w = __float2bfloat16_rn(Wp[(size_t)n * C + k] * gsm[i][cl]);
-                // fold > 1: `fold` consecutive pixels form one GEMM row (K' = fold * C, N' = fold * N) and the weight matrix is
-                // block-diagonal: copy f of W sits at rows f*N.., columns f*C.. (the off-diagonal blocks were zeroed once)
-                if (fold <= 1) Wg[((size_t)(b0 + i) * N + n) * C + k] = w;
-                else
-                    for (int fd = 0; fd < fold; fd++)
-                        Wg[((size_t)(b0 + i) * fold * N + fd * N + n) * (fold * C) + fd * C + k] = w;
+        // thread = one (output channel n, channel k of this CTA's slice): the weight is read once and gated for the 8 images
+        // (no per-element division: n = e / Cs by multiplication with a precomputed reciprocal, valid for e < 2^16)
+        const unsigned magic = 0xffffffffu / (unsigned)Cs + 1u;
+        for (int e = tid; e < N * Cs; e += 256) {
+            const int n = (int)__umulhi((unsigned)e, magic), cl = e - n * Cs;
+            const int k = rank * Cs + cl;
+            const float wv = __ldg(Wp + (size_t)n * C + k);
+#pragma unroll
+            for (int i = 0; i < SE_CL; i++) {
+                if (b0 + i < m) {
+                    const __nv_bfloat16 w = __float2bfloat16_rn(wv * gsm[i][cl]);
+                    // fold > 1: `fold` consecutive pixels form one GEMM row (K' = fold * C, N' = fold * N) and the weight matrix is
+                    // block-diagonal: copy f of W sits at rows f*N.., columns f*C.. (the off-diagonal blocks were zeroed once)
+                    if (fold <= 1) Wg[((size_t)(b0 + i) * N + n) * C + k] = w;
+                    else
+                        for (int fd = 0; fd < fold; fd++)
+                            Wg[((size_t)(b0 + i) * fold * N + fd * N + n) * (fold * C) + fd * C + k] = w;
+                }
             }
         }
     }
