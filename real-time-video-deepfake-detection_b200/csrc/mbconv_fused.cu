@@ -463,8 +463,8 @@ int dfd_mbconv_front_bf16(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const _
     const EffBlock& b = EFF_BLOCKS[blk];
 #define MF_ARGS ctx, blk, x, We, out, m, n_parts, st
     if (b.k == 3 && b.s == 2 && b.hin == 112) return launch_front<3, 2, 7, 8, 48, 112, false, 16, 2, 3>(MF_ARGS);      // 16 input channels: 32-byte operand rows
-    if (b.k == 3 && b.s == 1 && b.hin == 56) return launch_front<3, 1, 14, 14, 48, 56, false, 32, 4, 2>(MF_ARGS);    // 24 input channels: 64-byte operand rows
-    if (b.k == 5 && b.s == 2 && b.hin == 56) return launch_front<5, 2, 7, 7, 48, 56, false, 32, 4, 2>(MF_ARGS);
+    if (b.k == 3 && b.s == 1 && b.hin == 56) return launch_front<3, 1, 14, 14, 48, 56, false, 32, 2, 3>(MF_ARGS);    // 24 input channels: 64-byte operand rows, 3 CTAs/SM (-4 %)
+    if (b.k == 5 && b.s == 2 && b.hin == 56) return launch_front<5, 2, 7, 7, 48, 56, false, 32, 4, 2>(MF_ARGS);        // (3 CTAs/SM at 64 registers spills the 5x5 window: +17 %)
     // 64-wide chunks with 32-byte operand rows (40 / 80 input channels = 3 / 5 exact 16-channel k-blocks: no zero-filled
     // operand columns, which is what makes the wider patch fit two CTAs per SM)
     if (b.k == 5 && b.s == 1 && b.hin == 28) return launch_front<5, 1, 14, 14, 64, 28, false, 16>(MF_ARGS);
