@@ -169,6 +169,28 @@ def _emit(line):
     out.flush()
 
 
+def _bind_to_gpu_cpus(local):
+    """N > 1: run this rank on the CPUs NVML reports as local to its GPU, so the pinned host frames it allocates next land on
+    that GPU's NUMA node (four ranks copying from one node share that node's memory and PCIe root).  Best effort: returns the
+    CPU list, or None if NVML / the cpuset does not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (max(ncpu, 64) + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def main():
     # Libraries may print to file descriptor 1 (NCCL prints its version banner there when NCCL_DEBUG=VERSION is set in the
     # environment): keep the real stdout for the JSON line and send everything else written to fd 1 to stderr.
@@ -199,7 +221,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    numa = None
     if world > 1:
+        numa = _bind_to_gpu_cpus(local)      # before the pinned frame buffers are allocated (first touch decides their NUMA node)
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
@@ -503,7 +527,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(ms_e2e.item()) / K, "h2d_gbs_per_gpu": round(h2d / (float(ms_e2e.item()) / K) / 1e6, 1),
                     "note": "pinned host frames, H2D double-buffered on a copy stream; bound by the PCIe Gen5 x16 link "
-                            "(2.76 MB of raw frame per frame), not by the kernels"},
+                            "(2.76 MB of raw frame per frame), not by the kernels",
+                    "cpu_affinity": (f"rank 0 bound to the {len(numa)} CPUs local to its GPU" if numa else "unbound")},
             "gpu_launches": int(launches), "crops_per_sec": value, "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu, "latency": latency, "other_configs": side, "top_kernels": functions[:6],
         }
