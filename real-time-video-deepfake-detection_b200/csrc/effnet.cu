@@ -9,7 +9,8 @@
 //   k_se        SE excite: mean -> reduce FC -> swish -> expand FC -> sigmoid  (one CTA per image)
 //   k_scale     x * se (bf16 mode only; fp32 mode applies the scale while loading A in k_pw)
 //   k_pool      global average pool of the head output
-//   k_fc_layer  custom classifier 1280->512->256->1 (BN1d folded, ReLU): one launch per layer, 8 images per CTA
+//   k_fc_layer  custom classifier 1280->512->256->1 (BN1d folded, ReLU): one launch per layer, 16 images x 32 outputs per CTA
+//               at large batch (8 x 8 at small batch)
 //
 // Activations are float (fp32 mode: true fp32 FMA everywhere, parity 1e-4) or bf16 (storage only;
 // all accumulation in fp32).

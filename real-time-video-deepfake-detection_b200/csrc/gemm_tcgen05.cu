@@ -17,15 +17,17 @@
 //               A_SCALE) the A tile (128 x 64) into a multi-stage smem ring; out-of-bounds rows/columns are
 //               zero-filled by TMA so ragged M, K = 16..1152 and N = 16..256 need no padding copies.
 //   warps 12-19 two groups of 4 staging warps working on alternate k-blocks:
-//               A_SCALE: wait for the raw TMA tile, multiply it in place in shared memory by the SE gates
-//                        (ld.shared -> fp32 mul -> bf16 -> st.shared at the swizzled address), fence.proxy.async;
+//               A_SCALE: wait for the raw TMA tile, multiply it in place in shared memory by the SE gates (gates fetched
+//                        one k-block ahead, split into bf16 hi + lo and applied as fma(v, hi, v * lo) on packed bf16 pairs;
+//                        ld.shared -> 2 HFMA2.BF16 per pair -> st.shared at the swizzled address), fence.proxy.async;
 //               A_STEM:  gather the im2col row of each output pixel (15 aligned 4-byte loads) into the same
 //                        128-byte-swizzled K-major layout, fence.proxy.async.
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N, K=16) per K step
 //               from smem descriptors; tcgen05.commit frees the smem stage and publishes the accumulator.
 //   warp 2      allocates / frees TMEM (two accumulators of N fp32 columns).
 //   warps 4-7 / 8-11  two epilogue sets in ping-pong (set s owns accumulator s and the tiles of its parity):
-//               tcgen05.ld (32 lanes x 32 columns) -> + bias (smem), swish (one MUFU tanh), + residual -> bf16 ->
+//               tcgen05.ld (32 lanes x 32 columns) -> + bias (smem), swish (one MUFU tanh), + residual (prefetched one
+//               TMEM read ahead; the kernel is instantiated per <residual, swish, dense-store> variant) -> bf16 ->
 //               128-byte-swizzled smem staging (two 16 KB buffers per set) -> TMA tensor store of each
 //               64-column block (clips ragged M / N), so every global write is a full 128-byte line and the
 //               latency of one tile's epilogue hides behind the other set's.
