@@ -127,3 +127,15 @@ def test_numpy_order_reductions(hc):
         a = (rng.rand(n) * 10).astype(np.float32)
         assert hc.hc_np_mean(ptr(a), n) == np.mean(a)
         assert hc.hc_np_std(ptr(a), n) == np.std(a)
+
+
+def test_constant_division_is_exact(tmp_path):
+    """dfd_div_const (3-instruction division by 255 / the ImageNet std constants in k_vpass_up_norm) equals the IEEE
+    quotient: sampled run (every 97th float of the operand ranges) of the exhaustive checker; the full run is in its header."""
+    import subprocess
+    src = os.path.join(HERE, "hostcheck", "divconst_check.c")
+    exe = str(tmp_path / "divconst_check")
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", src, "-o", exe, "-lm"])
+    for which in "0123":
+        out = subprocess.run([exe, which, "97"], capture_output=True, text=True)
+        assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout
