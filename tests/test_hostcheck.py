@@ -55,7 +55,7 @@ def test_colour_conversions_exhaustive(hc):
         assert np.array_equal(dst, cv2.cvtColor(allc, code)), fn
 
 
-@pytest.mark.parametrize("shape", [(720, 1280), (1080, 1920), (480, 640), (120, 160), (333, 517), (256, 256), (97, 1001)])
+@pytest.mark.parametrize("shape", [(720, 1280), (1080, 1920), (2160, 3840), (480, 640), (120, 160), (333, 517), (256, 256), (97, 1001)])
 def test_cv_resize_256(hc, shape):
     rng = np.random.RandomState(shape[0])
     for fam in ("uniform", "pink"):
