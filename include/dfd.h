@@ -105,7 +105,8 @@ int dfd_load_weights(dfd_ctx* ctx, const float* blob_host, size_t n_floats);
  * deepfake_detection.py:504-515).  frames: n images of H x W BGR u8, image i at
  * frames + i*frame_stride, rows row_pitch bytes apart.  stream_ids[n], full[n]
  * (1 = analyze, 0 = analyze_fast) are device arrays.  A stream id may appear at
- * most once per call. */
+ * most once per call.  Preconditions checked on the device: a stream id outside [0, max_streams) touches no
+ * state and yields a record with frame_number = -1 and fake_probability = NaN (vote record: verdict = -1). */
 int dfd_forensics_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride,
                         int row_pitch, const int32_t* stream_ids, const uint8_t* full,
                         dfd_forensic_result* results, void* stream);
@@ -113,7 +114,12 @@ int dfd_forensics_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W
 /* preprocess_face_quality + _single_prediction preprocessing (deepfake_detection.py:357-389)
  * for m face boxes: crop -> LAB CLAHE -> RGB -> PIL-bilinear 160^2 -> bilinear 224^2 -> /255 ->
  * ImageNet normalise.  boxes[m*4] = x,y,w,h (device int32); frame_idx[m] selects the frame of each
- * box.  out: m x 224 x 224 x 3 (NHWC) of dtype. */
+ * box.  out: m x 224 x 224 x 3 (NHWC) of dtype.
+ * Boxes are clamped to the H x W frame exactly as the reference's numpy slicing frame[y:y+h, x:x+w] does
+ * (deepfake_detection.py:612-619).  A box that is empty after clamping, whose frame index is outside
+ * [0, n_frames) or whose clamped side exceeds max_crop is REJECTED: its output tensor is that of a dummy 8 x 8 crop and
+ * dfd_face_probability / dfd_analyze_batch report its probability as NaN ("no face": analyze_face -> (None, None, None),
+ * deepfake_detection.py:545-550).  Nothing is ever read outside the frames or written outside the workspaces. */
 int dfd_face_prep_batch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
                         int row_pitch, const int32_t* boxes, const int32_t* frame_idx, int m, void* out_nhwc,
                         int dtype, void* stream);
@@ -121,7 +127,8 @@ int dfd_face_prep_batch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H
 /* DeepfakeEfficientNet.forward (model.py:63-72): in m x 224 x 224 x 3 NHWC -> logits[m] (float32). */
 int dfd_effnet_forward(dfd_ctx* ctx, const void* in_nhwc, int m, int dtype, float* logits, void* stream);
 
-/* sigmoid + apply_heuristics (deepfake_detection.py:398,489-502): prob[i] = clip(sigmoid(logit) + 0.10*(w<80||h<80)). */
+/* sigmoid + apply_heuristics (deepfake_detection.py:398,489-502): prob[i] = clip(sigmoid(logit) + 0.10*(w<80||h<80)).
+ * When m equals the box count of the context's last dfd_face_prep_batch call, boxes that call rejected get NaN. */
 int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, void* stream);
 
 /* TemporalTracker.update for n streams (deepfake_detection.py:120-196).  vote_input[i] NaN = update(None).
@@ -190,7 +197,9 @@ int64_t dfd_dbg_activation(dfd_ctx* ctx, const char* name, float* out_dev, int64
 /* A/B switches for the parity tests: "no_fuse" (1 = run the expand 1x1 GEMM and the depthwise kernel separately
  * instead of the fused mbconv_fused.cu kernel), "se_mode" (bf16 SE excite: 0 = two kernels, 1 = one kernel, 2 = one kernel on 8-CTA clusters), "no_gated_w" (1 = blocks 0-4 gate the
  * project GEMM's A operand instead of using per-image gated weights), "pdl" (0 = no programmatic dependent launch),
- * "no_overlap" (1 = forensic kernels on the caller's stream). */
+ * "no_overlap" (1 = forensic kernels on the caller's stream).
+ * Threading / devices: one context per GPU; every entry point makes the context's device current for its duration and
+ * restores the caller's, so one process may drive several contexts on different GPUs (from one thread at a time each). */
 int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value);
 
 #ifdef __cplusplus

@@ -146,6 +146,39 @@ def _fold(sd, prefix, eps):
 
 
 @torch.no_grad()
+def block_bf16_storage(x, sd, i, gated_weight=False):
+    """One MBConv block of the bf16-storage restatement: x (bf16-representable fp32, NCHW) -> (block output, depthwise
+    output), both rounded where the CUDA bf16 path stores them.  Used by ``forward_bf16_storage`` and, fed with the CUDA
+    path's OWN previous-layer tap, by the per-block exactness test (which removes the network's error amplification from
+    the comparison: what is left is the kernels' own arithmetic)."""
+    k, st, cin, cexp, cout, se = BLOCKS[i]
+    p = f"net._blocks.{i}."
+    inp = x
+    if cexp != cin:
+        s, b = _fold(sd, p + "_bn0", BN_EPS)
+        w = _r(sd[p + "_expand_conv.weight"] * s.view(-1, 1, 1, 1))
+        x = _r(_swish(F.conv2d(x, w) + b.view(1, -1, 1, 1)))
+    s, b = _fold(sd, p + "_bn1", BN_EPS)
+    w = sd[p + "_depthwise_conv.weight"] * s.view(-1, 1, 1, 1)                 # fp32 weights on the CUDA cores
+    y = _swish(_conv_same(x, w, st, groups=cexp) + b.view(1, -1, 1, 1))       # fp32 before it is stored
+    sq = F.adaptive_avg_pool2d(y, 1)                                            # squeeze sums the unrounded values
+    sq = _swish(F.conv2d(sq, sd[p + "_se_reduce.weight"], sd[p + "_se_reduce.bias"]))
+    gate = torch.sigmoid(F.conv2d(sq, sd[p + "_se_expand.weight"], sd[p + "_se_expand.bias"]))
+    x = _r(y)
+    dw = x
+    s, b = _fold(sd, p + "_bn2", BN_EPS)
+    wp = (sd[p + "_project_conv.weight"] * s.view(-1, 1, 1, 1)).flatten(1)      # (cout, cexp)
+    if gated_weight:
+        wg = _r(wp.unsqueeze(0) * gate.flatten(1).unsqueeze(1))                 # (B, cout, cexp) per-image weights
+        x = torch.einsum("bchw,boc->bohw", x, wg) + b.view(1, -1, 1, 1)
+    else:
+        x = F.conv2d(_r(x * gate), _r(wp).view(cout, cexp, 1, 1)) + b.view(1, -1, 1, 1)
+    if st == 1 and cin == cout:
+        x = x + inp
+    return _r(x), dw
+
+
+@torch.no_grad()
 def forward_bf16_storage(x, sd, gated_weight_blocks=5):
     """The same network with every stored activation and every GEMM operand rounded to bfloat16 at exactly the points
     where the CUDA bf16 path rounds (fp32 accumulation, fp32 SE / pooling / classifier, BatchNorm folded into the
@@ -156,30 +189,8 @@ def forward_bf16_storage(x, sd, gated_weight_blocks=5):
     s, b = _fold(sd, "net._bn0", BN_EPS)
     w = _r(sd["net._conv_stem.weight"] * s.view(-1, 1, 1, 1))
     x = _r(_swish(_conv_same(x, w, 2) + b.view(1, -1, 1, 1)))
-    for i, (k, st, cin, cexp, cout, se) in enumerate(BLOCKS):
-        p = f"net._blocks.{i}."
-        inp = x
-        if cexp != cin:
-            s, b = _fold(sd, p + "_bn0", BN_EPS)
-            w = _r(sd[p + "_expand_conv.weight"] * s.view(-1, 1, 1, 1))
-            x = _r(_swish(F.conv2d(x, w) + b.view(1, -1, 1, 1)))
-        s, b = _fold(sd, p + "_bn1", BN_EPS)
-        w = sd[p + "_depthwise_conv.weight"] * s.view(-1, 1, 1, 1)                 # fp32 weights on the CUDA cores
-        y = _swish(_conv_same(x, w, st, groups=cexp) + b.view(1, -1, 1, 1))       # fp32 before it is stored
-        sq = F.adaptive_avg_pool2d(y, 1)                                            # squeeze sums the unrounded values
-        sq = _swish(F.conv2d(sq, sd[p + "_se_reduce.weight"], sd[p + "_se_reduce.bias"]))
-        gate = torch.sigmoid(F.conv2d(sq, sd[p + "_se_expand.weight"], sd[p + "_se_expand.bias"]))
-        x = _r(y)
-        s, b = _fold(sd, p + "_bn2", BN_EPS)
-        wp = (sd[p + "_project_conv.weight"] * s.view(-1, 1, 1, 1)).flatten(1)      # (cout, cexp)
-        if i < gated_weight_blocks:
-            wg = _r(wp.unsqueeze(0) * gate.flatten(1).unsqueeze(1))                 # (B, cout, cexp) per-image weights
-            x = torch.einsum("bchw,boc->bohw", x, wg) + b.view(1, -1, 1, 1)
-        else:
-            x = F.conv2d(_r(x * gate), _r(wp).view(cout, cexp, 1, 1)) + b.view(1, -1, 1, 1)
-        if st == 1 and cin == cout:
-            x = x + inp
-        x = _r(x)
+    for i in range(len(BLOCKS)):
+        x, _ = block_bf16_storage(x, sd, i, gated_weight=i < gated_weight_blocks)
     s, b = _fold(sd, "net._bn1", BN_EPS)
     w = _r(sd["net._conv_head.weight"] * s.view(-1, 1, 1, 1))
     x = _r(_swish(F.conv2d(x, w) + b.view(1, -1, 1, 1)))

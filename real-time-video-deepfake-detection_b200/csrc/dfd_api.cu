@@ -49,6 +49,7 @@ extern "C" {
 
 int dfd_profile_start(dfd_ctx* ctx, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     const size_t cap = 8192;
     if (ctx->prof_events.empty()) {
         ctx->prof_events.resize(cap);
@@ -65,6 +66,7 @@ int dfd_profile_start(dfd_ctx* ctx, void* stream) {
 // Stops profiling and writes "kernel:label,launches,total_ms" lines (sorted by first appearance) into buf.
 int dfd_profile_stop(dfd_ctx* ctx, char* buf, size_t buf_bytes, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     ctx->profiling = false;
     DFD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     std::vector<std::string> order;
@@ -143,6 +145,10 @@ static int create_impl(dfd_ctx* ctx) {
     DFD_CUDA(cudaMalloc(&ctx->d_pil, nb * 2 * 160 * (2 + 64) * sizeof(int)));
     DFD_CUDA(cudaMalloc(&ctx->d_hpass, nb * (size_t)c.max_crop * 480));
     DFD_CUDA(cudaMalloc(&ctx->d_face160, nb * 160 * 480));
+    DFD_CUDA(cudaMalloc(&ctx->d_boxes_ok, nb * 4 * sizeof(int32_t)));
+    DFD_CUDA(cudaMalloc(&ctx->d_fidx_ok, nb * sizeof(int32_t)));
+    DFD_CUDA(cudaMalloc(&ctx->d_box_bad, nb));
+    DFD_CUDA(cudaMemset(ctx->d_box_bad, 0, nb));
     DFD_CUDA(cudaMalloc(&ctx->d_pool, nb * DFD_POOL_FLOATS * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_sescale, nb * 1152 * sizeof(float)));
     DFD_CUDA(cudaMalloc(&ctx->d_se_r, nb * 64 * sizeof(float)));
@@ -191,8 +197,9 @@ int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
 
 void dfd_destroy(dfd_ctx* ctx) {
     if (!ctx) return;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     void* ptrs[] = {ctx->d_tables, ctx->d_twiddle, ctx->d_state, ctx->d_prev_gray, ctx->d_tile, ctx->d_gray, ctx->d_fft,
-                    ctx->d_part, ctx->d_fres, ctx->d_luts, ctx->d_pil, ctx->d_hpass, ctx->d_face160, ctx->d_wf32,
+                    ctx->d_part, ctx->d_fres, ctx->d_luts, ctx->d_pil, ctx->d_hpass, ctx->d_face160, ctx->d_boxes_ok, ctx->d_fidx_ok, ctx->d_box_bad, ctx->d_wf32,
                     ctx->d_wbf16, ctx->d_stem_wg, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
                     ctx->d_sescale, ctx->d_se_r, ctx->d_front_aux, ctx->d_wgated, ctx->d_wgated_fold, ctx->d_bias_fold, ctx->d_wxt, ctx->d_feat, ctx->d_fc_h1, ctx->d_fc_h2, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -209,6 +216,7 @@ size_t dfd_weights_blob_floats(void) { return dfd_effnet_blob_floats(); }
 
 int dfd_load_weights(dfd_ctx* ctx, const float* blob_host, size_t n_floats) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(blob_host != nullptr, DFD_ERR_INVALID, "load_weights: null blob");
     return dfd_effnet_upload(ctx, blob_host, n_floats);
 }
@@ -216,6 +224,7 @@ int dfd_load_weights(dfd_ctx* ctx, const float* blob_host, size_t n_floats) {
 int dfd_forensics_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, size_t frame_stride, int row_pitch,
                         const int32_t* stream_ids, const uint8_t* full, dfd_forensic_result* results, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(frames && stream_ids && full && results, DFD_ERR_INVALID, "forensics_batch: null pointer");
     return dfd_forensics_launch(ctx, frames, n, H, W, frame_stride, row_pitch, stream_ids, full, results, (cudaStream_t)stream);
 }
@@ -223,6 +232,7 @@ int dfd_forensics_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W
 int dfd_face_prep_batch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride, int row_pitch,
                         const int32_t* boxes, const int32_t* frame_idx, int m, void* out_nhwc, int dtype, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(frames && boxes && frame_idx && out_nhwc, DFD_ERR_INVALID, "face_prep_batch: null pointer");
     return dfd_faceprep_launch(ctx, frames, n_frames, H, W, frame_stride, row_pitch, boxes, frame_idx, m, out_nhwc, dtype,
                                (cudaStream_t)stream);
@@ -230,12 +240,14 @@ int dfd_face_prep_batch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H
 
 int dfd_effnet_forward(dfd_ctx* ctx, const void* in_nhwc, int m, int dtype, float* logits, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(in_nhwc && logits, DFD_ERR_INVALID, "effnet_forward: null pointer");
     return dfd_effnet_launch(ctx, in_nhwc, m, dtype, logits, (cudaStream_t)stream);
 }
 
 int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(logits && boxes && prob && m > 0, DFD_ERR_INVALID, "face_probability: bad argument");
     return dfd_faceprob_launch(ctx, logits, boxes, m, prob, (cudaStream_t)stream);
 }
@@ -243,6 +255,7 @@ int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes
 int dfd_vote_update(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
                     dfd_vote_record* records, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(stream_ids && vote_input && records && n > 0, DFD_ERR_INVALID, "vote_update: bad argument");
     return dfd_vote_launch(ctx, stream_ids, vote_input, np_flags, n, records, (cudaStream_t)stream);
 }
@@ -252,6 +265,7 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
                       int dtype, dfd_forensic_result* forensic_out, double* face_prob_out, dfd_vote_record* records,
                       void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(frames && stream_ids && full && records, DFD_ERR_INVALID, "analyze_batch: null pointer");
     DFD_REQUIRE(m == 0 || (boxes && box_frame), DFD_ERR_INVALID, "analyze_batch: boxes missing");
     cudaStream_t st = (cudaStream_t)stream;
@@ -273,7 +287,7 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
         if ((rc = dfd_ensure(ctx, ctx->face_in, (size_t)m * 224 * 224 * 3 * esz))) return rc;
         if ((rc = dfd_faceprep_launch(ctx, frames, n, H, W, frame_stride, row_pitch, boxes, box_frame, m, ctx->face_in.p, dtype, st))) return rc;
         if ((rc = dfd_effnet_launch(ctx, ctx->face_in.p, m, dtype, ctx->d_logits, st))) return rc;
-        if ((rc = dfd_faceprob_launch(ctx, ctx->d_logits, boxes, m, fprob, st))) return rc;
+        if ((rc = dfd_faceprob_launch(ctx, ctx->d_logits, ctx->d_boxes_ok, m, fprob, st))) return rc;   // heuristics see the clamped crop, as face_bgr.shape does
     }
     if (overlap) DFD_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     return dfd_select_vote_launch(ctx, n, m, box_frame, fprob, fres, stream_ids, records, st);
@@ -281,12 +295,14 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
 
 int dfd_reset_stream(dfd_ctx* ctx, int stream_id, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(stream_id < ctx->cfg.max_streams, DFD_ERR_CAPACITY, "reset_stream: id beyond max_streams");
     return dfd_reset_launch(ctx, stream_id, 3, (cudaStream_t)stream);
 }
 
 int dfd_reset_stream_part(dfd_ctx* ctx, int stream_id, int what, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(stream_id < ctx->cfg.max_streams, DFD_ERR_CAPACITY, "reset_stream: id beyond max_streams");
     DFD_REQUIRE(what >= 1 && what <= 3, DFD_ERR_INVALID, "reset_stream_part: what must be 1, 2 or 3");
     return dfd_reset_launch(ctx, stream_id, what, (cudaStream_t)stream);
@@ -295,6 +311,7 @@ int dfd_reset_stream_part(dfd_ctx* ctx, int stream_id, int what, void* stream) {
 int dfd_configure_stream(dfd_ctx* ctx, int stream_id, int window_size, int voting_window, double detection_threshold,
                          void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(stream_id < ctx->cfg.max_streams, DFD_ERR_CAPACITY, "configure_stream: id beyond max_streams");
     DFD_REQUIRE(window_size >= 10 && window_size <= DFD_MAX_SCORES, DFD_ERR_INVALID, "configure_stream: window_size must be 10..128");
     DFD_REQUIRE(voting_window >= 1 && voting_window <= DFD_MAX_VOTES, DFD_ERR_INVALID, "configure_stream: voting_window must be 1..64");
@@ -318,6 +335,7 @@ int64_t dfd_launch_count(dfd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 // ---- diagnostics ---------------------------------------------------------------------------------
 int dfd_dbg_tiles(dfd_ctx* ctx, uint8_t* tile_out, uint8_t* gray_out, int n, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(n > 0 && n <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "dbg_tiles: bad n");
     if (tile_out) DFD_CUDA(cudaMemcpyAsync(tile_out, ctx->d_tile, (size_t)n * 65536 * 3, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     if (gray_out) DFD_CUDA(cudaMemcpyAsync(gray_out, ctx->d_gray, (size_t)n * 65536, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -326,16 +344,19 @@ int dfd_dbg_tiles(dfd_ctx* ctx, uint8_t* tile_out, uint8_t* gray_out, int n, voi
 
 int dfd_dbg_jpeg_roundtrip(dfd_ctx* ctx, const uint8_t* tiles, uint8_t* out, int n, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     return dfd_dbg_jpeg_launch(ctx, tiles, out, n, (cudaStream_t)stream);
 }
 
 int dfd_dbg_canny(dfd_ctx* ctx, const uint8_t* gray, uint8_t* edges, int n, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     return dfd_dbg_canny_launch(ctx, gray, edges, n, (cudaStream_t)stream);
 }
 
 int dfd_dbg_face160(dfd_ctx* ctx, int i, uint8_t* out_dev, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(i >= 0 && i < ctx->cfg.max_batch, DFD_ERR_CAPACITY, "dbg_face160: bad index");
     DFD_CUDA(cudaMemcpyAsync(out_dev, ctx->d_face160 + (size_t)i * 160 * 480, 160 * 480, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return DFD_OK;
@@ -344,11 +365,13 @@ int dfd_dbg_face160(dfd_ctx* ctx, int i, uint8_t* out_dev, void* stream) {
 int dfd_dbg_face_clahe(dfd_ctx* ctx, const uint8_t* frames, int H, int W, size_t frame_stride, int row_pitch,
                        const int32_t* boxes, const int32_t* frame_idx, int i, uint8_t* out_dev, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     return dfd_dbg_clahe_launch(ctx, frames, frame_stride, row_pitch, boxes, frame_idx, i, out_dev, (cudaStream_t)stream);
 }
 
 int dfd_dbg_set_tap(dfd_ctx* ctx, const char* name) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     ctx->tap_name = name ? name : "";
     ctx->tap_elems = 0;
     return DFD_OK;
@@ -369,6 +392,7 @@ int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value) {
 
 int64_t dfd_dbg_activation(dfd_ctx* ctx, const char* name, float* out_dev, int64_t n_floats, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(name && ctx->tap_name == name && ctx->tap_elems > 0, DFD_ERR_INVALID,
                 "dbg_activation: call dfd_dbg_set_tap(name) before the forward pass");
     int64_t n = n_floats < ctx->tap_elems ? n_floats : ctx->tap_elems;

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <unordered_map>
 #include "../../include/dfd.h"
 #include "px_color.h"
 
@@ -77,6 +78,10 @@ struct dfd_ctx {
     int* d_pil = nullptr;                 // [m][2][160][2+KMAX]
     uint8_t* d_hpass = nullptr;           // [m][max_crop][160][3]
     uint8_t* d_face160 = nullptr;         // [m][160][160][3]
+    int32_t* d_boxes_ok = nullptr;        // [m][4] boxes clamped to the frame (k_box_sanitize)
+    int32_t* d_fidx_ok = nullptr;         // [m]
+    uint8_t* d_box_bad = nullptr;         // [m] 1 = box rejected (empty after clamping / larger than max_crop): probability NaN
+    int box_flags_m = 0;                  // number of boxes the flags describe (last face-prep call)
     // classifier
     bool has_weights = false;
     float* d_wf32 = nullptr;              // packed folded fp32 parameters
@@ -124,6 +129,9 @@ struct dfd_ctx {
     bool no_fuse = false;                 // DFD_NO_FUSE=1: expand GEMM + depthwise as two kernels (A/B testing of mbconv_fused.cu)
     bool no_overlap = false;              // DFD_NO_OVERLAP=1: run the forensic kernels on the caller's stream
     const char* label = "";               // set by the launch code before each kernel
+    // Function attributes (dynamic shared-memory limit, carve-out) are PER DEVICE: they are tracked per context, never in
+    // function-local statics, so a second context on another GPU of the same process sets them again for its device.
+    std::unordered_map<const void*, size_t> func_smem;
     std::vector<cudaEvent_t> prof_events;
     std::vector<std::string> prof_labels;
     size_t prof_used = 0;
@@ -162,6 +170,26 @@ void dfd_flight_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st);
     } while (0)
 
 int dfd_ensure(dfd_ctx* ctx, DfdBuf& b, size_t bytes);
+
+// Raises the kernel's dynamic shared-memory limit on this context's device to at least `bytes` (once per context and size).
+template <typename F>
+static inline int dfd_func_smem(dfd_ctx* ctx, F* fn, size_t bytes, bool full_carveout = false) {
+    size_t& have = ctx->func_smem[(const void*)fn];
+    if (bytes <= have) return DFD_OK;
+    DFD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (full_carveout) DFD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    have = bytes;
+    return DFD_OK;
+}
+
+// Makes the context's device current for the duration of a C entry point (a process may hold one context per GPU).
+struct DfdDeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DfdDeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DfdDeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 // Programmatic dependent launch (PDL): the kernel may become resident while its predecessor in the stream is still
 // draining, run its prologue (barrier init, TMEM allocation, descriptor prefetch, weight loads) and block in

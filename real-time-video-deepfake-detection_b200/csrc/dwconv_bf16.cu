@@ -144,11 +144,7 @@ static int launch(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, cons
     constexpr int PWP = (CC == 32 && (PW % 2 == 0)) ? PW + 1 : PW;
     constexpr int RW = 64 / CC;
     const size_t smem = (size_t)PH * PWP * CC * 2 + (size_t)K * K * CC * 4 + (size_t)DW_WARPS * RW * CC * 4;
-    static bool attr = false;
-    if (!attr) {
-        DFD_CUDA(cudaFuncSetAttribute(k_dw_tile<K, S, TW, TH, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    { int rc = dfd_func_smem(ctx, k_dw_tile<K, S, TW, TH, CC>, smem); if (rc) return rc; }
     const int tiles_x = (b.hout + TW - 1) / TW, tiles_y = (b.hout + TH - 1) / TH;
     dim3 grid(tiles_x * tiles_y, (b.cexp + CC - 1) / CC, m);
     *n_parts = tiles_x * tiles_y;

@@ -727,12 +727,8 @@ __global__ void __launch_bounds__(256) k_fc_layer(const float* __restrict__ in, 
 }
 
 template <int IN, int IPC, int JR>
-static int fc_launch(const float* in, const float* W, const float* bias, float* out, int J, int m, int relu, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(k_fc_layer<IN, IPC, JR>, cudaFuncAttributeMaxDynamicSharedMemorySize, IPC * IN * 4) != cudaSuccess) return DFD_ERR_CUDA;
-        attr = true;
-    }
+static int fc_launch(dfd_ctx* ctx, const float* in, const float* W, const float* bias, float* out, int J, int m, int relu, cudaStream_t st) {
+    { int rc = dfd_func_smem(ctx, k_fc_layer<IN, IPC, JR>, (size_t)IPC * IN * 4); if (rc) return rc; }
     k_fc_layer<IN, IPC, JR><<<dim3((J + 8 * JR - 1) / (8 * JR), (m + IPC - 1) / IPC), 256, IPC * IN * 4, st>>>(in, W, bias, out, J, m, relu);
     return DFD_OK;
 }
@@ -976,16 +972,16 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         ctx->label = "fc";
         {
             if (m >= 64) {
-                if ((rc = fc_launch<1280, 16, 4>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, ctx->d_fc_h1, 512, m, 1, st))) return rc;
+                if ((rc = fc_launch<1280, 16, 4>(ctx, ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, ctx->d_fc_h1, 512, m, 1, st))) return rc;
                 DFD_LAUNCH_CHECK("k_fc", st);
-                if ((rc = fc_launch<512, 16, 4>(ctx->d_fc_h1, Wf + o.fc2_w, Wf + o.fc2_b, ctx->d_fc_h2, 256, m, 1, st))) return rc;
+                if ((rc = fc_launch<512, 16, 4>(ctx, ctx->d_fc_h1, Wf + o.fc2_w, Wf + o.fc2_b, ctx->d_fc_h2, 256, m, 1, st))) return rc;
             } else {
-                if ((rc = fc_launch<1280, FC_IPC, 1>(ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, ctx->d_fc_h1, 512, m, 1, st))) return rc;
+                if ((rc = fc_launch<1280, FC_IPC, 1>(ctx, ctx->d_feat, Wf + o.fc1_w, Wf + o.fc1_b, ctx->d_fc_h1, 512, m, 1, st))) return rc;
                 DFD_LAUNCH_CHECK("k_fc", st);
-                if ((rc = fc_launch<512, FC_IPC, 1>(ctx->d_fc_h1, Wf + o.fc2_w, Wf + o.fc2_b, ctx->d_fc_h2, 256, m, 1, st))) return rc;
+                if ((rc = fc_launch<512, FC_IPC, 1>(ctx, ctx->d_fc_h1, Wf + o.fc2_w, Wf + o.fc2_b, ctx->d_fc_h2, 256, m, 1, st))) return rc;
             }
             DFD_LAUNCH_CHECK("k_fc", st);
-            if ((rc = fc_launch<256, FC_IPC, 1>(ctx->d_fc_h2, Wf + o.fc3_w, Wf + o.fc3_b, logits, 1, m, 0, st))) return rc;
+            if ((rc = fc_launch<256, FC_IPC, 1>(ctx, ctx->d_fc_h2, Wf + o.fc3_w, Wf + o.fc3_b, logits, 1, m, 0, st))) return rc;
         }
         DFD_LAUNCH_CHECK("k_fc", st);
         ctx->label = "";

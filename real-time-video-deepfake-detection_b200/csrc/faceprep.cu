@@ -277,23 +277,52 @@ __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict
     }
 }
 
+// Box sanitiser: the reference crops with numpy slicing (frame[y:y+h, x:x+w], deepfake_detection.py:612-619), which
+// clamps a box to the frame; a box that is empty after clamping gives `analyze_face` -> (None, None, None).  Here:
+// boxes are clamped to the H x W frame, frame indices to [0, n_frames); a box that is then empty, or whose side exceeds
+// max_crop (the workspaces are sized for it), is replaced by a harmless 8 x 8 box and FLAGGED: k_faceprob turns its
+// probability into NaN (= "no face" for the vote), so an oversized or out-of-frame box can never index out of bounds.
+__global__ void k_box_sanitize(const int32_t* __restrict__ boxes, const int32_t* __restrict__ frame_idx, int m, int n_frames,
+                               int H, int W, int max_crop, int32_t* __restrict__ boxes_ok, int32_t* __restrict__ fidx_ok,
+                               uint8_t* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int x = boxes[i * 4], y = boxes[i * 4 + 1], w = boxes[i * 4 + 2], h = boxes[i * 4 + 3];
+    int f = frame_idx[i];
+    bool is_bad = f < 0 || f >= n_frames || w <= 0 || h <= 0;
+    long long x1 = (long long)x + w, y1 = (long long)y + h;
+    if (x < 0) x = 0;
+    if (y < 0) y = 0;
+    if (x1 > W) x1 = W;
+    if (y1 > H) y1 = H;
+    w = (int)(x1 - x); h = (int)(y1 - y);
+    is_bad = is_bad || w <= 0 || h <= 0 || w > max_crop || h > max_crop;
+    if (is_bad) { x = 0; y = 0; w = W < 8 ? W : 8; h = H < 8 ? H : 8; f = f < 0 || f >= n_frames ? 0 : f; }
+    boxes_ok[i * 4] = x; boxes_ok[i * 4 + 1] = y; boxes_ok[i * 4 + 2] = w; boxes_ok[i * 4 + 3] = h;
+    fidx_ok[i] = f;
+    bad[i] = is_bad ? 1 : 0;
+}
+
 int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
-                        int row_pitch, const int32_t* boxes, const int32_t* frame_idx, int m, void* out, int dtype,
+                        int row_pitch, const int32_t* boxes_in, const int32_t* frame_idx_in, int m, void* out, int dtype,
                         cudaStream_t st) {
     DFD_REQUIRE(m > 0 && m <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "face_prep: box count exceeds max_batch");
     DFD_REQUIRE(dtype == DFD_F32 || dtype == DFD_BF16, DFD_ERR_INVALID, "face_prep: bad dtype");
+    DFD_REQUIRE(n_frames > 0 && H >= 1 && W >= 1 && row_pitch >= 3 * W, DFD_ERR_INVALID, "face_prep: bad frame geometry");
     const int mc = ctx->cfg.max_crop;
+    k_box_sanitize<<<(m + 127) / 128, 128, 0, st>>>(boxes_in, frame_idx_in, m, n_frames, H, W, mc, ctx->d_boxes_ok, ctx->d_fidx_ok,
+                                                    ctx->d_box_bad);
+    DFD_LAUNCH_CHECK("k_box_sanitize", st);
+    ctx->box_flags_m = m;
+    const int32_t* boxes = ctx->d_boxes_ok;
+    const int32_t* frame_idx = ctx->d_fidx_ok;
     k_pil_coeffs<<<m, 320, 0, st>>>(boxes, ctx->d_pil);
     DFD_LAUNCH_CHECK("k_pil_coeffs", st);
     const int lut_warps = m >= 16 ? 8 : 2;
     k_clahe_lut<<<dim3(64 / lut_warps, m), 32 * lut_warps, 0, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx, ctx->d_tables, ctx->d_luts);
     DFD_LAUNCH_CHECK("k_clahe_lut", st);
     const size_t hp_smem = sizeof(DfdColorTables) + 64 * 256 + 160 * (2 + DFD_PIL_KMAX_STAGED) * sizeof(int) + (size_t)8 * ((mc * 3 + 8 + 15) & ~15);
-    static size_t hp_attr = 0;
-    if (hp_smem > hp_attr) {
-        DFD_CUDA(cudaFuncSetAttribute(k_clahe_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem));
-        hp_attr = hp_smem;
-    }
+    { int rc = dfd_func_smem(ctx, k_clahe_hpass, hp_smem); if (rc) return rc; }
     const int hp_rows = m >= 16 ? HP_ROWS : 8;
     k_clahe_hpass<<<dim3((mc + hp_rows - 1) / hp_rows, m), 256, hp_smem, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx,
                                                                                ctx->d_tables, ctx->d_luts, ctx->d_pil, ctx->d_hpass, mc,
@@ -313,8 +342,10 @@ int dfd_dbg_clahe_launch(dfd_ctx* ctx, const uint8_t* frames, size_t frame_strid
     // luts of the last dfd_face_prep_batch call are reused; only box i is written
     const int mc = ctx->cfg.max_crop;
     const size_t hp_smem = sizeof(DfdColorTables) + 64 * 256 + 160 * (2 + DFD_PIL_KMAX_STAGED) * sizeof(int) + (size_t)8 * ((mc * 3 + 8 + 15) & ~15);
-    DFD_CUDA(cudaFuncSetAttribute(k_clahe_hpass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem));
-    k_clahe_hpass<<<dim3((mc + HP_ROWS - 1) / HP_ROWS, i + 1), 256, hp_smem, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx,
+    { int rc = dfd_func_smem(ctx, k_clahe_hpass, hp_smem); if (rc) return rc; }
+    // (the sanitised boxes of that call are used as well: see k_box_sanitize)
+    (void)boxes; (void)frame_idx;
+    k_clahe_hpass<<<dim3((mc + HP_ROWS - 1) / HP_ROWS, i + 1), 256, hp_smem, st>>>(frames, frame_stride, row_pitch, ctx->d_boxes_ok, ctx->d_fidx_ok,
                                                                                    ctx->d_tables, ctx->d_luts, ctx->d_pil, nullptr, mc, out, i, HP_ROWS);
     DFD_LAUNCH_CHECK("k_clahe_hpass", st);
     return DFD_OK;

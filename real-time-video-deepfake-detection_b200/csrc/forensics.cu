@@ -125,11 +125,12 @@ __global__ void __launch_bounds__(256, 6) k_tile_stats(const uint8_t* __restrict
                                                     const int32_t* __restrict__ stream_ids,
                                                     const uint8_t* __restrict__ full, const DfdColorTables* __restrict__ tab,
                                                     const DfdStreamState* __restrict__ state, uint8_t* __restrict__ prev_gray,
-                                                    DfdFramePartials* __restrict__ part) {
+                                                    DfdFramePartials* __restrict__ part, int max_streams) {
     const int n = blockIdx.y, blk = blockIdx.x;
     const int by = blk >> 3, bx = blk & 7;
     const bool is_full = full[n] != 0;
-    const int sid = stream_ids[n];
+    // an id outside [0, max_streams) is a caller error: k_finalize flags the record; here it must only not fault
+    const int sid = min(max(stream_ids[n], 0), max_streams - 1);
     __shared__ uint8_t sg[36][40];
     __shared__ int wpart[8][12];
     __shared__ unsigned int shue[6];
@@ -558,133 +559,231 @@ __global__ void __launch_bounds__(128) k_fft_cols(const float2* __restrict__ in,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Score tables + state update; one thread per frame.
+// Score tables + state update; one WARP per frame (8 frames per CTA).  The 64-block / 30-entry statistics are computed
+// lane-parallel, the float32 means / stds in NumPy's exact pairwise order (px_numpy.h): lanes 0-7 carry the eight partial
+// sums r[j] of the unrolled loop, lane 0 combines them ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and adds the tail.  Lane 0 owns
+// the thresholds, the per-stream ring and the weighted sum.  (One thread per frame walked every 64-element loop
+// serially with fp64 sqrt / div in it: 105 us per step on 4 CTAs.)
 __device__ double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
 
-__global__ void k_finalize(int n, const int32_t* __restrict__ stream_ids, const uint8_t* __restrict__ full,
-                           const DfdFramePartials* __restrict__ part, DfdStreamState* __restrict__ state,
-                           dfd_forensic_result* __restrict__ results) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+#define FIN_WARPS 8
+
+// np.sum of a float32 array a[0..n) (n <= 64) held in shared memory; result valid in every lane
+__device__ float warp_np_sum_f32(const float* a, int n, int lane) {
+    float res;
+    if (n < 8) {
+        res = 0.f;
+        if (lane == 0) for (int i = 0; i < n; i++) res = __fadd_rn(res, a[i]);
+    } else {
+        const int n8 = n - (n % 8);
+        float r = 0.f;
+        if (lane < 8) {
+            r = a[lane];
+            for (int i = 8 + lane; i < n8; i += 8) r = __fadd_rn(r, a[i]);
+        }
+        const float r1 = __shfl_down_sync(0xffffffffu, r, 1);
+        const float s01 = __fadd_rn(r, r1);                                    // lanes 0,2,4,6: r[j] + r[j+1]
+        const float s23 = __shfl_down_sync(0xffffffffu, s01, 2);
+        const float q = __fadd_rn(s01, s23);                                   // lanes 0,4: (r0+r1)+(r2+r3), (r4+r5)+(r6+r7)
+        const float q4 = __shfl_down_sync(0xffffffffu, q, 4);
+        res = __fadd_rn(q, q4);
+        if (lane == 0) for (int i = n8; i < n; i++) res = __fadd_rn(res, a[i]);
+    }
+    return __shfl_sync(0xffffffffu, res, 0);
+}
+__device__ float warp_np_mean_f32(const float* a, int n, int lane) { return __fdiv_rn(warp_np_sum_f32(a, n, lane), (float)n); }
+// np.std (population); tmp: n floats of scratch in shared memory
+__device__ float warp_np_std_f32(const float* a, int n, float* tmp, int lane) {
+    const float mean = warp_np_mean_f32(a, n, lane);
+    for (int i = lane; i < n; i += 32) { const float d = __fsub_rn(a[i], mean); tmp[i] = __fmul_rn(d, d); }
+    __syncwarp();
+    const float s = warp_np_sum_f32(tmp, n, lane);
+    __syncwarp();
+    return __fsqrt_rn(__fdiv_rn(s, (float)n));
+}
+template <typename V> __device__ __forceinline__ V warp_isum(V v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(32 * FIN_WARPS)
+k_finalize(int n, int max_streams, const int32_t* __restrict__ stream_ids, const uint8_t* __restrict__ full,
+           const DfdFramePartials* __restrict__ part, DfdStreamState* __restrict__ state,
+           dfd_forensic_result* __restrict__ results) {
+    __shared__ float s_a[FIN_WARPS][DFD_NBLK], s_b[FIN_WARPS][DFD_NBLK];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * FIN_WARPS + w;
     if (i >= n) return;
     const DfdFramePartials& P = part[i];
-    DfdStreamState& S = state[stream_ids[i]];
-    dfd_forensic_result R;
+    const int sid = stream_ids[i];
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    float* tmp = s_a[w];
+    float* tmp2 = s_b[w];
+    dfd_forensic_result R;                                      // assembled by lane 0
     for (int k = 0; k < DFD_N_RAW; k++) R.raw[k] = NaN;
     for (int k = 0; k < DFD_N_SIGNALS; k++) R.scores[k] = NaN;
+    if ((unsigned)sid >= (unsigned)max_streams) {               // caller error: no state is touched, the record says so
+        if (lane == 0) { R.fake_probability = NaN; R.frame_number = -1; R.full = 0; results[i] = R; }
+        return;
+    }
+    DfdStreamState& S = state[sid];
     const bool is_full = full[i] != 0;
-    S.analyzer_frames += 1;                                     // frame_analysis.py:68,110
-    R.frame_number = S.analyzer_frames;
+    int frames_now = S.analyzer_frames + 1;                     // frame_analysis.py:68,110
+    R.frame_number = frames_now;
     R.full = is_full ? 1 : 0;
 
-    // ---- frequency (frame_analysis.py:150-180) ----
+    // ---- frequency (frame_analysis.py:150-180): lane k sums column k of the 17 group partials in group order ----
     {
-        double a[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int g = 0; g < DFD_FFT_GROUPS; g++)
-            for (int k = 0; k < 7; k++) a[k] += P.fft[g][k];
-        float low = (float)(a[0] / a[4]), mid = (float)(a[1] / a[5]), high = (float)(a[3] / a[6]);
-        float total = __fadd_rn(__fadd_rn(__fadd_rn(low, mid), high), 1e-10f);
-        float hr = __fdiv_rn(high, total), mr = __fdiv_rn(mid, total);
-        double mmean = a[1] / a[5];
-        double var = a[2] / a[5] - mmean * mmean;
-        float mstd = (float)sqrt(var > 0 ? var : 0.0);
-        float mcv = __fdiv_rn(mstd, __fadd_rn(mid, 1e-10f));
-        R.raw[0] = hr; R.raw[1] = mr; R.raw[2] = mcv;
-        double s = 0.0;
-        if (hr < 0.18f) s += 0.4; else if (hr < 0.22f) s += 0.2;
-        if (mcv > 0.6f) s += 0.25; else if (mcv > 0.45f) s += 0.1;
-        if (mr > 0.45f && hr < 0.2f) s += 0.15;
-        R.scores[0] = clip01(s);
+        double a = 0.0;
+        if (lane < 7) for (int g = 0; g < DFD_FFT_GROUPS; g++) a += P.fft[g][lane];
+        const double a0 = __shfl_sync(0xffffffffu, a, 0), a1 = __shfl_sync(0xffffffffu, a, 1), a2 = __shfl_sync(0xffffffffu, a, 2);
+        const double a3 = __shfl_sync(0xffffffffu, a, 3), a4 = __shfl_sync(0xffffffffu, a, 4), a5 = __shfl_sync(0xffffffffu, a, 5);
+        const double a6 = __shfl_sync(0xffffffffu, a, 6);
+        if (lane == 0) {
+            float low = (float)(a0 / a4), mid = (float)(a1 / a5), high = (float)(a3 / a6);
+            float total = __fadd_rn(__fadd_rn(__fadd_rn(low, mid), high), 1e-10f);
+            float hr = __fdiv_rn(high, total), mr = __fdiv_rn(mid, total);
+            double mmean = a1 / a5;
+            double var = a2 / a5 - mmean * mmean;
+            float mstd = (float)sqrt(var > 0 ? var : 0.0);
+            float mcv = __fdiv_rn(mstd, __fadd_rn(mid, 1e-10f));
+            R.raw[0] = hr; R.raw[1] = mr; R.raw[2] = mcv;
+            double s = 0.0;
+            if (hr < 0.18f) s += 0.4; else if (hr < 0.22f) s += 0.2;
+            if (mcv > 0.6f) s += 0.25; else if (mcv > 0.45f) s += 0.1;
+            if (mr > 0.45f && hr < 0.2f) s += 0.15;
+            R.scores[0] = clip01(s);
+        }
     }
-    float tmp[DFD_NBLK], tmp2[DFD_NBLK];
     if (is_full) {
         // ---- noise (:194-225) ----
-        for (int b = 0; b < DFD_NBLK; b++) {
+        for (int b = lane; b < DFD_NBLK; b += 32) {
             double sx = (double)P.noise_sx[b], sxx = (double)P.noise_sxx[b];
             double var = (sxx - sx * sx / 1024.0) / 1024.0;
             tmp[b] = (float)(sqrt(var > 0 ? var : 0.0) / 256.0);
         }
-        float mean_noise = dfd_np_mean_f32(tmp, DFD_NBLK);
-        float ncv = __fdiv_rn(dfd_np_std_f32(tmp, DFD_NBLK, tmp2), __fadd_rn(mean_noise, 1e-10f));
-        R.raw[3] = ncv; R.raw[4] = mean_noise;
-        double s = 0.0;
-        if (ncv > 0.7f) s += 0.5; else if (ncv > 0.5f) s += 0.25;
-        if (mean_noise < 1.0f) s += 0.3; else if (mean_noise < 2.0f) s += 0.1;
-        R.scores[1] = clip01(s);
+        __syncwarp();
+        float mean_noise = warp_np_mean_f32(tmp, DFD_NBLK, lane);
+        float ncv = __fdiv_rn(warp_np_std_f32(tmp, DFD_NBLK, tmp2, lane), __fadd_rn(mean_noise, 1e-10f));
+        if (lane == 0) {
+            R.raw[3] = ncv; R.raw[4] = mean_noise;
+            double s = 0.0;
+            if (ncv > 0.7f) s += 0.5; else if (ncv > 0.5f) s += 0.25;
+            if (mean_noise < 1.0f) s += 0.3; else if (mean_noise < 2.0f) s += 0.1;
+            R.scores[1] = clip01(s);
+        }
+        __syncwarp();
         // ---- ELA (:245-276) ----
-        for (int b = 0; b < DFD_NBLK; b++) tmp[b] = __fdiv_rn((float)P.ela_sum[b], 1024.0f);
-        float emean = dfd_np_mean_f32(tmp, DFD_NBLK);
-        float ecv = __fdiv_rn(dfd_np_std_f32(tmp, DFD_NBLK, tmp2), __fadd_rn(emean, 1e-10f));
-        R.raw[5] = ecv; R.raw[6] = emean;
-        s = 0.0;
-        if (ecv > 0.9f) s += 0.5; else if (ecv > 0.6f) s += 0.2;
-        if (emean > 15.0f) s += 0.2; else if (emean > 10.0f) s += 0.1;
-        R.scores[2] = clip01(s);
+        for (int b = lane; b < DFD_NBLK; b += 32) tmp[b] = __fdiv_rn((float)P.ela_sum[b], 1024.0f);
+        __syncwarp();
+        float emean = warp_np_mean_f32(tmp, DFD_NBLK, lane);
+        float ecv = __fdiv_rn(warp_np_std_f32(tmp, DFD_NBLK, tmp2, lane), __fadd_rn(emean, 1e-10f));
+        if (lane == 0) {
+            R.raw[5] = ecv; R.raw[6] = emean;
+            double s = 0.0;
+            if (ecv > 0.9f) s += 0.5; else if (ecv > 0.6f) s += 0.2;
+            if (emean > 15.0f) s += 0.2; else if (emean > 10.0f) s += 0.1;
+            R.scores[2] = clip01(s);
+        }
+        __syncwarp();
     }
-    // ---- edges (:288-309) ----
+    // ---- edges (:288-309): exact integer sums, any order ----
     {
-        double density = (double)P.canny_count / 65536.0;
         long long ls = 0, lss = 0;
-        for (int b = 0; b < DFD_NBLK; b++) { ls += P.lap_s[b]; lss += P.lap_ss[b]; }
-        double mean = (double)ls / 65536.0;
-        double var = (double)lss / 65536.0 - mean * mean;
-        R.raw[7] = density; R.raw[8] = var;
-        double s = 0.0;
-        if (density < 0.02) s += 0.35; else if (density < 0.04) s += 0.15;
-        if (var < 50.0) s += 0.3; else if (var < 100.0) s += 0.1;
-        R.scores[3] = clip01(s);
+        for (int b = lane; b < DFD_NBLK; b += 32) { ls += P.lap_s[b]; lss += P.lap_ss[b]; }
+        ls = warp_isum(ls); lss = warp_isum(lss);
+        if (lane == 0) {
+            double density = (double)P.canny_count / 65536.0;
+            double mean = (double)ls / 65536.0;
+            double var = (double)lss / 65536.0 - mean * mean;
+            R.raw[7] = density; R.raw[8] = var;
+            double s = 0.0;
+            if (density < 0.02) s += 0.35; else if (density < 0.04) s += 0.15;
+            if (var < 50.0) s += 0.3; else if (var < 100.0) s += 0.1;
+            R.scores[3] = clip01(s);
+        }
     }
     if (is_full) {
         // ---- colour (:318-347) ----
         unsigned long long ss = 0, sss = 0, vs = 0, vss = 0;
         unsigned int hb[6] = {0, 0, 0, 0, 0, 0};
-        for (int b = 0; b < DFD_NBLK; b++) {
+        for (int b = lane; b < DFD_NBLK; b += 32) {
             ss += P.sat_s[b]; sss += P.sat_ss[b]; vs += P.val_s[b]; vss += P.val_ss[b];
+#pragma unroll
             for (int k = 0; k < 6; k++) hb[k] |= P.hue_bits[b][k];
         }
-        double sm = (double)ss / 65536.0, vm = (double)vs / 65536.0;
-        double svar = (double)sss / 65536.0 - sm * sm, vvar = (double)vss / 65536.0 - vm * vm;
-        float sstd = (float)sqrt(svar > 0 ? svar : 0.0), vstd = (float)sqrt(vvar > 0 ? vvar : 0.0);
-        int hues = 0;
-        for (int k = 0; k < 6; k++) hues += __popc(hb[k]);
-        R.raw[9] = sstd; R.raw[10] = vstd; R.raw[11] = hues;
-        double s = 0.0;
-        if (sstd < 15.0f) s += 0.3; else if (sstd < 25.0f) s += 0.1;
-        if (vstd < 15.0f) s += 0.25; else if (vstd < 25.0f) s += 0.1;
-        if (hues < 30) s += 0.25; else if (hues < 50) s += 0.1;
-        R.scores[4] = clip01(s);
+        ss = warp_isum(ss); sss = warp_isum(sss); vs = warp_isum(vs); vss = warp_isum(vss);
+#pragma unroll
+        for (int k = 0; k < 6; k++) hb[k] = __reduce_or_sync(0xffffffffu, hb[k]);
+        if (lane == 0) {
+            double sm = (double)ss / 65536.0, vm = (double)vs / 65536.0;
+            double svar = (double)sss / 65536.0 - sm * sm, vvar = (double)vss / 65536.0 - vm * vm;
+            float sstd = (float)sqrt(svar > 0 ? svar : 0.0), vstd = (float)sqrt(vvar > 0 ? vvar : 0.0);
+            int hues = 0;
+            for (int k = 0; k < 6; k++) hues += __popc(hb[k]);
+            R.raw[9] = sstd; R.raw[10] = vstd; R.raw[11] = hues;
+            double s = 0.0;
+            if (sstd < 15.0f) s += 0.3; else if (sstd < 25.0f) s += 0.1;
+            if (vstd < 15.0f) s += 0.25; else if (vstd < 25.0f) s += 0.1;
+            if (hues < 30) s += 0.25; else if (hues < 50) s += 0.1;
+            R.scores[4] = clip01(s);
+        }
     }
     // ---- temporal (:356-389) ----
     {
         double s = 0.0;
-        if (!S.has_prev) {
-            S.has_prev = 1;
-            R.raw[14] = 0;
-        } else {
-            int td = 0;
-            for (int b = 0; b < DFD_NBLK; b++) td += P.tdiff[b];
-            float mean_diff = __fdiv_rn((float)td, 65536.0f);       // exact: integer sum < 2^24
-            if (S.ring_n < DFD_RING) { S.ring[(S.ring_head + S.ring_n) % DFD_RING] = mean_diff; S.ring_n++; }
-            else { S.ring[S.ring_head] = mean_diff; S.ring_head = (S.ring_head + 1) % DFD_RING; }
-            R.raw[13] = mean_diff; R.raw[14] = S.ring_n;
-            if (S.ring_n >= 5) {
-                for (int k = 0; k < S.ring_n; k++) tmp[k] = S.ring[(S.ring_head + k) % DFD_RING];
-                float md = dfd_np_mean_f32(tmp, S.ring_n);
-                float cv = __fdiv_rn(dfd_np_std_f32(tmp, S.ring_n, tmp2), __fadd_rn(md, 1e-10f));
-                R.raw[12] = cv;
-                if (cv > 1.5f) s += 0.4; else if (cv > 1.0f) s += 0.2;
-                if (mean_diff < 0.3f && S.analyzer_frames > 10) s += 0.3;
-                else if (mean_diff < 0.8f && S.analyzer_frames > 10) s += 0.1;
+        const int has_prev = S.has_prev;
+        int td = 0;
+        for (int b = lane; b < DFD_NBLK; b += 32) td += P.tdiff[b];
+        td = warp_isum(td);
+        int ring_n = S.ring_n, ring_head = S.ring_head;
+        const float mean_diff = __fdiv_rn((float)td, 65536.0f);       // exact: integer sum < 2^24
+        if (has_prev) {
+            if (lane == 0) {
+                if (ring_n < DFD_RING) S.ring[(ring_head + ring_n) % DFD_RING] = mean_diff;
+                else S.ring[ring_head] = mean_diff;
             }
+            if (ring_n < DFD_RING) ring_n++; else ring_head = (ring_head + 1) % DFD_RING;
+            __syncwarp();
         }
-        R.scores[5] = clip01(s);
+        float cv = 0.f;
+        if (has_prev && ring_n >= 5) {
+            if (lane < ring_n) tmp[lane] = S.ring[(ring_head + lane) % DFD_RING];
+            __syncwarp();
+            const float md = warp_np_mean_f32(tmp, ring_n, lane);
+            cv = __fdiv_rn(warp_np_std_f32(tmp, ring_n, tmp2, lane), __fadd_rn(md, 1e-10f));
+        }
+        if (lane == 0) {
+            if (!has_prev) {
+                S.has_prev = 1;
+                R.raw[14] = 0;
+            } else {
+                S.ring_n = ring_n; S.ring_head = ring_head;
+                R.raw[13] = mean_diff; R.raw[14] = ring_n;
+                if (ring_n >= 5) {
+                    R.raw[12] = cv;
+                    if (cv > 1.5f) s += 0.4; else if (cv > 1.0f) s += 0.2;
+                    if (mean_diff < 0.3f && frames_now > 10) s += 0.3;
+                    else if (mean_diff < 0.8f && frames_now > 10) s += 0.1;
+                }
+            }
+            S.analyzer_frames = frames_now;
+            R.scores[5] = clip01(s);
+        }
     }
-    // ---- weighted sum in the reference's dict order, Python float arithmetic (:94,119) ----
-    double c = 0.0;
-#define ACC(si, w) c = __dadd_rn(c, __dmul_rn(R.scores[si], w))      /* no FMA: Python rounds the product */
-    if (is_full) { ACC(0, 0.25); ACC(1, 0.20); ACC(2, 0.20); ACC(3, 0.15); ACC(4, 0.10); ACC(5, 0.10); }
-    else { ACC(0, 0.45); ACC(5, 0.25); ACC(3, 0.30); }
-#undef ACC
+    if (lane != 0) return;
+    // ---- weighted sum in the reference's dict order with Python's compensated sum() (:94,119) ----
+    double c;
+    if (is_full) {
+        const double sc[6] = {R.scores[0], R.scores[1], R.scores[2], R.scores[3], R.scores[4], R.scores[5]};
+        const double wt[6] = {0.25, 0.20, 0.20, 0.15, 0.10, 0.10};
+        c = dfd_py_sum_products(sc, wt, 6);
+    } else {
+        const double sc[3] = {R.scores[0], R.scores[5], R.scores[3]};
+        const double wt[3] = {0.45, 0.25, 0.30};
+        c = dfd_py_sum_products(sc, wt, 3);
+    }
     R.fake_probability = clip01(c);
     results[i] = R;
 }
@@ -701,7 +800,7 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
     k_resize256<<<dim3(T, n), 256, 0, st>>>(frames, H, W, frame_stride, row_pitch, rs_tab, wide_ok, ctx->d_tile, ctx->d_gray);
     DFD_LAUNCH_CHECK("k_resize256", st);
     k_tile_stats<<<dim3(DFD_NBLK, n), 256, 0, st>>>(ctx->d_tile, ctx->d_gray, stream_ids, full, ctx->d_tables, ctx->d_state,
-                                                     ctx->d_prev_gray, ctx->d_part);
+                                                     ctx->d_prev_gray, ctx->d_part, ctx->cfg.max_streams);
     DFD_LAUNCH_CHECK("k_tile_stats", st);
     k_canny<<<n, 1024, CN_SMEM, st>>>(ctx->d_gray, &ctx->d_part[0].canny_count, sizeof(DfdFramePartials), nullptr);
     DFD_LAUNCH_CHECK("k_canny", st);
@@ -711,14 +810,15 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
     DFD_LAUNCH_CHECK("k_fft_rows", st);
     k_fft_cols<<<dim3(DFD_FFT_GROUPS, n), 128, 0, st>>>(ctx->d_fft, ctx->d_twiddle, ctx->d_part);
     DFD_LAUNCH_CHECK("k_fft_cols", st);
-    k_finalize<<<(n + 63) / 64, 64, 0, st>>>(n, stream_ids, full, ctx->d_part, ctx->d_state, results);
+    k_finalize<<<(n + FIN_WARPS - 1) / FIN_WARPS, 32 * FIN_WARPS, 0, st>>>(n, ctx->cfg.max_streams, stream_ids, full, ctx->d_part, ctx->d_state, results);
     DFD_LAUNCH_CHECK("k_finalize", st);
     return DFD_OK;
 }
 
 int dfd_forensics_init(dfd_ctx* ctx) {
-    DFD_CUDA(cudaFuncSetAttribute(k_canny, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_SMEM));
-    DFD_CUDA(cudaFuncSetAttribute(k_ela, cudaFuncAttributeMaxDynamicSharedMemorySize, T * T + 2 * 128 * 128));
+    int rc;
+    if ((rc = dfd_func_smem(ctx, k_canny, CN_SMEM))) return rc;
+    if ((rc = dfd_func_smem(ctx, k_ela, T * T + 2 * 128 * 128))) return rc;
     return DFD_OK;
 }
 

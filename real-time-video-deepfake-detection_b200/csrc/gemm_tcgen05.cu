@@ -555,15 +555,13 @@ static GemmKernel gemm_kernel(const GemmParams& p) {
     }
 }
 static int gemm_set_attrs(dfd_ctx* ctx) {
-    static bool done = false;
-    if (done) return DFD_OK;
     GemmParams q;
     memset(&q, 0, sizeof q);
     for (int sel = 0; sel < 8; sel++) {
         q.residual = (sel & 4) ? (const __nv_bfloat16*)1 : nullptr; q.act = (sel & 2) ? 1 : 0; q.dense_c = sel & 1;
-        DFD_CUDA(cudaFuncSetAttribute(gemm_kernel(q), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        int rc = dfd_func_smem(ctx, gemm_kernel(q), 210 * 1024);        // per context (= per device), see dfd_func_smem
+        if (rc) return rc;
     }
-    done = true;
     return DFD_OK;
 }
 
@@ -622,11 +620,7 @@ int dfd_gemm_bf16_ex(dfd_ctx* ctx, int a_mode, const __nv_bfloat16* A, const flo
     DFD_REQUIRE(stages >= 2, DFD_ERR_INVALID, "gemm: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if ((rc = gemm_set_attrs(ctx))) return rc;
-        attr_set = true;
-    }
+    if ((rc = gemm_set_attrs(ctx))) return rc;
     CUtensorMap ma, mb, mc;
     if (a_mode != A_STEM) { if ((rc = make_map(ctx, &ma, A, (uint64_t)M, (uint64_t)K, BLOCK_M))) return rc; }
     else memset(&ma, 0, sizeof ma);
@@ -661,11 +655,7 @@ int dfd_gemm_bf16_img(dfd_ctx* ctx, const __nv_bfloat16* A, const __nv_bfloat16*
     DFD_REQUIRE(stages >= 2, DFD_ERR_INVALID, "gemm_img: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if ((rc = gemm_set_attrs(ctx))) return rc;
-        attr_set = true;
-    }
+    if ((rc = gemm_set_attrs(ctx))) return rc;
     CUtensorMap ma, mb, mc;
     {
         const uint64_t d[3] = {(uint64_t)K, (uint64_t)hw, (uint64_t)n_img}, s[2] = {(uint64_t)K * 2, (uint64_t)hw * K * 2};
@@ -739,6 +729,7 @@ __global__ void k_maxerr(const __nv_bfloat16* c, const float* ref, size_t n, flo
 extern "C" int dfd_gemm_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int with_residual, double* max_err_host,
                                  void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     const bool use_res = with_residual & 1, use_se = (with_residual & 2) != 0;
     const int hw = 49, n_img = (M + hw - 1) / hw;
@@ -779,6 +770,7 @@ extern "C" int dfd_gemm_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int
 // bit 3 = residual).  Writes the mean milliseconds per launch to *ms_host.
 extern "C" int dfd_gemm_bench(dfd_ctx* ctx, int M, int N, int K, int act, int flags, int iters, double* ms_host, void* stream) {
     if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = 49, n_img = (M + hw - 1) / hw;
     __nv_bfloat16 *A, *W, *R, *C;

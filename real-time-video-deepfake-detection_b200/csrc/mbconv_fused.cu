@@ -414,13 +414,8 @@ static int launch_front(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __n
     const size_t budget = (size_t)(227 * 1024) / MINB - 1536;
     const int na = G::smem_bytes(num_kb, 2) <= budget ? 2 : 1;
     const size_t smem = G::smem_bytes(num_kb, na);
-    static size_t attr_bytes = 0;
-    if (smem > attr_bytes) {
-        DFD_CUDA(cudaFuncSetAttribute(k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE, KW, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // two CTAs per SM need the full shared-memory carve-out (the driver's default picks a smaller one)
-        DFD_CUDA(cudaFuncSetAttribute(k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE, KW, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_bytes = smem;
-    }
+    // (two CTAs per SM need the full shared-memory carve-out: the driver's default picks a smaller one)
+    { int rc0 = dfd_func_smem(ctx, k_mbconv_front<K, S, TW, TH, CC, HIN, WHOLE, KW, NT, MINB>, smem, true); if (rc0) return rc0; }
     CUtensorMap mx, mw;
     int rc;
     {

@@ -39,3 +39,20 @@ DFD_HD float dfd_np_std_f32(const float* a, int n, float* tmp) {
     for (int i = 0; i < n; i++) { float d = DFD_FSUB(a[i], mean); tmp[i] = DFD_FMUL(d, d); }
     return DFD_FSQRT(DFD_FDIV(dfd_np_sum_f32(tmp, n), (float)n));
 }
+
+// Python's builtin sum() over exact floats (CPython >= 3.12, Python/bltinmodule.c: Neumaier-compensated (hi, lo) pair, the
+// correction added once at the end) of the products s[k] * w[k] -- the reference's combined forensic score,
+// sum(scores[k] * weights[k] for k in weights), frame_analysis.py:94,119.  A plain running sum differs in the last bit for
+// a third of the reachable score combinations and flips the strict `p > 0.5` vote for a few hundred of them.
+DFD_HD double dfd_py_sum_products(const double* s, const double* w, int n) {
+    double hi = 0.0, lo = 0.0;
+    for (int k = 0; k < n; k++) {
+        const double x = DFD_DMUL(s[k], w[k]);                                 // no FMA: Python rounds the product
+        const double t = DFD_DADD(hi, x);
+        if (fabs(hi) >= fabs(x)) lo = DFD_DADD(lo, DFD_DADD(DFD_DSUB(hi, t), x));
+        else lo = DFD_DADD(lo, DFD_DADD(DFD_DSUB(x, t), hi));
+        hi = t;
+    }
+    if (lo != 0.0 && isfinite(lo)) hi = DFD_DADD(hi, lo);
+    return hi;
+}

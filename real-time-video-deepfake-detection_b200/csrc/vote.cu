@@ -105,11 +105,17 @@ __device__ void tracker_update(DfdStreamState& S, const VoteCfg&, double p, int 
     }
 }
 
+// record of a frame whose stream id is outside [0, max_streams): verdict -1, counts 0
+__device__ void bad_record(dfd_vote_record& r, double p) {
+    r.verdict = -1; r.fake_count = 0; r.real_count = 0; r.history_len = 0; r.frame_count = 0; r.last_vote = -1; r.reserved = 0;
+    r.vote_input = p; r.temporal_average = 0.0; r.stability_score = 0.0;
+}
+
 // CTA = VOTE_WARPS streams, one warp per stream.
 __global__ void __launch_bounds__(32 * VOTE_WARPS)
 k_vote(int n, const int32_t* __restrict__ stream_ids, const double* __restrict__ vote_input,
        const uint8_t* __restrict__ np_flags, DfdStreamState* __restrict__ state, VoteCfg cfg,
-       dfd_vote_record* __restrict__ rec) {
+       dfd_vote_record* __restrict__ rec, int max_streams) {
     __shared__ double s_v[VOTE_WARPS][DFD_MAX_SCORES];
     __shared__ uint8_t s_np[VOTE_WARPS][DFD_MAX_SCORES];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,6 +125,10 @@ k_vote(int n, const int32_t* __restrict__ stream_ids, const double* __restrict__
     r.stream_id = stream_ids[i];
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
     r.face_probability = NaN; r.forensic_probability = NaN;
+    if ((unsigned)r.stream_id >= (unsigned)max_streams) {        // caller error: flagged in the record, no state touched
+        if (lane == 0) { bad_record(r, vote_input[i]); rec[i] = r; }
+        return;
+    }
     tracker_update(state[r.stream_id], cfg, vote_input[i], np_flags ? np_flags[i] : 0, r, s_v[w], s_np[w]);
     if (lane == 0) rec[i] = r;
 }
@@ -128,7 +138,7 @@ k_vote(int n, const int32_t* __restrict__ stream_ids, const double* __restrict__
 __global__ void __launch_bounds__(32 * VOTE_WARPS)
 k_select_vote(int n, int m, const int32_t* __restrict__ box_frame, const double* __restrict__ face_prob,
               const dfd_forensic_result* __restrict__ fres, const int32_t* __restrict__ stream_ids,
-              DfdStreamState* __restrict__ state, VoteCfg cfg, dfd_vote_record* __restrict__ rec) {
+              DfdStreamState* __restrict__ state, VoteCfg cfg, dfd_vote_record* __restrict__ rec, int max_streams) {
     // first box of every frame of this CTA (faces[0], backend_server.py:160): all threads sweep the box list once and
     // keep the smallest box index per frame in shared memory (a per-thread scan of all m boxes was O(m) dependent loads)
     __shared__ int s_first[VOTE_WARPS];
@@ -150,10 +160,18 @@ k_select_vote(int n, int m, const int32_t* __restrict__ box_frame, const double*
     if (s_first[w] != 0x7fffffff) fp = face_prob[s_first[w]];
     double forensic = fres[i].fake_probability;
     double p;
-    if (fp == fp) p = cfg.blend_mode == DFD_BLEND_README ? cfg.face_w * fp + cfg.forensic_w * forensic : fp;
+    // README blend (opt-in): face_w * face + forensic_w * forensic in Python float arithmetic (two rounded products,
+    // one rounded sum -- no FMA contraction)
+    if (fp == fp) p = cfg.blend_mode == DFD_BLEND_README ? __dadd_rn(__dmul_rn(cfg.face_w, fp), __dmul_rn(cfg.forensic_w, forensic)) : fp;
     else p = forensic;                                               // backend_server.py:206
     dfd_vote_record r;
     r.stream_id = stream_ids[i];
+    r.face_probability = fp;
+    r.forensic_probability = forensic;
+    if ((unsigned)r.stream_id >= (unsigned)max_streams) {
+        if (lane == 0) { bad_record(r, p); rec[i] = r; }
+        return;
+    }
     DfdStreamState& S = state[r.stream_id];
     if (lane == 0) S.detector_frames += 1;                           // backend_server.py:156
     r.face_probability = fp;
@@ -164,9 +182,10 @@ k_select_vote(int n, int m, const int32_t* __restrict__ box_frame, const double*
 
 // sigmoid + apply_heuristics (deepfake_detection.py:398,489-502)
 __global__ void k_faceprob(int m, const float* __restrict__ logits, const int32_t* __restrict__ boxes,
-                           double* __restrict__ prob) {
+                           const uint8_t* __restrict__ bad, double* __restrict__ prob) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
+    if (bad && bad[i]) { prob[i] = __longlong_as_double(0x7ff8000000000000LL); return; }   // rejected box: "no face"
     float z = logits[i];
     float s = 1.0f / (1.0f + expf(-z));                              // torch.sigmoid in float32
     double p = (double)s;                                            // .item() -> Python float
@@ -198,14 +217,16 @@ static VoteCfg make_cfg(const dfd_ctx* ctx) {
 }
 
 int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, cudaStream_t st) {
-    k_faceprob<<<(m + 127) / 128, 128, 0, st>>>(m, logits, boxes, prob);
+    // boxes the last face-prep call rejected (k_box_sanitize) get NaN; the flags describe exactly its m boxes
+    const uint8_t* bad = ctx->box_flags_m == m ? ctx->d_box_bad : nullptr;
+    k_faceprob<<<(m + 127) / 128, 128, 0, st>>>(m, logits, boxes, bad, prob);
     DFD_LAUNCH_CHECK("k_faceprob", st);
     return DFD_OK;
 }
 
 int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
                     dfd_vote_record* rec, cudaStream_t st) {
-    k_vote<<<(n + VOTE_WARPS - 1) / VOTE_WARPS, 32 * VOTE_WARPS, 0, st>>>(n, stream_ids, vote_input, np_flags, ctx->d_state, make_cfg(ctx), rec);
+    k_vote<<<(n + VOTE_WARPS - 1) / VOTE_WARPS, 32 * VOTE_WARPS, 0, st>>>(n, stream_ids, vote_input, np_flags, ctx->d_state, make_cfg(ctx), rec, ctx->cfg.max_streams);
     DFD_LAUNCH_CHECK("k_vote", st);
     return DFD_OK;
 }
@@ -213,7 +234,7 @@ int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_
 int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame, const double* face_prob,
                            const dfd_forensic_result* fres, const int32_t* stream_ids, dfd_vote_record* rec,
                            cudaStream_t st) {
-    k_select_vote<<<(n + VOTE_WARPS - 1) / VOTE_WARPS, 32 * VOTE_WARPS, 0, st>>>(n, m, box_frame, face_prob, fres, stream_ids, ctx->d_state, make_cfg(ctx), rec);
+    k_select_vote<<<(n + VOTE_WARPS - 1) / VOTE_WARPS, 32 * VOTE_WARPS, 0, st>>>(n, m, box_frame, face_prob, fres, stream_ids, ctx->d_state, make_cfg(ctx), rec, ctx->cfg.max_streams);
     DFD_LAUNCH_CHECK("k_select_vote", st);
     return DFD_OK;
 }

@@ -213,6 +213,8 @@ class DeepfakeDetector:
             logits = self._eng.effnet_forward(x)
             p = self._eng.face_probability(logits, box)
             p = np.float64(p.cpu().numpy()[0])              # np.float64, like np.clip in apply_heuristics
+            if np.isnan(p):                                 # box rejected on the device (k_box_sanitize)
+                raise ValueError(f"face crop {w}x{h} exceeds the engine's max_crop ({self._eng.cfg.max_crop})")
             return p, p, None
         except Exception as e:                              # the reference swallows and reports (:548-550)
             print(f"Face analysis error: {e}")

@@ -200,5 +200,9 @@ void hc_gauss_resid(const uint8_t* g, int h, int w, float* dst) {    // gray - b
         dst[y * w + x] = (float)g[y * w + x] - (float)dfd_gauss5_x256(g, w, h, x, y) / 256.0f;
 }
 float hc_np_mean(const float* a, int n) { return dfd_np_mean_f32(a, n); }
+double hc_py_sum_products(const double* s, const double* w, int n) { return dfd_py_sum_products(s, w, n); }
+void hc_py_sum_products_batch(const double* s, const double* w, int n, long count, double* out) {
+    for (long i = 0; i < count; i++) out[i] = dfd_py_sum_products(s + i * n, w, n);
+}
 float hc_np_std(const float* a, int n) { std::vector<float> t(n); return dfd_np_std_f32(a, n, t.data()); }
 }

@@ -53,21 +53,62 @@ def test_fp32_activation_taps(setup, name):
 
 
 def test_bf16_logits(setup):
-    """bf16 mode against (a) the fp32 oracle and (b) the oracle's bf16-STORAGE restatement, which rounds exactly where
-    the CUDA path rounds.  (b) isolates the kernels' own error from the inherent loss of bf16 storage: the north_star
-    bf16 gate (5e-3 absolute on the probability) is asserted against (b); against (a) the difference on these
-    random-init weights is the storage loss itself (oracle-vs-oracle), reported and bounded relative to it."""
+    """bf16 mode end to end, reported against (a) the fp32 oracle and (b) the oracle's bf16-STORAGE restatement.
+
+    What is asserted -- and what is NOT.  north_star's bf16 gate is |dp| <= 5e-3 against the reference (fp32).  On the
+    fixed-seed random-init weights that gate is NOT met and cannot be: the synthetic network amplifies ANY 2^-9-relative
+    perturbation (rounding the input image alone) into |dp| ~ 0.03, so the bf16-storage restatement itself is ~0.05 away
+    from fp32 and two bf16 implementations that differ in one rounding (tanh.approx vs exact swish) are ~0.01-0.03 apart.
+    The kernels' own arithmetic is therefore gated where the amplification cannot interfere -- per block, on identical
+    inputs, in test_bf16_blockwise_exactness -- and this test bounds the end-to-end numbers as a regression guard:
+    max |dp| vs fp32 <= 0.08 and no worse than the storage restatement by more than 1.5x.  The parity-green fast mode is
+    dtype="fp32" (3xTF32 tensor-core path, <= 1e-4), see test_fp32_*."""
     e, sd, x, ref, taps = setup
     xn = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
     logits = e.effnet_forward(xn).cpu()
     emu = oeff.forward_bf16_storage(x, sd).flatten()
     ref = ref.flatten()
     p, pe, pr = torch.sigmoid(logits), torch.sigmoid(emu), torch.sigmoid(ref)
-    print("bf16 CUDA vs bf16-storage oracle: max |dlogit|", float((logits - emu).abs().max()), "max |dp|", float((p - pe).abs().max()))
+    print("bf16 CUDA vs bf16-storage oracle: max |dlogit|", float((logits - emu).abs().max()), "max |dp|", float((p - pe).abs().max()),
+          "mean |dp|", float((p - pe).abs().mean()))
     print("bf16-storage oracle vs fp32 oracle (inherent): max |dp|", float((pe - pr).abs().max()), "mean", float((pe - pr).abs().mean()))
     print("bf16 CUDA vs fp32 oracle: max |dp|", float((p - pr).abs().max()), "mean", float((p - pr).abs().mean()))
+    print("north_star bf16 gate (5e-3 vs fp32):", "MET" if float((p - pr).abs().max()) <= 5e-3 else "NOT MET on these weights")
+    assert float((p - pr).abs().max()) <= 0.08
     assert float((p - pr).abs().mean()) <= 1.5 * float((pe - pr).abs().mean()) + 1e-3    # no worse than bf16 storage itself
-    assert float((logits - ref).abs().mean()) < 0.5
+    assert float((p - pe).abs().max()) <= 0.06                                           # and near the restatement
+
+
+@pytest.mark.parametrize("blk", list(range(16)))
+def test_bf16_blockwise_exactness(setup, blk):
+    """The bf16 kernels' own error, with the network's amplification taken out: block `blk` of the CPU bf16-storage
+    restatement is fed the CUDA path's OWN input to that block (the previous tap, exact bf16 values) and must reproduce
+    the CUDA depthwise output and block output to within a few bf16 ulps: max <= 2^-6 and mean <= 2^-10 of the tensor
+    scale (the old test allowed 6 % / 1 % against the end-to-end fp32 taps).  What may differ: fp32 accumulation order,
+    tanh.approx vs exact swish (2^-11), the fixed-order squeeze partials."""
+    e, sd, x, ref, taps = setup
+    xn = x[:4].permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    got = {}
+    names = ["stem" if blk == 0 else f"b{blk - 1}.out", f"b{blk}.dw", f"b{blk}.out"]
+    shapes = {}
+    k, st, cin, cexp, cout, se = oeff.BLOCKS[blk]
+    hin = [112, 112, 56, 56, 28, 28, 14, 14, 14, 14, 14, 14, 7, 7, 7, 7][blk]
+    hout = (hin + st - 1) // st
+    shapes[names[0]] = (4, hin, hin, cin)
+    shapes[names[1]] = (4, hout, hout, cexp)
+    shapes[names[2]] = (4, hout, hout, cout)
+    for name in names:
+        e.set_tap(name)
+        e.effnet_forward(xn)
+        got[name] = e.activation(name).cpu().reshape(shapes[name]).permute(0, 3, 1, 2).contiguous()
+    e.set_tap("")
+    out, dw = oeff.block_bf16_storage(got[names[0]], sd, blk, gated_weight=blk < 5)
+    for name, want in ((names[1], dw), (names[2], out)):
+        d = (got[name] - want).abs()
+        scale = max(1.0, float(want.abs().max()))
+        print(name, "max", float(d.max()), "mean", float(d.mean()), "scale", scale, "exact frac", float((d == 0).float().mean()))
+        assert float(d.max()) <= 2.0 ** -6 * scale, name
+        assert float(d.mean()) <= 2.0 ** -10 * scale, name
 
 
 def test_batch_invariance_fp32(setup):

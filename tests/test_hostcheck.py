@@ -129,6 +129,49 @@ def test_numpy_order_reductions(hc):
         assert hc.hc_np_std(ptr(a), n) == np.std(a)
 
 
+def _reachable(*groups):
+    """Every value a score function can return: score = 0.0; score += a; score += b; ... ; float(np.clip(score, 0, 1))
+    (frame_analysis.py:154-180 and the other five), in the reference's order of additions."""
+    import itertools
+    out = set()
+    for combo in itertools.product(*groups):
+        s = 0.0
+        for v in combo:
+            if v:
+                s += v
+        out.add(float(np.clip(s, 0.0, 1.0)))
+    return sorted(out)
+
+
+def test_combined_score_is_pythons_compensated_sum(hc):
+    """The combined forensic probability is Python's sum() over floats (Neumaier-compensated since CPython 3.12) of
+    scores[k] * weights[k] in dict order (frame_analysis.py:94,119).  Enumerates EVERY reachable combination of the six
+    (three) step scores and compares dfd_py_sum_products -- the function k_finalize inlines -- with sum() bit for bit; a plain
+    running sum fails this test (it flips the strict `p > 0.5` vote for some hundred combinations)."""
+    import itertools
+    freq = _reachable((0.4, 0.2, 0), (0.25, 0.1, 0), (0.15, 0))
+    noise = _reachable((0.5, 0.25, 0), (0.3, 0.1, 0))
+    ela = _reachable((0.5, 0.2, 0), (0.2, 0.1, 0))
+    edge = _reachable((0.35, 0.15, 0), (0.3, 0.1, 0))
+    color = _reachable((0.3, 0.1, 0), (0.25, 0.1, 0), (0.25, 0.1, 0))
+    temporal = _reachable((0.4, 0.2, 0), (0.3, 0.1, 0))
+    hc.hc_py_sum_products_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p]
+    for groups, weights in (((freq, noise, ela, edge, color, temporal), (0.25, 0.20, 0.20, 0.15, 0.10, 0.10)),
+                            ((freq, temporal, edge), (0.45, 0.25, 0.30))):
+        combos = np.array(list(itertools.product(*groups)), np.float64)
+        w = np.array(weights, np.float64)
+        got = np.zeros(len(combos), np.float64)
+        hc.hc_py_sum_products_batch(ptr(combos), ptr(w), len(weights), len(combos), ptr(got))
+        wl = list(weights)
+        want = np.array([sum(s * k for s, k in zip(row, wl)) for row in combos.tolist()], np.float64)
+        assert np.array_equal(got, want), int((got != want).sum())
+        plain = np.zeros(len(combos))
+        for j in range(len(wl)):
+            plain = plain + combos[:, j] * wl[j]
+        print(len(combos), "combinations; a plain running sum differs on", int((plain != want).sum()),
+              "and flips p > 0.5 on", int(((plain > 0.5) != (want > 0.5)).sum()))
+
+
 def test_constant_division_is_exact(tmp_path):
     """dfd_div_const (3-instruction division by 255 / the ImageNet std constants in k_vpass_up_norm) equals the IEEE
     quotient: sampled run (every 97th float of the operand ranges) of the exhaustive checker; the full run is in its header."""
