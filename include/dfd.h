@@ -183,6 +183,11 @@ int dfd_gemm_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int with_resid
 /* Mean milliseconds per launch of one GEMM shape over `iters` launches (kernel tuning; flags: 1 = no stores, 2 = no epilogue
  * math, 4 = SE-gated A, 8 = residual). */
 int dfd_gemm_bench(dfd_ctx* ctx, int M, int N, int K, int act, int flags, int iters, double* ms_host, void* stream);
+/* 3xTF32 GEMM self-test (fp32 accuracy mode, gemm_tf32x3.cu): C = act(A . W^T + bias) (+ residual) on random fp32 data against a
+ * CUDA-core reference with fp64 accumulation; mode bit 0 = residual, bit 1 = SE-gated A (hw = 49).  Writes max relative error to
+ * *max_err_host; iters > 0 also times the launch (mean ms -> *ms_host). */
+int dfd_gemm_tf32_selftest(dfd_ctx* ctx, int M, int N, int K, int act, int mode, int iters, double* max_err_host,
+                           double* ms_host, void* stream);
 /* After dfd_face_prep_batch: the 160 x 160 x 3 RGB u8 image of box i. */
 int dfd_dbg_face160(dfd_ctx* ctx, int i, uint8_t* out_dev, void* stream);
 /* After dfd_face_prep_batch: the CLAHE'd crop of box i as w*h*3 BGR u8 (tight). */
@@ -197,7 +202,8 @@ int64_t dfd_dbg_activation(dfd_ctx* ctx, const char* name, float* out_dev, int64
 /* A/B switches for the parity tests: "no_fuse" (1 = run the expand 1x1 GEMM and the depthwise kernel separately
  * instead of the fused mbconv_fused.cu kernel), "se_mode" (bf16 SE excite: 0 = two kernels, 1 = one kernel, 2 = one kernel on 8-CTA clusters), "no_gated_w" (1 = blocks 0-4 gate the
  * project GEMM's A operand instead of using per-image gated weights), "pdl" (0 = no programmatic dependent launch),
- * "no_overlap" (1 = forensic kernels on the caller's stream).
+ * "no_overlap" (1 = forensic kernels on the caller's stream), "fp32_simt" (1 = fp32 mode on the CUDA-core kernels instead of
+ * the 3xTF32 tensor-core path).
  * Threading / devices: one context per GPU; every entry point makes the context's device current for its duration and
  * restores the caller's, so one process may drive several contexts on different GPUs (from one thread at a time each). */
 int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value);

@@ -67,6 +67,7 @@ SYMBOLS = {
     "dfd_dbg_set_option": (_I, [_P, C.c_char_p, _I]),
     "dfd_gemm_selftest": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(C.c_double), _P]),
     "dfd_gemm_bench": (_I, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_double), _P]),
+    "dfd_gemm_tf32_selftest": (_I, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
 }
 
 _lib = None

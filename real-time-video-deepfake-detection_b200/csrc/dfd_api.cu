@@ -188,6 +188,7 @@ int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
     ctx->no_gated_w = getenv("DFD_NO_GATED_W") != nullptr;
     if (const char* e = getenv("DFD_GATED_W_MAX")) { ctx->gated_w_max = atoi(e); if (ctx->gated_w_max > 10) ctx->gated_w_max = 10; }
     ctx->no_fold = getenv("DFD_NO_FOLD") != nullptr;
+    ctx->fp32_simt = getenv("DFD_FP32_SIMT") != nullptr;
     if (getenv("DFD_SE_MODE")) ctx->se_mode = atoi(getenv("DFD_SE_MODE"));
     int rc = create_impl(ctx);
     if (rc) { g_create_err = ctx->err; dfd_destroy(ctx); *out = nullptr; return rc; }
@@ -200,7 +201,7 @@ void dfd_destroy(dfd_ctx* ctx) {
     DfdDeviceGuard dev_guard(ctx->cfg.device);
     void* ptrs[] = {ctx->d_tables, ctx->d_twiddle, ctx->d_state, ctx->d_prev_gray, ctx->d_tile, ctx->d_gray, ctx->d_fft,
                     ctx->d_part, ctx->d_fres, ctx->d_luts, ctx->d_pil, ctx->d_hpass, ctx->d_face160, ctx->d_boxes_ok, ctx->d_fidx_ok, ctx->d_box_bad, ctx->d_wf32,
-                    ctx->d_wbf16, ctx->d_stem_wg, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
+                    ctx->d_wbf16, ctx->d_stem_wg, ctx->d_wtf_hi, ctx->d_wtf_lo, ctx->d_stem_wtf, ctx->act[0].p, ctx->act[1].p, ctx->act[2].p, ctx->face_in.p, ctx->d_pool,
                     ctx->d_sescale, ctx->d_se_r, ctx->d_front_aux, ctx->d_wgated, ctx->d_wgated_fold, ctx->d_bias_fold, ctx->d_wxt, ctx->d_feat, ctx->d_fc_h1, ctx->d_fc_h2, ctx->d_logits, ctx->d_faceprob, ctx->d_voteinput, ctx->tap.p};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : ctx->rs_cache) if (e.p) cudaFree(e.p);
@@ -386,6 +387,7 @@ int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value) {
     else if (n == "no_fold") ctx->no_fold = value != 0;
     else if (n == "se_mode") ctx->se_mode = value;
     else if (n == "no_overlap") ctx->no_overlap = value != 0;
+    else if (n == "fp32_simt") ctx->fp32_simt = value != 0;
     else { ctx->err = "dbg_set_option: unknown option " + n; return DFD_ERR_INVALID; }
     return DFD_OK;
 }

@@ -88,6 +88,10 @@ struct dfd_ctx {
     size_t w_floats = 0;
     __nv_bfloat16* d_wbf16 = nullptr;     // bf16 copies of the GEMM weights (same offsets)
     __nv_bfloat16* d_stem_wg = nullptr;   // stem weights as a [32][32] K-major GEMM operand (27 taps + zero pad)
+    float* d_wtf_hi = nullptr;            // fp32 accuracy mode on the tensor cores (gemm_tf32x3.cu): tf32 hi / lo planes of the
+    float* d_wtf_lo = nullptr;            //   parameter blob (same offsets), W = hi + lo to ~2^-22
+    float* d_stem_wtf = nullptr;          // stem [32][32] K-major operand, hi plane then lo plane
+    bool fp32_simt = false;               // "fp32_simt" / DFD_FP32_SIMT=1: run the fp32 mode on the CUDA-core kernels (k_pw / k_dw / k_stem; A/B testing)
     DfdBuf act[3];                        // activation ping-pong + expanded buffer
     DfdBuf face_in;                       // prepared crops for analyze_batch
     float* d_pool = nullptr;              // [m][n_parts][C] SE squeeze partial sums (<= DFD_POOL_FLOATS per image)
@@ -209,6 +213,21 @@ static inline cudaError_t dfd_launch(bool pdl, void (*kern)(KArgs...), dim3 grid
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// x * sigmoid(x) for the fp32 accuracy mode in ~10 instructions and ~3 ulp (expf + IEEE division: ~35 instructions, which made
+// the epilogues of the expand convs ALU-bound).  exp(-x) = 2^t with t = -x * log2(e) carried as hi + lo (the rounding error
+// of the product would otherwise scale with |x|), 2^t from MUFU.EX2 (2 ulp), corrected by (1 + lo * ln 2); division by
+// 1 + e with the 2-ulp approximate divide.  t is clamped so that e stays finite (swish(-87) is 0 to fp32 anyway).
+__device__ __forceinline__ float swish_f32(float x) {
+    const float nx = -x;
+    float t = nx * 1.44269502162933349609375f;
+    float tl = fmaf(nx, 1.44269502162933349609375f, -t);
+    tl = fmaf(nx, 1.92596299112661746e-8f, tl);
+    t = fminf(t, 126.0f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    e = fmaf(e * tl, 0.693147182464599609375f, e);
+    return __fdividef(x, 1.0f + e);
+}
 #endif
 
 // forensics.cu

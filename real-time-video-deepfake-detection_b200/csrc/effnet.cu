@@ -34,6 +34,11 @@ int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const 
 int dfd_mbconv_front_bf16(dfd_ctx* ctx, int blk, const __nv_bfloat16* x, const __nv_bfloat16* We, __nv_bfloat16* out, int m,
                           int* n_parts, cudaStream_t st);
 int dfd_front_pack(dfd_ctx* ctx, const float* blob);
+int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, int hw, const float* W_hi, const float* W_lo,
+                    const float* bias, const float* residual, float* C, int M, int N, int K, int act, cudaStream_t st);
+void dfd_tf32_split_host(const float* w, size_t n, float* hi, float* lo);
+int dfd_dw_f32(dfd_ctx* ctx, const EffBlock& b, const float* in, const float* W, const float* bias, float* out, int m,
+               int* n_parts, cudaStream_t st);
 
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
 template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
@@ -772,6 +777,22 @@ int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n) {
     for (int n = 0; n < 32; n++)
         for (int k = 0; k < 32; k++) wg[n * 32 + k] = __float2bfloat16_rn(k < 27 ? blob[o.stem_w + (size_t)k * 32 + n] : 0.f);
     DFD_CUDA(cudaMemcpy(ctx->d_stem_wg, wg.data(), wg.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    {   // tf32 hi / lo planes for the fp32 accuracy mode (gemm_tf32x3.cu)
+        if (!ctx->d_wtf_hi) {
+            DFD_CUDA(cudaMalloc(&ctx->d_wtf_hi, o.total * sizeof(float)));
+            DFD_CUDA(cudaMalloc(&ctx->d_wtf_lo, o.total * sizeof(float)));
+            DFD_CUDA(cudaMalloc(&ctx->d_stem_wtf, 2 * 32 * 32 * sizeof(float)));
+        }
+        std::vector<float> hi(o.total), lo(o.total);
+        dfd_tf32_split_host(blob, o.total, hi.data(), lo.data());
+        DFD_CUDA(cudaMemcpy(ctx->d_wtf_hi, hi.data(), o.total * sizeof(float), cudaMemcpyHostToDevice));
+        DFD_CUDA(cudaMemcpy(ctx->d_wtf_lo, lo.data(), o.total * sizeof(float), cudaMemcpyHostToDevice));
+        std::vector<float> sw(32 * 32), sh(2 * 32 * 32);
+        for (int n = 0; n < 32; n++)
+            for (int k = 0; k < 32; k++) sw[n * 32 + k] = k < 27 ? blob[o.stem_w + (size_t)k * 32 + n] : 0.f;
+        dfd_tf32_split_host(sw.data(), 32 * 32, sh.data(), sh.data() + 32 * 32);
+        DFD_CUDA(cudaMemcpy(ctx->d_stem_wtf, sh.data(), sh.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     { int rc = dfd_front_pack(ctx, blob); if (rc) return rc; }
     {   // block 0 project bias repeated for the 2-pixel folded GEMM rows
         float hb[32];
@@ -826,6 +847,8 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
     constexpr bool BF = sizeof(T) == 2;
     constexpr int VEC = BF ? 8 : 4;
     const bool tc = BF && dfd_gemm_bf16_enabled();
+    // fp32 accuracy mode: 3xTF32 tensor-core GEMMs + tiled fp32 depthwise (default); "fp32_simt" keeps the CUDA-core kernels
+    const bool tc32 = !BF && !ctx->fp32_simt;
     // activation buffers: x (block input / output ping-pong in act[0], act[1]) and e (expanded, act[2])
     const size_t max_io = (size_t)m * 112 * 112 * 32;          // stem out
     const size_t max_e = (size_t)m * (112 * 112 * 96 + 56 * 56 * 96);   // block 1: expand out + depthwise out
@@ -848,6 +871,9 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         if (tc) {
             if ((rc = dfd_gemm_bf16_ex(ctx, 2, (const __nv_bfloat16*)in, nullptr, 0, ctx->d_stem_wg, Wf + o.stem_b, nullptr,
                                        (__nv_bfloat16*)x, total, 32, 32, 1, st))) return rc;
+        } else if (tc32) {
+            if ((rc = dfd_gemm_tf32x3(ctx, 2, (const float*)in, nullptr, 0, ctx->d_stem_wtf, ctx->d_stem_wtf + 32 * 32, Wf + o.stem_b,
+                                      nullptr, (float*)x, total, 32, 32, 1, st))) return rc;
         } else {
             k_stem<T><<<(total + 127) / 128, 128, 0, st>>>(in, Wf + o.stem_w, Wf + o.stem_b, x, total);
             DFD_LAUNCH_CHECK("k_stem", st);
@@ -860,6 +886,9 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             return dfd_gemm_bf16(ctx, (const __nv_bfloat16*)A, ctx->d_wbf16 + w_off, Wf + b_off, (const __nv_bfloat16*)res,
                                  (__nv_bfloat16*)C, M, N, K, act, st);
         }
+        if (tc32)       // (a gate is applied while the A tile is staged: the gated tensor never exists in HBM)
+            return dfd_gemm_tf32x3(ctx, se ? 1 : 0, (const float*)A, se, hw, ctx->d_wtf_hi + w_off, ctx->d_wtf_lo + w_off, Wf + b_off,
+                                   (const float*)res, (float*)C, M, N, K, act, st);
         // 32-row tiles when 64-row tiles would leave SMs idle
         if ((size_t)((M + 63) / 64) * ((N + 63) / 64) < (size_t)2 * ctx->sm_count)
             k_pw<T, 32><<<dim3((M + 31) / 32, (N + 63) / 64), 128, 0, st>>>(A, Wf + w_off, Wf + b_off, se, hw, res, C, M, N, K, act);
@@ -905,6 +934,8 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             ctx->label = L_DW[i];
             if constexpr (BF) {
                 if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, &n_parts, st))) return rc;
+            } else if (tc32) {
+                if ((rc = dfd_dw_f32(ctx, b, (const float*)dw_in, Wf + f.wd, Wf + f.bd, (float*)dw_out, m, &n_parts, st))) return rc;
             } else {
                 if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, &n_parts, st))) return rc;
             }
@@ -920,7 +951,7 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
         __nv_bfloat16* wg_buf = fold > 1 ? ctx->d_wgated_fold : ctx->d_wgated;
         if (BF && ctx->se_mode == 3) {
             // timing experiment only (DFD_SE_MODE=3): no SE excite at all, gates stay whatever they were
-        } else if (BF && ctx->se_mode == 2) {
+        } else if ((BF || tc32) && ctx->se_mode == 2) {
             DFD_CUDA(dfd_launch(ctx->pdl, k_se_cluster, dim3((m + SE_CL - 1) / SE_CL * SE_CL), dim3(256), 0, st, (const float*)ctx->d_pool, n_parts,
                                 (const float*)(Wf + f.wr), (const float*)(Wf + f.br), (const float*)(ctx->d_wxt + wxt_off[i]),
                                 (const float*)(Wf + f.bx), ctx->d_sescale, b.cexp, b.se, 1.0f / (float)(b.hout * b.hout), m,

@@ -517,9 +517,10 @@ static int make_map(dfd_ctx* ctx, CUtensorMap* m, const void* base, uint64_t row
     return DFD_OK;
 }
 
-// generic bf16 tiled map (rank <= 4), 128-byte swizzle, zero OOB fill -- used by mbconv_fused.cu for NHWC patches
-int dfd_tmap_bf16(dfd_ctx* ctx, CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, int swizzle_bytes) {
+// generic tiled map (rank <= 4; bf16 or fp32 elements), 32/64/128-byte swizzle, zero OOB fill -- used by mbconv_fused.cu for
+// NHWC patches and by gemm_tf32x3.cu for the fp32 operands
+int dfd_tmap_encode(dfd_ctx* ctx, CUtensorMap* m, int dtype_f32, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
     int rc = get_encode(ctx);
     if (rc) return rc;
     cuuint64_t d[4], s[3];
@@ -527,10 +528,14 @@ int dfd_tmap_bf16(dfd_ctx* ctx, CUtensorMap* m, const void* base, int rank, cons
     for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; }
     for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
     const CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode(m, dtype_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base, d, s, b, e,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled (rank " + std::to_string(rank) + ") failed (" + std::to_string((int)r) + ")"; return DFD_ERR_CUDA; }
     return DFD_OK;
+}
+int dfd_tmap_bf16(dfd_ctx* ctx, CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, int swizzle_bytes) {
+    return dfd_tmap_encode(ctx, m, 0, base, rank, dims, strides_bytes, box, swizzle_bytes);
 }
 
 // accumulator ring depth: as many n_pad-column accumulators as fit 512 TMEM columns (the last one rounded up to 32), even, <= 8

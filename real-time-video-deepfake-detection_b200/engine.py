@@ -160,6 +160,13 @@ class Engine:
                     "dfd_gemm_selftest")
         return err.value
 
+    def gemm_tf32_selftest(self, M, N, K, act=1, mode=0, iters=0):
+        """-> (max relative error vs an fp64-accumulated reference, mean ms per launch or 0)."""
+        err, ms = C.c_double(-1.0), C.c_double(0.0)
+        self._check(self.lib.dfd_gemm_tf32_selftest(self.h, M, N, K, act, mode, iters, C.byref(err), C.byref(ms), self._stream()),
+                    "dfd_gemm_tf32_selftest")
+        return err.value, ms.value
+
     def analyze_batch(self, frames, stream_ids, full, boxes, box_frame, dtype="bf16", want_forensic=False,
                       records_out=None):
         """Whole per-frame path for one frame per stream (see dfd_analyze_batch)."""

@@ -206,3 +206,120 @@ void hc_py_sum_products_batch(const double* s, const double* w, int n, long coun
 }
 float hc_np_std(const float* a, int n) { std::vector<float> t(n); return dfd_np_std_f32(a, n, t.data()); }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Baseline JPEG decode with the product's functions (csrc/px_jpegdec.h), on the CPU: sequentially (sub_bits = 0) or as a
+// faithful simulation of the GPU kernel's self-synchronising parallel schedule (sub_bits = subsequence size in bits).
+#include "px_jpegdec.h"
+#include <string.h>
+extern "C" {
+int hc_jpeg_info(const uint8_t* data, long n, int* info /* H, W, ncomp, hs0, vs0, ecs bytes, total blocks */) {
+    DfdJpegHeader* h = new DfdJpegHeader;
+    int rc = dfd_jpeg_parse(data, (size_t)n, h);
+    info[0] = h->height; info[1] = h->width; info[2] = h->ncomp; info[3] = h->hs[0]; info[4] = h->vs[0];
+    info[5] = h->ecs_end - h->ecs_begin; info[6] = h->total_blocks;
+    delete h;
+    return rc;
+}
+
+int hc_jpeg_decode(const uint8_t* data, long n, uint8_t* out, int sub_bits, int* rounds_out) {
+    DfdJpegHeader* h = new DfdJpegHeader;
+    int rc = dfd_jpeg_parse(data, (size_t)n, h);
+    if (rc) { delete h; return rc; }
+    // 1. remove byte stuffing, pack MSB-first words
+    std::vector<uint8_t> clean;
+    for (int i = h->ecs_begin; i < h->ecs_end; i++) {
+        clean.push_back(data[i]);
+        if (data[i] == 0xFF && i + 1 < h->ecs_end && data[i + 1] == 0x00) i++;
+    }
+    const uint32_t nbits = (uint32_t)clean.size() * 8;
+    while (clean.size() % 4) clean.push_back(0);
+    std::vector<uint32_t> words(clean.size() / 4 + 2, 0);
+    for (size_t w = 0; w < clean.size() / 4; w++)
+        words[w] = ((uint32_t)clean[4 * w] << 24) | ((uint32_t)clean[4 * w + 1] << 16) | ((uint32_t)clean[4 * w + 2] << 8) | clean[4 * w + 3];
+    const uint32_t nwords = (uint32_t)words.size();
+    // 2. Huffman decode
+    std::vector<int16_t> coef((size_t)h->total_blocks * 64, 0);
+    int32_t dc_off[3] = {0, 0, 0};
+    int ndc = 0;
+    for (int c = 0; c < h->ncomp; c++) { dc_off[c] = ndc; ndc += h->comp_bw[c] * h->comp_bh[c]; }
+    std::vector<int32_t> dcdiff(ndc, 0);
+    int rounds = 0, total = 0, nb, ne;
+    if (sub_bits <= 0) {
+        DfdJpegState s0 = {0, 0, 0};
+        dfd_jpeg_decode_sub<true>(h, words.data(), nwords, dfd_jpeg_pack_state(s0), nbits, &nb, &ne, 0, coef.data(), dcdiff.data(), dc_off);
+        total = nb;
+    } else {
+        const int nsub = (int)((nbits + sub_bits - 1) / sub_bits);
+        std::vector<uint64_t> E(nsub), used(nsub);
+        std::vector<int> cnt(nsub);
+        for (int i = 0; i < nsub; i++) {                           // blind pass
+            DfdJpegState s = {(uint32_t)i * (uint32_t)sub_bits, 0, 0};
+            used[i] = dfd_jpeg_pack_state(s);
+            const uint32_t lim = (uint32_t)std::min<uint64_t>((uint64_t)(i + 1) * sub_bits, nbits);
+            E[i] = dfd_jpeg_decode_sub<false>(h, words.data(), nwords, used[i], lim, &cnt[i], &ne, 0, nullptr, nullptr, nullptr);
+        }
+        bool changed = true;
+        while (changed) {                                          // synchronisation rounds
+            changed = false;
+            rounds++;
+            std::vector<uint64_t> snap = E;                        // (a round reads the previous round's states)
+            for (int i = 1; i < nsub; i++) {
+                if (used[i] == snap[i - 1]) continue;
+                used[i] = snap[i - 1];
+                const uint32_t lim = (uint32_t)std::min<uint64_t>((uint64_t)(i + 1) * sub_bits, nbits);
+                const uint64_t e = dfd_jpeg_decode_sub<false>(h, words.data(), nwords, used[i], lim, &cnt[i], &ne, 0, nullptr, nullptr, nullptr);
+                if (e != E[i]) changed = true;                     // its successor must look at it again
+                E[i] = e;
+            }
+            if (rounds > nsub + 2) break;
+        }
+        std::vector<int> blk0(nsub + 1, 0);
+        for (int i = 0; i < nsub; i++) blk0[i + 1] = blk0[i] + cnt[i];
+        total = blk0[nsub];
+        for (int i = 0; i < nsub; i++) {                           // write pass
+            const uint32_t lim = (uint32_t)std::min<uint64_t>((uint64_t)(i + 1) * sub_bits, nbits);
+            dfd_jpeg_decode_sub<true>(h, words.data(), nwords, used[i], lim, &nb, &ne, blk0[i], coef.data(), dcdiff.data(), dc_off);
+        }
+    }
+    if (rounds_out) *rounds_out = rounds;
+    if (total < h->total_blocks) { delete h; return DFD_JPEG_ERR_DATA; }
+    // 3. DC prediction chains
+    for (int c = 0; c < h->ncomp; c++) {
+        int acc = 0;
+        const int nbk = h->comp_bw[c] * h->comp_bh[c];
+        for (int i = 0; i < nbk; i++) { acc += dcdiff[dc_off[c] + i]; dcdiff[dc_off[c] + i] = acc; }
+    }
+    // 4. IDCT into component planes
+    std::vector<std::vector<uint8_t>> plane(h->ncomp);
+    for (int c = 0; c < h->ncomp; c++) {
+        const int pw = h->comp_bw[c] * 8, ph = h->comp_bh[c] * 8;
+        plane[c].assign((size_t)pw * ph, 0);
+        for (int by = 0; by < h->comp_bh[c]; by++)
+            for (int bx = 0; bx < h->comp_bw[c]; bx++) {
+                uint8_t o[64];
+                const int index = h->comp_blk0[c] + by * h->comp_bw[c] + bx;
+                dfd_jpeg_idct_block(&coef[(size_t)index * 64], dcdiff[dc_off[c] + dfd_jpeg_dc_seq(h, c, bx, by)], h->qt[c], o);
+                for (int i = 0; i < 64; i++) plane[c][(size_t)(by * 8 + i / 8) * pw + bx * 8 + i % 8] = o[i];
+            }
+    }
+    // 5. up-sampling + colour conversion
+    const int W = h->width, H = h->height;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int Y = plane[0][(size_t)y * h->comp_bw[0] * 8 + x];
+            int r = Y, g = Y, b = Y;
+            if (h->ncomp == 3) {
+                int cc[2];
+                for (int c = 1; c < 3; c++) {
+                    const int cw = (W * h->hs[c] + h->hmax - 1) / h->hmax, chh = (H * h->vs[c] + h->vmax - 1) / h->vmax;
+                    cc[c - 1] = dfd_jpeg_chroma_at(plane[c].data(), h->comp_bw[c] * 8, cw, chh, h->hs[c], h->vs[c], h->hmax, h->vmax, x, y);
+                }
+                dfd_jpeg_ycc2rgb(Y, cc[0], cc[1], &r, &g, &b);
+            }
+            out[((size_t)y * W + x) * 3] = (uint8_t)b; out[((size_t)y * W + x) * 3 + 1] = (uint8_t)g; out[((size_t)y * W + x) * 3 + 2] = (uint8_t)r;
+        }
+    delete h;
+    return 0;
+}
+}

@@ -31,3 +31,19 @@ def test_gemm_tiny_and_ragged(eng):
     for M in (1, 7, 127, 128, 129, 300):
         err = eng.gemm_selftest(M, 96, 16, 1, 0)
         assert 0 <= err < 2e-2, (M, err)
+
+
+@pytest.mark.parametrize("N,K", LAYERS + [(32, 32)])
+def test_gemm_tf32x3_layer_shapes(eng, N, K):
+    """3xTF32 tensor-core GEMM (csrc/gemm_tf32x3.cu, the fp32 accuracy mode) against an fp64-accumulated reference on the
+    same fp32 operands: the error must be fp32-rounding sized (a single tf32 product would be ~5e-4), for every 1x1-conv
+    shape, ragged M, residual and SE-gated operands."""
+    for M, act, mode in ((12544, 1, 0), (49 * 5, 0, 1), (128 * 148 * 2 + 77, 1, 1), (49 * 37, 0, 2), (12544, 0, 3)):
+        err, _ = eng.gemm_tf32_selftest(M, N, K, act, mode)
+        assert 0 <= err < 4e-6, (M, N, K, act, mode, err)
+
+
+def test_gemm_tf32x3_tiny_and_ragged(eng):
+    for M in (1, 7, 127, 128, 129, 300):
+        err, _ = eng.gemm_tf32_selftest(M, 96, 16, 1, 0)
+        assert 0 <= err < 4e-6, (M, err)
