@@ -5,9 +5,14 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
 A step = one pass of the whole per-frame hot path (six forensic signals, face-crop preparation,
-EfficientNet-B0 bf16, sigmoid + heuristics, vote-input selection, 10-frame vote) over one 1280x720
+EfficientNet-B0, sigmoid + heuristics, vote-input selection, 10-frame vote) over one 1280x720
 frame from each of S=256 streams on every GPU (weak scaling), one synthetic face box per frame,
 plus -- for N>1 -- the NCCL gather of the per-stream verdict records.  Prints ONE JSON line.
+
+Default classifier precision: fp32 accuracy mode on the tensor cores (3xTF32), the mode that meets the
+reference-parity gate (|dp| <= 1e-4; measured 7e-6).  bf16 is reported beside it (`other_configs`).
+`value`: frames resident in HBM.  `e2e`: the /analyze wire format -- JPEG streams in pinned host memory ->
+H2D -> device JPEG decode -> path -> D2H of the verdict records (`e2e_raw`: the same with raw frames).
 """
 import argparse
 import json
@@ -41,8 +46,11 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def make_inputs(n_streams, n_sets, seed):
-    """n_sets x n_streams synthetic 720p BGR frames in pinned host memory + one face box per frame."""
+def make_inputs(n_streams, n_sets, seed, jpeg=False):
+    """n_sets x n_streams synthetic 720p BGR frames in pinned host memory + one face box per frame.
+    jpeg=True: the frames are what cv2.imdecode returns for their JPEG streams (quality 85, 4:2:0 -- the /analyze wire
+    format), and the streams are returned as well, so that `value` (resident frames) and `e2e` (JPEG ingest) run the
+    path on identical pixels."""
     rng = np.random.RandomState(seed)
     bases = []
     for fam in synth.FAMILIES:
@@ -59,7 +67,18 @@ def make_inputs(n_streams, n_sets, seed):
             jit = rng.randint(-2, 3, size=(H, W, 1)).astype(np.int16)
             fn[k, s] = np.clip(b.astype(np.int16) + jit, 0, 255).astype(np.uint8)
     boxes = np.stack([synth.make_boxes(n_streams, H, W, rng, lo=96, hi=400) for _ in range(n_sets)])
-    return frames, boxes
+    if not jpeg:
+        return frames, boxes
+    import cv2
+    streams = []
+    for k in range(n_sets):
+        row = []
+        for s in range(n_streams):
+            ok, enc = cv2.imencode(".jpg", fn[k, s], [cv2.IMWRITE_JPEG_QUALITY, 85])
+            fn[k, s] = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+            row.append(enc.tobytes())
+        streams.append(row)
+    return frames, boxes, streams
 
 
 class ClockSampler:
@@ -106,8 +125,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_pipeline(frames, boxes, sd, n_threads):
-    """The reference's CPU path (oracle port) over frames[t][s]: returns frames processed."""
+def cpu_pipeline(frames, boxes, sd, n_threads, streams=None):
+    """The reference's CPU path (oracle port) over frames[t][s]: returns frames processed.  With `streams` the frame is
+    first decoded from its JPEG stream with cv2.imdecode, as /analyze does (backend_server.py:140-142)."""
     import cv2
     from oracle import effnet as oeff, faceprep as ofp, forensics as ofor, tracker as otr
     torch.set_num_threads(n_threads)
@@ -118,7 +138,7 @@ def cpu_pipeline(frames, boxes, sd, n_threads):
     done = 0
     for t in range(n_sets):
         for s in range(n_streams):
-            f = frames[t, s]
+            f = frames[t, s] if streams is None else cv2.imdecode(np.frombuffer(streams[t][s], np.uint8), cv2.IMREAD_COLOR)
             r = analyzers[s].analyze(f) if t % 3 == 0 else analyzers[s].analyze_fast(f)
             x = ofp.prepare(f, boxes[t, s])
             p = float(torch.sigmoid(oeff.forward(x, sd)).item())
@@ -137,21 +157,22 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = 8                                      # frames per step
     sd = synth.make_state_dict()
-    frames, boxes = make_inputs(sample, 3, seed=1234)
+    frames, boxes, streams = make_inputs(sample, 3, seed=1234, jpeg=True)
     fn = frames.numpy()
     for _ in range(args.warmup):
-        cpu_pipeline(fn[:1], boxes[:1], sd, cores)
+        cpu_pipeline(fn[:1], boxes[:1], sd, cores, streams[:1])
     t0 = time.perf_counter()
     n = 0
     for k in range(args.steps):
-        n += cpu_pipeline(fn[k % 3:k % 3 + 1], boxes[k % 3:k % 3 + 1], sd, cores)
+        n += cpu_pipeline(fn[k % 3:k % 3 + 1], boxes[k % 3:k % 3 + 1], sd, cores, streams[k % 3:k % 3 + 1])
     dt = time.perf_counter() - t0
     v = n / dt
     _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"720p full per-frame path on CPU, {sample} frames/step, 1 face/frame, fp32 bs=1"},
+        "config": {"workload": f"720p full per-frame path on CPU from JPEG streams (cv2.imdecode + 6 forensic signals + face prep + "
+                               f"EfficientNet-B0 fp32 bs=1 + vote), {sample} frames/step, 1 face/frame"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} frames/step x {args.steps} steps of the bench workload"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -204,7 +225,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS)
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="fp32", choices=["bf16", "fp32"],
+                    help="classifier precision: fp32 = 3xTF32 tensor-core accuracy mode (parity-green, default), bf16 = fastest")
+    ap.add_argument("--sustain", type=float, default=5.0, help="seconds of back-to-back steps for the sustained-rate figure (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", dest="graphs", action="store_false", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
@@ -237,14 +260,26 @@ def main():
     sd = synth.make_state_dict()
     eng = Engine(device=local, max_streams=S, max_batch=S, max_crop=512, detection_threshold=0.55)
     eng.load_state_dict(sd)
-    host_frames, boxes = make_inputs(S, n_sets, seed=1234 + rank)
+    host_frames, boxes, jpeg_streams = make_inputs(S, n_sets, seed=1234 + rank, jpeg=True)
+    jpeg_packed = [eng.pack_jpegs(jpeg_streams[k]) for k in range(n_sets)]     # pinned host buffers + offsets (the wire format)
     dev_frames = host_frames.to(dev)                              # resident inputs for `value`
     dev_boxes = [torch.from_numpy(boxes[k]).to(dev) for k in range(n_sets)]
     sids = torch.arange(S, dtype=torch.int32, device=dev)
     box_frame = torch.arange(S, dtype=torch.int32, device=dev)
     full_flags = [torch.full((S,), int(k == 0), dtype=torch.uint8, device=dev) for k in range(3)]
-    rec = torch.empty(S * RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(world * S * RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev) if world > 1 else None
+    # N > 1: streams are sharded by owner(stream) = id mod world (sharding.StreamSharder); this rank's engine numbers them
+    # by local slot.  The vote kernel writes its records straight into the sharder's preallocated send buffer.
+    sharder = None
+    if world > 1:
+        from dfd_b200.sharding import StreamSharder
+        sharder = StreamSharder(rank, world)
+        global_ids = np.arange(world * S)
+        own_idx, own_slots = sharder.select(global_ids)
+        assert len(own_idx) == S and list(own_slots) == list(range(S))
+        rec, gathered = sharder.make_buffers(S, dev)
+    else:
+        rec = torch.empty(S * RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        gathered = None
     rec_host = torch.empty(S * RECORD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # L2 flush buffer (> 126 MB)
 
@@ -262,7 +297,7 @@ def main():
             eng.analyze_batch(frames_dev, sids, full_flags[i % 3], dev_boxes[i % n_sets], box_frame, dtype=args.dtype,
                               records_out=rec)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, rec)              # NCCL verdict gather (config 4)
+            sharder.gather_records(rec, S, out=gathered)            # NCCL verdict gather (config 4), no staging copy
 
     def barrier():
         if world > 1:
@@ -273,6 +308,18 @@ def main():
     for i in range(Wm):
         step(i, dev_frames[i % n_sets])
     barrier()
+    gather_check = None
+    if world > 1:
+        # every rank must hold every stream's record: world x S distinct global ids, this rank's own segment identical to
+        # what its engine wrote, all streams at the same frame count
+        allrec = sharder.globalize(gathered, S)
+        mine = Engine.records_to_numpy(rec)
+        seg = allrec[np.isin(allrec["stream_id"], global_ids[own_idx])]
+        ok = (len(allrec) == world * S and sorted(allrec["stream_id"].tolist()) == list(range(world * S))
+              and np.array_equal(np.sort(seg["vote_input"]), np.sort(mine["vote_input"]))
+              and len(set(allrec["frame_count"].tolist())) == 1)
+        gather_check = bool(ok)
+        assert ok, "gathered verdict records are inconsistent"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -303,13 +350,17 @@ def main():
     consumed = [torch.cuda.Event() for _ in range(2)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def e2e_loop(n, base):
+    def e2e_loop(n, base, jpeg=True):
         for i in range(n):
             b = i % 2
             with torch.cuda.stream(copy_stream):
                 if i >= 2:
                     copy_stream.wait_event(consumed[b])
-                stage[b].copy_(host_frames[(base + i) % n_sets], non_blocking=True)
+                if jpeg:      # host: header parsing; H2D of the streams; device: unstuff / Huffman / IDCT / colour -> stage[b]
+                    pk, off = jpeg_packed[(base + i) % n_sets]
+                    eng.decode_jpeg_batch(pk, off, H, W, out=stage[b])
+                else:
+                    stage[b].copy_(host_frames[(base + i) % n_sets], non_blocking=True)
                 copied[b].record(copy_stream)
             with torch.cuda.stream(comp_stream):
                 comp_stream.wait_event(copied[b])
@@ -318,20 +369,58 @@ def main():
                 rec_host.copy_(rec, non_blocking=True)
         comp_stream.synchronize()
 
-    e2e_loop(3, 0)
-    barrier()
-    with torch.cuda.stream(copy_stream):
-        e0.record(copy_stream)
-    e2e_loop(K, 3)
-    with torch.cuda.stream(comp_stream):
-        e1.record(comp_stream)
-    barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    def timed_e2e(jpeg):
+        e2e_loop(3, 0, jpeg)
+        barrier()
+        with torch.cuda.stream(copy_stream):
+            e0.record(copy_stream)
+        e2e_loop(K, 3, jpeg)
+        with torch.cuda.stream(comp_stream):
+            e1.record(comp_stream)
+        barrier()
+        t_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return t_
+
+    ms_e2e = timed_e2e(True)                 # the /analyze wire format: JPEG streams in, verdict records out
     e2e_value = world * S * K / (float(ms_e2e.item()) / 1e3)
-    h2d = S * H * W * 3
+    ms_raw = timed_e2e(False)                # raw decoded frames in (2.76 MB each): PCIe-bound
+    e2e_raw_value = world * S * K / (float(ms_raw.item()) / 1e3)
+    h2d = int(np.mean([int(off[-1]) for _, off in jpeg_packed]))      # JPEG bytes per step
+    h2d_raw = S * H * W * 3
     d2h = S * RECORD_DTYPE.itemsize
+    # JPEG decode alone (device time of the ingest stage, streams already in pinned memory)
+    dec0, dec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dec0.record()
+    for i in range(6):
+        eng.decode_jpeg_batch(jpeg_packed[i % n_sets][0], jpeg_packed[i % n_sets][1], H, W, out=stage[0])
+    dec1.record()
+    torch.cuda.synchronize()
+    ms_decode = dec0.elapsed_time(dec1) / 6
+
+    # ---- sustained rate: back-to-back steps for >= args.sustain seconds (the timed region above is ~0.1 s) ----
+    sustained = None
+    if args.sustain > 0:
+        barrier()
+        s_sampler = ClockSampler(local)
+        if rank == 0:
+            s_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        est = max(ms / K, 1e-3)
+        n_s = max(int(args.sustain * 1e3 / est), K)
+        s0.record()
+        for i in range(n_s):
+            step(i, dev_frames[i % n_sets])
+        s1.record()
+        barrier()
+        t_s = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        sc = s_sampler.stop() if rank == 0 else None
+        sustained = {"value": world * S * n_s / (float(t_s.item()) / 1e3), "unit": UNIT, "steps": n_s,
+                     "seconds": float(t_s.item()) / 1e3, "clocks": sc}
 
     # ---- per-kernel device times (3 extra steps, one event after every launch) -> roofline ----
     roof, kernels, functions = None, [], []
@@ -376,12 +465,14 @@ def main():
         tf_ = fn[top_fn]
         gbs = tf_["bytes"] / tf_["ms"] / 1e6
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")      # ncu dram bytes per step for that kernel (committed)
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            if tj.get("kernel") == top_fn:
-                traffic = tj.get("dram_bytes_per_launch")
+        for tname in ("traffic_r02.json", "traffic_r01.json"):          # ncu dram bytes per launch of that kernel (committed)
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if traffic is None and os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                ent = tj.get(top_fn) if isinstance(tj.get(top_fn), dict) else (tj if tj.get("kernel") == top_fn else None)
+                if ent:
+                    traffic = ent.get("dram_bytes_per_launch")
         roof = {"bound": "hbm", "kernel": top_fn, "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
                 "frac": round(gbs / hbm, 4), "traffic": traffic, "peak_source": how,
                 "launches_per_step": tf_["launches"] // 3,
@@ -471,11 +562,43 @@ def main():
                 torch.cuda.synchronize()
                 return (t_all - a.elapsed_time(b)) / reps
 
-            # config 2: EfficientNet-B0 classifier only, 224x224 bf16, batch 256
+            # config 2: EfficientNet-B0 classifier only, 224x224, batch 256 -- bf16 (BASELINE config 2) and the fp32 accuracy mode
             crops = eng.face_prep_batch(dev_frames[0], dev_boxes[0], box_frame, dtype="bf16")
             ms2 = graph_time(lambda: eng.effnet_forward(crops), 10)
             side["config2_classifier_bf16_b256"] = {"crops_per_sec": S / ms2 * 1e3, "ms": ms2,
-                                                    "hbm_layer_granular_bound_crops_per_sec": hbm * 1e9 / 27.42e6}
+                                                    "hbm_layer_granular_bound_crops_per_sec": hbm * 1e9 / 27.42e6,
+                                                    "parity": "bf16 gate (5e-3) NOT met on the synthetic weights: max |dp| 0.06, "
+                                                              "0 / 1920 verdicts and 0.26 % of votes differ (tests/test_gpu_configs.py)"}
+            crops32 = eng.face_prep_batch(dev_frames[0], dev_boxes[0], box_frame, dtype="fp32")
+            ms2f = graph_time(lambda: eng.effnet_forward(crops32), 10)
+            side["config2_classifier_fp32_3xtf32_b256"] = {"crops_per_sec": S / ms2f * 1e3, "ms": ms2f,
+                                                           "hbm_layer_granular_bound_crops_per_sec": hbm * 1e9 / 54.84e6,
+                                                           "parity": "fp32 gate (1e-4) met: max |dp| 7e-6, verdicts identical"}
+            del crops, crops32
+            # the whole path in the OTHER precision (device-resident frames, one graph replay per step)
+            other = "bf16" if args.dtype == "fp32" else "fp32"
+            go = eng.capture_step(dev_frames[0], sids, full_flags[0], dev_boxes[0], box_frame, dtype=other, records_out=rec)
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            go.replay()
+            a_.record()
+            for _ in range(10):
+                flush.zero_()
+                go.replay()
+            b_.record()
+            torch.cuda.synchronize()
+            t_all = a_.elapsed_time(b_)
+            a_.record()
+            for _ in range(10):
+                flush.zero_()
+            b_.record()
+            torch.cuda.synchronize()
+            mso = (t_all - a_.elapsed_time(b_)) / 10
+            side[f"full_path_{other}"] = {"frames_per_sec": S / mso * 1e3, "ms": mso}
+            side["jpeg_decode_720p"] = {"frames_per_sec": S / ms_decode * 1e3, "ms_per_step": ms_decode,
+                                        "mean_stream_bytes": h2d // S,
+                                        "how": "dfd_decode_jpeg_batch alone (host header parsing + H2D of the streams + unstuff / "
+                                               "Huffman / IDCT / colour kernels), 256 frames per call"}
             # config 3: six forensic signals on 1080p frames, batch 64 (all frames "full")
             f1080 = torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, device=dev)
             sid64 = torch.arange(64, dtype=torch.int32, device=dev)
@@ -508,27 +631,37 @@ def main():
         n_sample = 48
         fn = host_frames.numpy()[:, :n_sample // 3]
         t0 = time.perf_counter()
-        n = cpu_pipeline(fn, boxes[:, :n_sample // 3], sd, cores)
+        n = cpu_pipeline(fn, boxes[:, :n_sample // 3], sd, cores, [row[:n_sample // 3] for row in jpeg_streams])
         dt = time.perf_counter() - t0
         cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} frames (3 consecutive frames of {n_sample // 3} streams) of the bench workload, fp32 bs=1"}
+               "sample": f"{n} frames (3 consecutive frames of {n_sample // 3} streams) of the bench workload from their JPEG streams "
+                         f"(cv2.imdecode + path), fp32 bs=1"}
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
+            "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": f"720p full per-frame path (6 forensic signals + face prep + EfficientNet-B0 "
-                                   f"{args.dtype} + vote), {S} streams/GPU, 1 face box/frame, full/fast/fast cadence",
+                                   f"{'fp32 accuracy mode (3xTF32 tensor cores)' if args.dtype == 'fp32' else 'bf16'} + vote), "
+                                   f"{S} streams/GPU, 1 face box/frame, full/fast/fast cadence",
+                       "classifier_mode": args.dtype,
+                       "parity": ("fp32 gate 1e-4 met (max |dp| 7e-6, verdicts bit-identical over 1920 frames)" if args.dtype == "fp32"
+                                  else "bf16 gate 5e-3 NOT met on the synthetic weights (max |dp| 0.06)"),
                        "frames_per_step_per_gpu": S, "frame": "1280x720 BGR u8", "l2": "inputs larger than L2 "
                        "(707 MB of frames per step, 3 rotating sets)", "weights": "fixed-seed random init (synth.make_state_dict)",
                        "submission": "one CUDA graph replay per step" if graphs is not None else "host launches",
                        "collective": "nccl all_gather of 72-B verdict records" if world > 1 else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(ms_e2e.item()) / K, "h2d_gbs_per_gpu": round(h2d / (float(ms_e2e.item()) / K) / 1e6, 1),
-                    "note": "pinned host frames, H2D double-buffered on a copy stream; bound by the PCIe Gen5 x16 link "
-                            "(2.76 MB of raw frame per frame), not by the kernels",
+                    "ms_per_step": float(ms_e2e.item()) / K, "h2d_gbs_per_gpu": round(h2d / (float(ms_e2e.item()) / K) / 1e6, 2),
+                    "ingest": "JPEG quality 85 4:2:0 streams (the /analyze wire format) in pinned host memory -> dfd_decode_jpeg_batch "
+                              "(host header parsing, H2D, device Huffman / IDCT / colour, bit-exact with cv2.imdecode) -> "
+                              "dfd_analyze_batch -> D2H of the 72-B records; ingest of step i+1 overlaps the path of step i",
                     "cpu_affinity": (f"rank 0 bound to the {len(numa)} CPUs local to its GPU" if numa else "unbound")},
+            "e2e_raw": {"value": e2e_raw_value, "unit": UNIT, "h2d_bytes_per_step": h2d_raw, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": float(ms_raw.item()) / K, "h2d_gbs_per_gpu": round(h2d_raw / (float(ms_raw.item()) / K) / 1e6, 1),
+                        "note": "the same with raw decoded frames in pinned host memory (2.76 MB per frame): PCIe-bound"},
+            "sustained": sustained, "gather_check": gather_check,
             "gpu_launches": int(launches), "crops_per_sec": value, "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu, "latency": latency, "other_configs": side, "top_kernels": functions[:6],
         }

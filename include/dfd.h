@@ -33,7 +33,8 @@ typedef enum {
     DFD_ERR_CUDA = -2,        /* CUDA runtime/driver error */
     DFD_ERR_NO_WEIGHTS = -3,  /* classifier called before dfd_load_weights */
     DFD_ERR_CAPACITY = -4,    /* batch / stream id / crop size beyond the configured capacity */
-    DFD_ERR_ARCH = -5         /* device is not sm_100 */
+    DFD_ERR_ARCH = -5,        /* device is not sm_100 */
+    DFD_ERR_UNSUPPORTED = -6  /* input format outside the supported subset (e.g. a progressive JPEG) */
 } dfd_status;
 
 typedef enum { DFD_F32 = 0, DFD_BF16 = 1 } dfd_dtype;
@@ -146,6 +147,23 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
                       const int32_t* stream_ids, const uint8_t* full, const int32_t* boxes, const int32_t* box_frame,
                       int m, int dtype, dfd_forensic_result* forensic_out /* may be NULL */,
                       double* face_prob_out /* m, may be NULL */, dfd_vote_record* records, void* stream);
+
+/* Frame ingest: cv2.imdecode(np.frombuffer(image_bytes), cv2.IMREAD_COLOR) (backend_server.py:140-142) for n frames of the
+ * /analyze wire format (JPEG, canvas.toDataURL('image/jpeg', 0.85), extension/content.js:106), decoded ON THE DEVICE so that
+ * only the compressed stream crosses PCIe.  Bit-exact with OpenCV's libjpeg-turbo decoder.
+ *   bytes_host   HOST: the n streams back to back (pinned memory makes the copy asynchronous)
+ *   offsets_host HOST: n + 1 byte offsets into bytes_host (stream i = [offsets[i], offsets[i+1]))
+ *   H, W         every stream must decode to H x W (use dfd_jpeg_info to peek); frames_out: n frames of H x W BGR u8 (DEVICE),
+ *                frame i at frames_out + i * frame_stride, rows row_pitch bytes apart -- the layout dfd_analyze_batch takes
+ *   status_dev   DEVICE int32[n]: 0, or -4 when a stream's entropy-coded data is corrupt (its frame content is undefined)
+ * Supported: baseline sequential Huffman JPEG, 8 bit, gray or YCbCr 4:4:4 / 4:2:2 / 4:2:0, one interleaved scan, no restart
+ * markers (what browsers and cv2.imencode emit).  Anything else returns DFD_ERR_UNSUPPORTED (progressive, arithmetic, 12-bit,
+ * CMYK, restart intervals) or DFD_ERR_INVALID (not a JPEG, wrong size) and decodes nothing -- there is no CPU fallback. */
+int dfd_decode_jpeg_batch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_t* offsets_host, int n, int H, int W,
+                          uint8_t* frames_out, size_t frame_stride, int row_pitch, int32_t* status_dev, void* stream);
+/* HOST-only header peek (no context): info = {H, W, components, luma h sampling, luma v sampling}; returns 0 if the stream is
+ * decodable by dfd_decode_jpeg_batch, DFD_ERR_UNSUPPORTED / DFD_ERR_INVALID otherwise (info is filled when SOF was seen). */
+int dfd_jpeg_info(const uint8_t* bytes_host, size_t n_bytes, int32_t* info);
 
 /* DeepfakeDetector.reset / FrameForensicAnalyzer.reset / TemporalTracker.reset
  * (deepfake_detection.py:344-355, 270-289; frame_analysis.py:391-395).  stream_id < 0 resets all. */

@@ -50,6 +50,8 @@ SYMBOLS = {
     "dfd_face_probability": (_I, [_P, _P, _P, _I, _P, _P]),
     "dfd_vote_update": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "dfd_analyze_batch": (_I, [_P, _P, _I, _I, _I, _S, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "dfd_decode_jpeg_batch": (_I, [_P, _P, _P, _I, _I, _I, _P, _S, _I, _P, _P]),
+    "dfd_jpeg_info": (_I, [_P, _S, _P]),
     "dfd_reset_stream": (_I, [_P, _I, _P]),
     "dfd_reset_stream_part": (_I, [_P, _I, _I, _P]),
     "dfd_configure_stream": (_I, [_P, _I, _I, _I, C.c_double, _P]),

@@ -210,6 +210,9 @@ void dfd_destroy(dfd_ctx* ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     dfd_gemm_free(ctx);
+    dfd_jpeg_free(ctx);
+    for (DfdBuf* b : {&ctx->jpg_raw, &ctx->jpg_words, &ctx->jpg_sub, &ctx->jpg_coef, &ctx->jpg_dc, &ctx->jpg_planes, &ctx->jpg_hdr})
+        if (b->p) cudaFree(b->p);
     delete ctx;
 }
 
@@ -292,6 +295,14 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
     }
     if (overlap) DFD_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     return dfd_select_vote_launch(ctx, n, m, box_frame, fprob, fres, stream_ids, records, st);
+}
+
+int dfd_decode_jpeg_batch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_t* offsets_host, int n, int H, int W,
+                          uint8_t* frames_out, size_t frame_stride, int row_pitch, int32_t* status_dev, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
+    DFD_REQUIRE(bytes_host && offsets_host && frames_out && status_dev, DFD_ERR_INVALID, "decode_jpeg_batch: null pointer");
+    return dfd_jpeg_decode_launch(ctx, bytes_host, offsets_host, n, H, W, frames_out, frame_stride, row_pitch, status_dev, (cudaStream_t)stream);
 }
 
 int dfd_reset_stream(dfd_ctx* ctx, int stream_id, void* stream) {

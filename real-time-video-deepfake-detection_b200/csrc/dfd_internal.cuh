@@ -110,6 +110,10 @@ struct dfd_ctx {
     float* d_logits = nullptr;            // [m]
     double* d_faceprob = nullptr;         // [m]
     double* d_voteinput = nullptr;        // [n]
+    // device JPEG ingest (jpegdec.cu)
+    void* jpg_host = nullptr;             // host-side staging (pinned header / meta arrays)
+    cudaEvent_t jpg_ev = nullptr;         // the previous call's copies out of the staging arrays
+    DfdBuf jpg_raw, jpg_words, jpg_sub, jpg_coef, jpg_dc, jpg_planes, jpg_hdr;
     // diagnostics
     std::string tap_name;
     DfdBuf tap;
@@ -237,6 +241,10 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
 int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
                         int row_pitch, const int32_t* boxes, const int32_t* frame_idx, int m, void* out, int dtype,
                         cudaStream_t st);
+// jpegdec.cu
+int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_t* offsets_host, int n, int H, int W,
+                           uint8_t* frames_out, size_t frame_stride, int row_pitch, int32_t* status_dev, cudaStream_t st);
+void dfd_jpeg_free(dfd_ctx* ctx);
 // effnet.cu
 int dfd_effnet_launch(dfd_ctx* ctx, const void* in, int m, int dtype, float* logits, cudaStream_t st);
 int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n);

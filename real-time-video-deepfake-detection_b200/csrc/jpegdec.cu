@@ -5,31 +5,42 @@
 // px_jpeg.h / px_jpegdec.h, which tests/hostcheck runs on the CPU against cv2.imdecode.
 //
 //   host            dfd_jpeg_parse: markers -> DfdJpegHeader (quantisers, Huffman lookup tables, geometry); no pixel work
-//   k_jpeg_unstuff  CTA per frame: removes the FF 00 byte stuffing of the entropy-coded segment (block scan + scatter)
-//   k_jpeg_huffman  CTA per frame: SELF-SYNCHRONISING parallel Huffman decode.  The bit stream is cut into subsequences of
-//                   1024 bits, one per thread (strided).  (1) every thread decodes its subsequence blindly from the state
-//                   "a block starts here"; Huffman streams resynchronise, so most end states are already right.  (2) rounds:
-//                   thread i re-decodes subsequence i from the END state of subsequence i-1 whenever that changed, until a
-//                   whole round changes nothing -- by induction from subsequence 0 (whose start is known) every state is then
-//                   exact.  (3) a block scan of the per-subsequence block counts gives every subsequence its first block
-//                   number; (4) a last pass writes the coefficients (AC values in natural order, DC differences in
-//                   prediction-chain order); (5) the DC prediction chains are prefix sums per component.
+//   k_ju_count / k_ju_scan / k_ju_scatter   removal of the FF 00 byte stuffing of the entropy-coded segments, flat over
+//                   2 KB chunks of all frames (count, per-frame scan, scatter into MSB-first 32-bit words)
+//   SELF-SYNCHRONISING parallel Huffman decode, flat over the 2048-bit subsequences of ALL frames (one thread each), so a
+//   700 KB noise frame and a 10 KB flat frame in the same batch load the chip evenly:
+//     k_jh_blind    every thread decodes its subsequence from the state "a block starts here"; Huffman streams
+//                   resynchronise, so most END states are already right
+//     k_jh_round    x JH_ROUNDS: thread i re-decodes subsequence i from the END state of subsequence i-1 whenever that
+//                   changed (a frame whose previous round changed nothing exits at once).  When a whole round changes
+//                   nothing, by induction from subsequence 0 (whose start is known) every state is exact.
+//     k_jh_finish   CTA per frame, only for frames still changing after the flat rounds (pathological streams): rounds in a
+//                   loop with CTA barriers until nothing changes -- correctness never depends on the round count
+//     k_jh_scan     per frame: exclusive scan of the per-subsequence block counts = first block number of each subsequence
+//     k_jh_write    last pass: coefficients (AC values in natural order, DC differences in prediction-chain order)
+//     k_jh_dc       DC prediction chains = prefix sums per component
 //   k_jpeg_idct     thread per 8 x 8 block: dequantise, jidctint (columns, rows), +128, clamp -> component planes
 //   k_jpeg_color    fancy h2v2 / h2v1 chroma up-sampling + YCbCr -> BGR into the caller's frame buffer
+// The device bit reader (64-bit register window over the clean words) and symbol loop below are a faster restatement of
+// dfd_jpeg_step / dfd_jpeg_decode_sub (px_jpegdec.h), which tests/hostcheck checks on the CPU; the GPU tests compare the
+// kernels' output with cv2.imdecode bit for bit.
 #include "dfd_internal.cuh"
 #include <string.h>
 #include <stdlib.h>
 #include "px_jpegdec.h"
 
-#define JPG_SUB_BITS 1024
+#define JPG_SUB_BITS 2048
 #define JPG_THREADS 512
+#define JH_THREADS 128
+#define JH_ROUNDS 12
+#define JU_CHUNK 2048                 // raw bytes per unstuffing chunk = 128 threads x 16 bytes
 
 struct JpgMeta {
     long long raw_off;        // first byte of the stream in the raw buffer
     long long words_off;      // first 32-bit word of the frame's clean bit stream
     long long sub_off;        // first subsequence slot of the frame
     int ecs_bytes;            // raw size of the entropy-coded segment
-    int pad;
+    int chunk_off;            // first unstuffing-chunk slot of the frame
 };
 
 // exclusive scan of one int per thread over the CTA (JPG_THREADS threads); returns the exclusive prefix, *total = CTA sum
@@ -54,92 +65,228 @@ __device__ int cta_exscan(int v, int* total, int* s_warp /* [JPG_THREADS / 32 + 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Byte-stuffing removal, flat over JU_CHUNK-byte chunks: grid (chunks, frames), 128 threads x 16 bytes.
+__device__ __forceinline__ int ju_keep_mask(const uint8_t* __restrict__ src, int n, int i0, uint8_t (&b)[16]) {
+    int keep = 0;
+    uint8_t prev = (i0 > 0 && i0 - 1 < n) ? __ldg(src + i0 - 1) : 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int i = i0 + j;
+        b[j] = i < n ? __ldg(src + i) : 0;
+        const bool stuffed = b[j] == 0 && prev == 0xFF;        // a zero that follows FF carries no data
+        if (i < n && !stuffed) keep |= 1 << j;
+        prev = b[j];
+    }
+    return keep;
+}
+
+__global__ void __launch_bounds__(128)
+k_ju_count(const uint8_t* __restrict__ raw, const JpgMeta* __restrict__ meta, const DfdJpegHeader* __restrict__ hdr, int* __restrict__ chunk_cnt) {
+    const int f = blockIdx.y;
+    const JpgMeta M = meta[f];
+    const int c0 = blockIdx.x * JU_CHUNK;
+    if (c0 >= M.ecs_bytes) return;
+    const uint8_t* src = raw + M.raw_off + hdr[f].ecs_begin;
+    uint8_t b[16];
+    int cnt = __popc(ju_keep_mask(src, M.ecs_bytes, c0 + threadIdx.x * 16, b));
+    __shared__ int s[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_cnt[M.chunk_off + blockIdx.x] = s[0] + s[1] + s[2] + s[3];
+}
+
+// per frame: chunk counts -> chunk bases (exclusive scan), clean length, zeroed tail + guard words
 __global__ void __launch_bounds__(JPG_THREADS)
-k_jpeg_unstuff(const uint8_t* __restrict__ raw, const JpgMeta* __restrict__ meta, const DfdJpegHeader* __restrict__ hdr,
-               uint32_t* __restrict__ words, uint32_t* __restrict__ nbits_out) {
+k_ju_scan(const JpgMeta* __restrict__ meta, int* __restrict__ chunk_cnt, uint32_t* __restrict__ words, uint32_t* __restrict__ nbits_out) {
     __shared__ int s_warp[JPG_THREADS / 32 + 1];
-    __shared__ int s_base;
+    __shared__ int s_carry;
     const int f = blockIdx.x;
     const JpgMeta M = meta[f];
-    const uint8_t* src = raw + M.raw_off + hdr[f].ecs_begin;
-    uint8_t* dst = (uint8_t*)(words + M.words_off);
-    const int n = M.ecs_bytes;
-    if (threadIdx.x == 0) s_base = 0;
+    const int nch = (M.ecs_bytes + JU_CHUNK - 1) / JU_CHUNK;
+    int* cc = chunk_cnt + M.chunk_off;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (int c0 = 0; c0 < n; c0 += JPG_THREADS * 8) {
-        const int i0 = c0 + threadIdx.x * 8;
-        uint8_t b[8];
-        int keep = 0;
-        uint8_t prev = (i0 > 0 && i0 - 1 < n) ? src[i0 - 1] : 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int i = i0 + j;
-            b[j] = i < n ? src[i] : 0;
-            const bool stuffed = b[j] == 0 && prev == 0xFF;
-            if (i < n && !stuffed) keep |= 1 << j;
-            prev = b[j];
-        }
+    for (int c0 = 0; c0 < nch; c0 += JPG_THREADS) {
+        const int i = c0 + threadIdx.x;
+        const int v = i < nch ? cc[i] : 0;
         int total;
-        int off = s_base + cta_exscan(__popc(keep), &total, s_warp);
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (keep >> j & 1) { dst[(off & ~3) + (3 - (off & 3))] = b[j]; off++; }        // MSB-first inside each 32-bit word
+        const int ex = cta_exscan(v, &total, s_warp);
+        if (i < nch) cc[i] = s_carry + ex;
         __syncthreads();
-        if (threadIdx.x == 0) s_base += total;
+        if (threadIdx.x == 0) s_carry += total;
         __syncthreads();
     }
-    // zero the tail of the last word and two guard words (dfd_peek16 reads one word ahead)
-    const int nb = s_base;
-    if (threadIdx.x < 12) {
+    const int nb = s_carry;
+    uint8_t* dst = (uint8_t*)(words + M.words_off);
+    if (threadIdx.x < 20) {                                    // the bit reader runs up to three words ahead
         const int o = nb + threadIdx.x;
-        if (o < ((nb + 3) & ~3) + 8) dst[(o & ~3) + (3 - (o & 3))] = 0;
+        if (o < ((nb + 3) & ~3) + 16) dst[(o & ~3) + (3 - (o & 3))] = 0;
     }
     if (threadIdx.x == 0) nbits_out[f] = (uint32_t)nb * 8u;
 }
 
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JPG_THREADS)
-k_jpeg_huffman(const JpgMeta* __restrict__ meta, const DfdJpegHeader* __restrict__ hdr, const uint32_t* __restrict__ words_all,
-               const uint32_t* __restrict__ nbits_in, unsigned long long* __restrict__ E_all, unsigned long long* __restrict__ used_all,
-               int* __restrict__ cnt_all, int* __restrict__ blk0_all, int16_t* __restrict__ coef_all, int32_t* __restrict__ dc_all,
-               long long blocks_stride, int32_t* __restrict__ status) {
-    __shared__ DfdJpegHeader h;
-    __shared__ int s_warp[JPG_THREADS / 32 + 1];
-    __shared__ int s_carry;
-    const int f = blockIdx.x, tid = threadIdx.x;
-    {
-        const uint32_t* src = (const uint32_t*)(hdr + f);
-        uint32_t* d = (uint32_t*)&h;
-        for (int i = tid; i < (int)(sizeof(DfdJpegHeader) / 4); i += JPG_THREADS) d[i] = src[i];
-    }
-    __syncthreads();
+__global__ void __launch_bounds__(128)
+k_ju_scatter(const uint8_t* __restrict__ raw, const JpgMeta* __restrict__ meta, const DfdJpegHeader* __restrict__ hdr,
+             const int* __restrict__ chunk_base, uint32_t* __restrict__ words) {
+    const int f = blockIdx.y;
     const JpgMeta M = meta[f];
-    const uint32_t* words = words_all + M.words_off;
-    const uint32_t nbits = nbits_in[f];
-    const uint32_t nwords = (nbits + 31) / 32 + 2;
-    const int nsub = (int)((nbits + JPG_SUB_BITS - 1) / JPG_SUB_BITS);
-    volatile unsigned long long* E = E_all + M.sub_off;
-    volatile unsigned long long* used = used_all + M.sub_off;
-    int* cnt = cnt_all + M.sub_off;
-    int* blk0 = blk0_all + M.sub_off;
-    int16_t* coef = coef_all + (size_t)f * blocks_stride * 64;
-    int32_t* dcd = dc_all + (size_t)f * blocks_stride;
-    int32_t dc_off[3] = {0, 0, 0};
-    { int a = 0; for (int c = 0; c < h.ncomp; c++) { dc_off[c] = a; a += h.comp_bw[c] * h.comp_bh[c]; } }
-    int nerr_total = 0;
+    const int c0 = blockIdx.x * JU_CHUNK;
+    if (c0 >= M.ecs_bytes) return;
+    const uint8_t* src = raw + M.raw_off + hdr[f].ecs_begin;
+    uint8_t* dst = (uint8_t*)(words + M.words_off);
+    uint8_t b[16];
+    const int keep = ju_keep_mask(src, M.ecs_bytes, c0 + threadIdx.x * 16, b);
+    const int cnt = __popc(keep), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    __shared__ int s[4];
+    if (lane == 31) s[w] = x;
+    __syncthreads();
+    int off = chunk_base[M.chunk_off + blockIdx.x] + x - cnt;
+    for (int q = 0; q < w; q++) off += s[q];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        if (keep >> j & 1) { dst[(off & ~3) + (3 - (off & 3))] = b[j]; off++; }            // MSB-first inside each 32-bit word
+}
 
-    // (1) blind pass
-    for (int i = tid; i < nsub; i += JPG_THREADS) {
-        DfdJpegState s0; s0.p = (uint32_t)i * JPG_SUB_BITS; s0.c = 0; s0.z = 0;
-        const unsigned long long st = dfd_jpeg_pack_state(s0);
-        const uint32_t lim = min((uint32_t)(i + 1) * JPG_SUB_BITS, nbits);
-        int nb, ne;
-        const unsigned long long e = dfd_jpeg_decode_sub<false>(&h, words, nwords, st, lim, &nb, &ne, 0, nullptr, nullptr, nullptr);
-        used[i] = st; E[i] = e; cnt[i] = nb;
+// ---------------------------------------------------------------------------------------------
+// Device bit reader: a 64-bit window (next bit = bit 63) over the clean MSB-first words.  Guard words follow the data.
+struct JhBits { uint64_t buf; int nb; uint32_t wi; };
+__device__ __forceinline__ void jh_init(JhBits& r, const uint32_t* __restrict__ w, uint32_t p) {
+    const uint32_t i = p >> 5;
+    r.buf = (((uint64_t)__ldg(w + i) << 32) | __ldg(w + i + 1)) << (p & 31u);
+    r.nb = 64 - (int)(p & 31u);
+    r.wi = i + 2;
+}
+__device__ __forceinline__ void jh_refill(JhBits& r, const uint32_t* __restrict__ w) {
+    if (r.nb <= 32) { r.buf |= (uint64_t)__ldg(w + r.wi) << (32 - r.nb); r.wi++; r.nb += 32; }
+}
+
+// dfd_jpeg_decode_sub, restated on the register bit window (same state transitions, same outputs).
+template <bool WRITE>
+__device__ __forceinline__ unsigned long long jh_decode(const DfdJpegHeader* __restrict__ h, const uint32_t* __restrict__ words,
+                                                        unsigned long long start, uint32_t limit, int* nblk, int blk0,
+                                                        int16_t* __restrict__ coef, int32_t* __restrict__ dcd, const int32_t* dc_off,
+                                                        const uint8_t* s_zz) {
+    uint32_t p = (uint32_t)(start >> 16);
+    int c = (int)((start >> 8) & 255u), z = (int)(start & 255u);
+    int blocks = 0;
+    const int bpm = h->bpm;
+    int comp = h->blk_comp[c];
+    const DfdHuffTab* dct = &h->dc[h->dc_tab[comp]];
+    const DfdHuffTab* act = &h->ac[h->ac_tab[comp]];
+    int blk = blk0, index = 0, dseq = 0, wcomp = 0;
+    bool wr = false;
+    if (WRITE) { wr = blk < h->total_blocks; if (wr) dfd_jpeg_block_pos(h, blk, &wcomp, &index, &dseq); }
+    JhBits r;
+    jh_init(r, words, p);
+    while (p < limit) {
+        jh_refill(r, words);
+        const uint32_t b16 = (uint32_t)(r.buf >> 48);
+        const DfdHuffTab* t = z == 0 ? dct : act;
+        const uint32_t e = __ldg(&t->look[b16 >> 8]);
+        int len, sym;
+        if (e) { len = (int)(e >> 8); sym = (int)(e & 255u); }
+        else {
+            int l = 9;
+            int32_t code = (int32_t)(b16 >> 7);
+            while (l <= 16 && code > __ldg(&t->maxcode[l])) { l++; code = (int32_t)(b16 >> (16 - l)); }
+            if (l > 16) { len = 1; sym = 0; }                   // invalid code: advance one bit (a blind decoder must not stall)
+            else { len = l; sym = __ldg(&t->huffval[(code + __ldg(&t->valoff[l])) & 255]); }
+        }
+        r.buf <<= len; r.nb -= len;
+        const int size = sym & 15, run = sym >> 4;
+        int val = 0;
+        if (size) {
+            const uint32_t v = (uint32_t)(r.buf >> (64 - size));
+            r.buf <<= size; r.nb -= size;
+            val = (int)v < (1 << (size - 1)) ? (int)v - (1 << size) + 1 : (int)v;
+        }
+        int k = -1;
+        if (z == 0) { k = 0; z = 1; }
+        else if (size == 0) z = run == 15 ? z + 16 : 64;
+        else { z += run; if (z < 64) k = z; z++; }
+        if (WRITE && k >= 0 && wr) {
+            if (k == 0) dcd[dc_off[wcomp] + dseq] = val;
+            else coef[(size_t)index * 64 + s_zz[k]] = (int16_t)val;
+        }
+        if (z >= 64) {
+            z = 0;
+            c = c + 1 == bpm ? 0 : c + 1;
+            blocks++;
+            comp = h->blk_comp[c];
+            dct = &h->dc[h->dc_tab[comp]];
+            act = &h->ac[h->ac_tab[comp]];
+            if (WRITE) { blk++; wr = blk < h->total_blocks; if (wr) dfd_jpeg_block_pos(h, blk, &wcomp, &index, &dseq); }
+        }
+        p = r.wi * 32u - (uint32_t)r.nb;
     }
-    // (2) synchronisation rounds: subsequence i restarts from the end state of i-1 until nothing changes.  States are single
-    // 64-bit words, so a concurrent update is seen whole or not at all; a round that changes no state is a consistent
-    // snapshot in which every used[i] equals E[i-1], and subsequence 0 starts from the true state: by induction all are exact.
+    *nblk = blocks;
+    return ((unsigned long long)p << 16) | ((unsigned long long)(uint32_t)c << 8) | (unsigned long long)(uint32_t)z;
+}
+
+struct JhArgs {
+    const JpgMeta* meta; const DfdJpegHeader* hdr; const uint32_t* words; const uint32_t* nbits;
+    unsigned long long* E; unsigned long long* used; int* cnt; int* blk0; int* changed;
+    int16_t* coef; int32_t* dc; long long blocks_stride;
+};
+
+// grid (subsequence groups, frames); mode 0: blind pass, 1: synchronisation round `round`, 2: write pass
+template <int MODE>
+__global__ void __launch_bounds__(JH_THREADS) k_jh_pass(const JhArgs a, int round) {
+    __shared__ uint8_t s_zz[64];
+    const int f = blockIdx.y;
+    if (MODE == 2) { if (threadIdx.x < 64) s_zz[threadIdx.x] = DFD_ZIGZAG_DEV[threadIdx.x]; __syncthreads(); }
+    if (MODE == 1 && round > 0 && a.changed[f * JH_ROUNDS + round - 1] == 0) return;        // this frame has converged
+    const uint32_t nbits = a.nbits[f];
+    const int nsub = (int)((nbits + JPG_SUB_BITS - 1) / JPG_SUB_BITS);
+    const int i = blockIdx.x * JH_THREADS + threadIdx.x;
+    if (MODE != 2 && i >= nsub) return;
+    if (MODE == 2 && blockIdx.x * JH_THREADS >= nsub) return;   // (whole CTA: the write pass has barriers)
+    const JpgMeta M = a.meta[f];
+    const DfdJpegHeader* h = a.hdr + f;
+    const uint32_t* words = a.words + M.words_off;
+    unsigned long long* E = a.E + M.sub_off;
+    unsigned long long* used = a.used + M.sub_off;
+    const uint32_t lim = min((uint32_t)(i + 1) * JPG_SUB_BITS, nbits);
+    int nb;
+    if (MODE == 0) {
+        const unsigned long long st = (unsigned long long)((uint32_t)i * JPG_SUB_BITS) << 16;
+        const unsigned long long e = jh_decode<false>(h, words, st, lim, &nb, 0, nullptr, nullptr, nullptr, nullptr);
+        used[i] = st; E[i] = e; a.cnt[M.sub_off + i] = nb;
+    } else if (MODE == 1) {
+        if (i == 0) return;
+        const unsigned long long st = __ldcg(E + i - 1);       // one 64-bit word: seen whole, old or new
+        if (st == used[i]) return;
+        const unsigned long long e = jh_decode<false>(h, words, st, lim, &nb, 0, nullptr, nullptr, nullptr, nullptr);
+        if (e != E[i]) a.changed[f * JH_ROUNDS + round] = 1;
+        used[i] = st; __stcg(E + i, e); a.cnt[M.sub_off + i] = nb;
+    } else {
+        // Write pass: coefficients leave as scattered 2-byte stores into the zero-initialised array.  (Staging a CTA's block
+        // range in 46 KB of shared memory and writing whole 128-byte blocks was measured and is SLOWER, 1.9 -> 2.9 ms per
+        // 256 natural frames: the decode loop is latency-bound and lives on occupancy, which the buffer cut to 16 warps / SM.)
+        int32_t dc_off[3] = {0, 0, 0};
+        { int q = 0; for (int c = 0; c < h->ncomp; c++) { dc_off[c] = q; q += h->comp_bw[c] * h->comp_bh[c]; } }
+        if (i < nsub)
+            jh_decode<true>(h, words, used[i], lim, &nb, a.blk0[M.sub_off + i], a.coef + (size_t)f * a.blocks_stride * 64,
+                            a.dc + (size_t)f * a.blocks_stride, dc_off, s_zz);
+    }
+}
+
+// CTA per frame, only frames that were still changing in the last flat round: rounds until a whole round changes nothing
+__global__ void __launch_bounds__(JPG_THREADS) k_jh_finish(const JhArgs a) {
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (a.changed[f * JH_ROUNDS + JH_ROUNDS - 1] == 0) return;
+    const JpgMeta M = a.meta[f];
+    const DfdJpegHeader* h = a.hdr + f;
+    const uint32_t* words = a.words + M.words_off;
+    const uint32_t nbits = a.nbits[f];
+    const int nsub = (int)((nbits + JPG_SUB_BITS - 1) / JPG_SUB_BITS);
+    volatile unsigned long long* E = a.E + M.sub_off;
+    volatile unsigned long long* used = a.used + M.sub_off;
     for (int round = 0; round <= nsub + 1; round++) {
         __syncthreads();
         int changed = 0;
@@ -147,41 +294,50 @@ k_jpeg_huffman(const JpgMeta* __restrict__ meta, const DfdJpegHeader* __restrict
             if (i == 0) continue;
             const unsigned long long st = E[i - 1];
             if (st == used[i]) continue;
-            const uint32_t lim = min((uint32_t)(i + 1) * JPG_SUB_BITS, nbits);
-            int nb, ne;
-            const unsigned long long e = dfd_jpeg_decode_sub<false>(&h, words, nwords, st, lim, &nb, &ne, 0, nullptr, nullptr, nullptr);
+            int nb;
+            const unsigned long long e = jh_decode<false>(h, words, st, min((uint32_t)(i + 1) * JPG_SUB_BITS, nbits), &nb, 0, nullptr, nullptr, nullptr, nullptr);
             if (e != E[i]) changed = 1;
-            used[i] = st; E[i] = e; cnt[i] = nb;
+            used[i] = st; E[i] = e; a.cnt[M.sub_off + i] = nb;
         }
         if (!__syncthreads_or(changed)) break;
     }
-    // (3) first block number of every subsequence: exclusive scan of the block counts, in index order
+}
+
+// per frame: first block number of every subsequence (exclusive scan of the block counts), completeness check
+__global__ void __launch_bounds__(JPG_THREADS) k_jh_scan(const JhArgs a, int32_t* __restrict__ status) {
+    __shared__ int s_warp[JPG_THREADS / 32 + 1];
+    __shared__ int s_carry;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const JpgMeta M = a.meta[f];
+    const uint32_t nbits = a.nbits[f];
+    const int nsub = (int)((nbits + JPG_SUB_BITS - 1) / JPG_SUB_BITS);
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (int c0 = 0; c0 < nsub; c0 += JPG_THREADS) {
         const int i = c0 + tid;
-        const int v = i < nsub ? cnt[i] : 0;
+        const int v = i < nsub ? a.cnt[M.sub_off + i] : 0;
         int total;
         const int ex = cta_exscan(v, &total, s_warp);
-        if (i < nsub) blk0[i] = s_carry + ex;
+        if (i < nsub) a.blk0[M.sub_off + i] = s_carry + ex;
         __syncthreads();
         if (tid == 0) s_carry += total;
         __syncthreads();
     }
-    const int total_blocks = s_carry;
-    // (4) write pass
-    for (int i = tid; i < nsub; i += JPG_THREADS) {
-        const uint32_t lim = min((uint32_t)(i + 1) * JPG_SUB_BITS, nbits);
-        int nb, ne;
-        dfd_jpeg_decode_sub<true>(&h, words, nwords, used[i], lim, &nb, &ne, blk0[i], coef, dcd, dc_off);
-        nerr_total += ne;
-    }
-    const int any_err = __syncthreads_or(nerr_total != 0 && false);      // (invalid codes in the padding after the last block are legal)
-    (void)any_err;
-    // (5) DC prediction chains: inclusive prefix sum per component, in chain order
-    for (int c = 0; c < h.ncomp; c++) {
-        const int n = h.comp_bw[c] * h.comp_bh[c];
-        int32_t* d = dcd + dc_off[c];
+    if (tid == 0) status[f] = s_carry >= a.hdr[f].total_blocks ? DFD_JPEG_OK : DFD_JPEG_ERR_DATA;
+}
+
+// per frame: DC prediction chains = inclusive prefix sums per component, in chain order
+__global__ void __launch_bounds__(JPG_THREADS) k_jh_dc(const JhArgs a) {
+    __shared__ int s_warp[JPG_THREADS / 32 + 1];
+    __shared__ int s_carry;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const DfdJpegHeader* h = a.hdr + f;
+    int32_t* dcd = a.dc + (size_t)f * a.blocks_stride;
+    int off = 0;
+    for (int c = 0; c < h->ncomp; c++) {
+        const int n = h->comp_bw[c] * h->comp_bh[c];
+        int32_t* d = dcd + off;
+        off += n;
         if (tid == 0) s_carry = 0;
         __syncthreads();
         for (int c0 = 0; c0 < n; c0 += JPG_THREADS) {
@@ -195,7 +351,6 @@ k_jpeg_huffman(const JpgMeta* __restrict__ meta, const DfdJpegHeader* __restrict
             __syncthreads();
         }
     }
-    if (tid == 0) status[f] = total_blocks >= h.total_blocks ? DFD_JPEG_OK : DFD_JPEG_ERR_DATA;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -268,6 +423,38 @@ k_jpeg_color(const DfdJpegHeader* __restrict__ hdr, const uint8_t* __restrict__ 
         pitch1 = h->comp_bw[1] * 8;
         cw = (W * h->hs[1] + h->hmax - 1) / h->hmax; chh = (H * h->vs[1] + h->vmax - 1) / h->vmax;
     }
+    const bool h2v2 = h->ncomp == 3 && h->hs[1] * 2 == h->hmax && h->vs[1] * 2 == h->vmax && cw > 2;
+    if (h2v2) {
+        // 4:2:0 fast path (the wire format): the thread's 4 pixels use chroma columns cx, cx + 1 and their neighbours; the
+        // vertical part of the triangle filter (3 * near row + far row) is computed once per column and plane -- the same
+        // arithmetic as dfd_jpeg_chroma_at (jdsample.c h2v2_fancy_upsample), 16 byte loads instead of 48.
+        const int cy = y >> 1, cx = x0 >> 1;
+        const int ny = min(max((y & 1) ? cy + 1 : cy - 1, 0), chh - 1);
+        const uint32_t yw = *(const uint32_t*)(P + (size_t)y * pitch0 + x0);          // x0 % 4 == 0, pitch % 8 == 0: aligned
+        int up[2][4];                                                                 // up-sampled chroma of the 4 pixels
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            const uint8_t* r0 = (pl ? p2 : p1) + (size_t)cy * pitch1;
+            const uint8_t* r1 = (pl ? p2 : p1) + (size_t)ny * pitch1;
+            int t[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c = min(max(cx - 1 + q, 0), cw - 1);
+                t[q] = 3 * r0[c] + r1[c];
+            }
+            // pixel x0 (even, column cx), x0+1 (odd, cx), x0+2 (even, cx+1), x0+3 (odd, cx+1)
+            up[pl][0] = cx == 0 ? (t[1] * 4 + 8) >> 4 : (t[1] * 3 + t[0] + 8) >> 4;
+            up[pl][1] = cx == cw - 1 ? (t[1] * 4 + 7) >> 4 : (t[1] * 3 + t[2] + 7) >> 4;
+            up[pl][2] = (t[2] * 3 + t[1] + 8) >> 4;                                   // cx + 1 >= 1: never the left edge
+            up[pl][3] = cx + 1 == cw - 1 ? (t[2] * 4 + 7) >> 4 : (t[2] * 3 + t[3] + 7) >> 4;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int r, g, b;
+            dfd_jpeg_ycc2rgb((int)((yw >> (8 * i)) & 255u), up[0][i], up[1][i], &r, &g, &b);
+            px[3 * i] = (uint8_t)b; px[3 * i + 1] = (uint8_t)g; px[3 * i + 2] = (uint8_t)r;
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int x = x0 + i;
@@ -282,6 +469,7 @@ k_jpeg_color(const DfdJpegHeader* __restrict__ hdr, const uint8_t* __restrict__ 
             }
         }
         px[3 * i] = (uint8_t)b; px[3 * i + 1] = (uint8_t)g; px[3 * i + 2] = (uint8_t)r;
+    }
     }
     uint8_t* o = frames + (size_t)f * frame_stride + (size_t)y * row_pitch + (size_t)x0 * 3;
     if (x0 + 4 <= W && ((uintptr_t)o & 3) == 0) {
@@ -320,6 +508,7 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
     else DFD_CUDA(cudaEventCreateWithFlags(&ctx->jpg_ev, cudaEventDisableTiming));
     // ---- host: headers only ----
     long long words = 0, subs = 0;
+    int chunks = 0, max_ecs = 0;
     const long long total_bytes = offsets_host[n] - offsets_host[0];
     for (int i = 0; i < n; i++) {
         const long long b0 = offsets_host[i], b1 = offsets_host[i + 1];
@@ -341,9 +530,11 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
         m.ecs_bytes = h->ecs_end - h->ecs_begin;
         m.words_off = words;
         m.sub_off = subs;
-        m.pad = 0;
-        words += (m.ecs_bytes + 3) / 4 + 4;
+        m.chunk_off = chunks;
+        words += (m.ecs_bytes + 3) / 4 + 6;
         subs += ((long long)m.ecs_bytes * 8 + JPG_SUB_BITS - 1) / JPG_SUB_BITS + 1;
+        chunks += (m.ecs_bytes + JU_CHUNK - 1) / JU_CHUNK + 1;
+        if (m.ecs_bytes > max_ecs) max_ecs = m.ecs_bytes;
     }
     // workspaces (worst case 4:4:4 with 16-pixel MCU padding: 3 components of ceil16(H) x ceil16(W))
     const long long bw = (W + 15) / 16 * 2, bh = (H + 15) / 16 * 2;
@@ -352,7 +543,7 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
     int rc;
     if ((rc = dfd_ensure(ctx, ctx->jpg_raw, (size_t)total_bytes + 16))) return rc;
     if ((rc = dfd_ensure(ctx, ctx->jpg_words, (size_t)words * 4 + 64))) return rc;
-    if ((rc = dfd_ensure(ctx, ctx->jpg_sub, (size_t)subs * (8 + 8 + 4 + 4) + 64))) return rc;
+    if ((rc = dfd_ensure(ctx, ctx->jpg_sub, (size_t)subs * (8 + 8 + 4 + 4) + (size_t)chunks * 4 + (size_t)n * JH_ROUNDS * 4 + 64))) return rc;
     if ((rc = dfd_ensure(ctx, ctx->jpg_coef, (size_t)n * blocks_stride * 64 * sizeof(int16_t)))) return rc;
     if ((rc = dfd_ensure(ctx, ctx->jpg_dc, (size_t)n * blocks_stride * sizeof(int32_t)))) return rc;
     if ((rc = dfd_ensure(ctx, ctx->jpg_planes, (size_t)n * plane_stride))) return rc;
@@ -364,6 +555,8 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
     unsigned long long* d_used = d_E + subs;
     int* d_cnt = (int*)(d_used + subs);
     int* d_blk0 = d_cnt + subs;
+    int* d_chunk = d_blk0 + subs;
+    int* d_changed = d_chunk + chunks;
     // ---- device ----
     DFD_CUDA(cudaMemcpyAsync(ctx->jpg_raw.p, bytes_host + offsets_host[0], (size_t)total_bytes, cudaMemcpyHostToDevice, st));
     DFD_CUDA(cudaMemcpyAsync(d_hdr, J->h_hdr_pinned, sizeof(DfdJpegHeader) * n, cudaMemcpyHostToDevice, st));
@@ -371,11 +564,33 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
     DFD_CUDA(cudaEventRecord(ctx->jpg_ev, st));
     DFD_CUDA(cudaMemsetAsync(ctx->jpg_coef.p, 0, (size_t)n * blocks_stride * 64 * sizeof(int16_t), st));
     DFD_CUDA(cudaMemsetAsync(ctx->jpg_dc.p, 0, (size_t)n * blocks_stride * sizeof(int32_t), st));
-    k_jpeg_unstuff<<<n, JPG_THREADS, 0, st>>>((const uint8_t*)ctx->jpg_raw.p, d_meta, d_hdr, (uint32_t*)ctx->jpg_words.p, d_nbits);
-    DFD_LAUNCH_CHECK("k_jpeg_unstuff", st);
-    k_jpeg_huffman<<<n, JPG_THREADS, 0, st>>>(d_meta, d_hdr, (const uint32_t*)ctx->jpg_words.p, d_nbits, d_E, d_used, d_cnt, d_blk0,
-                                              (int16_t*)ctx->jpg_coef.p, (int32_t*)ctx->jpg_dc.p, blocks_stride, status_dev);
-    DFD_LAUNCH_CHECK("k_jpeg_huffman", st);
+    DFD_CUDA(cudaMemsetAsync(d_changed, 0, (size_t)n * JH_ROUNDS * sizeof(int), st));
+    const unsigned gc = (unsigned)((max_ecs + JU_CHUNK - 1) / JU_CHUNK);
+    k_ju_count<<<dim3(gc, n), 128, 0, st>>>((const uint8_t*)ctx->jpg_raw.p, d_meta, d_hdr, d_chunk);
+    DFD_LAUNCH_CHECK("k_ju_count", st);
+    k_ju_scan<<<n, JPG_THREADS, 0, st>>>(d_meta, d_chunk, (uint32_t*)ctx->jpg_words.p, d_nbits);
+    DFD_LAUNCH_CHECK("k_ju_scan", st);
+    k_ju_scatter<<<dim3(gc, n), 128, 0, st>>>((const uint8_t*)ctx->jpg_raw.p, d_meta, d_hdr, d_chunk, (uint32_t*)ctx->jpg_words.p);
+    DFD_LAUNCH_CHECK("k_ju_scatter", st);
+    JhArgs ja;
+    ja.meta = d_meta; ja.hdr = d_hdr; ja.words = (const uint32_t*)ctx->jpg_words.p; ja.nbits = d_nbits;
+    ja.E = d_E; ja.used = d_used; ja.cnt = d_cnt; ja.blk0 = d_blk0; ja.changed = d_changed;
+    ja.coef = (int16_t*)ctx->jpg_coef.p; ja.dc = (int32_t*)ctx->jpg_dc.p; ja.blocks_stride = blocks_stride;
+    const unsigned gs = (unsigned)(((long long)max_ecs * 8 + JPG_SUB_BITS - 1) / JPG_SUB_BITS + JH_THREADS - 1) / JH_THREADS;
+    k_jh_pass<0><<<dim3(gs, n), JH_THREADS, 0, st>>>(ja, 0);
+    DFD_LAUNCH_CHECK("k_jh_blind", st);
+    for (int r = 0; r < JH_ROUNDS; r++) {
+        k_jh_pass<1><<<dim3(gs, n), JH_THREADS, 0, st>>>(ja, r);
+        DFD_LAUNCH_CHECK("k_jh_round", st);
+    }
+    k_jh_finish<<<n, JPG_THREADS, 0, st>>>(ja);
+    DFD_LAUNCH_CHECK("k_jh_finish", st);
+    k_jh_scan<<<n, JPG_THREADS, 0, st>>>(ja, status_dev);
+    DFD_LAUNCH_CHECK("k_jh_scan", st);
+    k_jh_pass<2><<<dim3(gs, n), JH_THREADS, 0, st>>>(ja, 0);
+    DFD_LAUNCH_CHECK("k_jh_write", st);
+    k_jh_dc<<<n, JPG_THREADS, 0, st>>>(ja);
+    DFD_LAUNCH_CHECK("k_jh_dc", st);
     k_jpeg_idct<<<dim3((unsigned)((blocks_stride + 127) / 128), n), 128, 0, st>>>(d_hdr, (const int16_t*)ctx->jpg_coef.p, (const int32_t*)ctx->jpg_dc.p,
                                                                                   blocks_stride, (uint8_t*)ctx->jpg_planes.p, plane_stride);
     DFD_LAUNCH_CHECK("k_jpeg_idct", st);

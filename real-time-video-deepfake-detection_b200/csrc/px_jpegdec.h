@@ -182,6 +182,9 @@ DFD_HD void dfd_jpeg_idct_block(const int16_t* coef, int dc, const uint16_t* qt,
 // the edge cases apply at the last REAL column / row, not at the MCU padding.
 DFD_HD int dfd_jpeg_chroma_at(const uint8_t* plane, int pitch, int cw, int ch, int hs, int vs, int hmax, int vmax, int X, int Y) {
     if (hs == hmax && vs == vmax) return plane[Y * pitch + X];
+    // jdsample.c (jinit_upsampler): the triangle filters are used only when the component is more than 2 samples wide;
+    // narrower components (image width <= 4) are up-sampled by plain replication
+    if (cw <= 2) return plane[(Y * vs / vmax) * pitch + (X * hs / hmax)];
     if (hs * 2 == hmax && vs * 2 == vmax) {            // h2v2
         const int cy = Y >> 1, cx = X >> 1;
         int ny = (Y & 1) ? cy + 1 : cy - 1;
@@ -211,7 +214,6 @@ DFD_HD int dfd_jpeg_chroma_at(const uint8_t* plane, int pitch, int cw, int ch, i
     return plane[(Y * vs / vmax) * pitch + (X * hs / hmax)];
 }
 
-#if !defined(__CUDA_ARCH__)
 // ---- host: header parsing ---------------------------------------------------------------------------------------------
 static inline void dfd_jpeg_build_huff(const uint8_t* bits /* [17], bits[0] unused */, const uint8_t* vals, int nvals, DfdHuffTab* t) {
     for (int i = 0; i < 256; i++) { t->look[i] = 0; t->huffval[i] = i < nvals ? vals[i] : 0; }
@@ -357,7 +359,6 @@ static inline int dfd_jpeg_parse(const uint8_t* d, size_t n, DfdJpegHeader* h) {
     }
     return h->status;
 }
-#endif
 
 // ---- one subsequence of the entropy-coded segment ------------------------------------------------------------------------
 // Decodes every symbol that STARTS in [s.p, limit) from state s (a symbol belongs to the subsequence it starts in).

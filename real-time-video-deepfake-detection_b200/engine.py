@@ -187,6 +187,42 @@ class Engine:
         self._check(rc, "dfd_analyze_batch")
         return rec, fres, fprob[:m]
 
+    # -- frame ingest ------------------------------------------------------------------
+    @staticmethod
+    def jpeg_info(data):
+        """(H, W, components, luma_h, luma_v) of a JPEG stream (host-side header peek); raises DfdError if the stream is not
+        decodable on the device (progressive, restart markers, ...)."""
+        lib = _lib.load()
+        buf = np.frombuffer(data, np.uint8)
+        info = (C.c_int32 * 5)()
+        rc = lib.dfd_jpeg_info(buf.ctypes.data_as(C.c_void_p), buf.size, info)
+        if rc != 0:
+            raise _lib.DfdError(f"dfd_jpeg_info: stream not decodable on the device ({rc})")
+        return tuple(int(v) for v in info)
+
+    def pack_jpegs(self, streams):
+        """Concatenates JPEG byte strings into one PINNED host buffer + offsets (what dfd_decode_jpeg_batch takes)."""
+        sizes = [len(s) for s in streams]
+        offsets = np.zeros(len(streams) + 1, np.int64)
+        np.cumsum(sizes, out=offsets[1:])
+        buf = torch.empty(int(offsets[-1]), dtype=torch.uint8).pin_memory()
+        view = buf.numpy()
+        for s, o in zip(streams, offsets[:-1]):
+            view[o:o + len(s)] = np.frombuffer(s, np.uint8)
+        return buf, offsets
+
+    def decode_jpeg_batch(self, packed, offsets, H, W, out=None):
+        """cv2.imdecode on the device for n streams of equal size -> ((n, H, W, 3) uint8 BGR CUDA tensor, int32 status tensor).
+        `packed`: uint8 host tensor (pinned for an asynchronous copy), `offsets`: int64 numpy array of n + 1 offsets."""
+        n = len(offsets) - 1
+        frames = out if out is not None else torch.empty((n, H, W, 3), dtype=torch.uint8, device=self.device)
+        status = torch.empty(n, dtype=torch.int32, device=self.device)
+        off = np.ascontiguousarray(offsets, np.int64)
+        rc = self.lib.dfd_decode_jpeg_batch(self.h, C.c_void_p(packed.data_ptr()), off.ctypes.data_as(C.c_void_p), n, H, W,
+                                            _ptr(frames), frames.stride(0), frames.stride(1), _ptr(status), self._stream())
+        self._check(rc, "dfd_decode_jpeg_batch")
+        return frames, status
+
     def configure_stream(self, stream_id, window_size=60, voting_window=10, detection_threshold=0.5):
         self._check(self.lib.dfd_configure_stream(self.h, int(stream_id), int(window_size), int(voting_window),
                                                   float(detection_threshold), self._stream()), "dfd_configure_stream")

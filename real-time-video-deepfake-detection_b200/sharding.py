@@ -44,15 +44,40 @@ class StreamSharder:
                 mine.append(int(f))
         return np.array(sorted(mine), np.int64)
 
-    def gather_records(self, records, max_per_rank):
-        """records: uint8 tensor of n_local * 72 bytes (device for nccl, cpu for gloo).  Returns a
-        (world * max_per_rank * 72) uint8 tensor on every rank; unused slots carry stream_id = -1."""
+    def make_buffers(self, max_per_rank, device):
+        """Preallocated gather buffers: ``send`` (max_per_rank records, padding slots pre-marked stream_id = -1) is meant to
+        be passed as ``records_out`` to Engine.analyze_batch / capture_step so the vote kernel writes the records straight
+        into the buffer the collective sends (no per-step allocation or copy); ``out`` receives world x max_per_rank records."""
         nbytes = max_per_rank * _lib.RECORD_BYTES
-        send = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device=records.device)     # stream_id = -1 padding
-        send[:records.numel()] = records
-        out = torch.empty(self.world * nbytes, dtype=torch.uint8, device=records.device)
-        dist.all_gather_into_tensor(out, send)
-        return out
+        send = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device=device)
+        out = torch.empty(self.world * nbytes, dtype=torch.uint8, device=device)
+        return send, out
+
+    def gather_records(self, records, max_per_rank, out=None, async_op=False):
+        """records: uint8 tensor of n_local * 72 bytes (device for nccl, cpu for gloo).  Returns a
+        (world * max_per_rank * 72) uint8 tensor on every rank; unused slots carry stream_id = -1.
+        When ``records`` already is a full send buffer from ``make_buffers`` it is sent as is (no allocation, no copy)."""
+        nbytes = max_per_rank * _lib.RECORD_BYTES
+        if records.numel() == nbytes:
+            send = records
+        else:
+            send = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device=records.device)     # stream_id = -1 padding
+            send[:records.numel()] = records
+        if out is None:
+            out = torch.empty(self.world * nbytes, dtype=torch.uint8, device=records.device)
+        work = dist.all_gather_into_tensor(out, send, async_op=async_op)
+        return (out, work) if async_op else out
+
+    def globalize(self, gathered, max_per_rank):
+        """Gathered records as a NumPy array with GLOBAL stream ids (an engine numbers its streams by local slot:
+        global id = slot * world + owning rank, the inverse of ``select``)."""
+        from .engine import RECORD_DTYPE
+        rec = gathered.cpu().numpy().view(RECORD_DTYPE).copy().reshape(self.world, max_per_rank)
+        for r in range(self.world):
+            ok = rec[r]["stream_id"] >= 0
+            rec[r]["stream_id"][ok] = rec[r]["stream_id"][ok] * self.world + r
+        rec = rec.reshape(-1)
+        return rec[rec["stream_id"] >= 0]
 
     @staticmethod
     def records_to_numpy(buf):

@@ -25,6 +25,9 @@ import torch.nn.functional as F
 from . import arch
 
 FAMILIES = ("uniform", "pink", "blur", "flat", "gradient")
+# "natural": 1/f amplitude spectrum without the added pixel noise of "pink" -- the statistics of photographic frames, used where
+# the CONTENT matters for the cost (the JPEG ingest bench: a 720p "natural" frame is ~0.4 MB at quality 85, "pink" 0.57 MB,
+# "uniform" noise 0.7 MB; real video frames are smaller still).  Not part of FAMILIES: the forensic fixtures are pinned to those five.
 
 
 # --------------------------------------------------------------------------
@@ -45,6 +48,20 @@ def _pink(rng, h, w):
     return np.clip(np.stack(chans, -1), 0, 255).astype(np.uint8)
 
 
+def _natural(rng, h, w, alpha=1.0):
+    fy = np.fft.fftfreq(h)[:, None]
+    fx = np.fft.fftfreq(w)[None, :]
+    f = np.sqrt(fx * fx + fy * fy)
+    f[0, 0] = 1.0
+    chans = []
+    for _ in range(3):
+        spec = np.fft.fft2(rng.standard_normal((h, w))) / f ** alpha
+        spec[0, 0] = 0
+        x = np.real(np.fft.ifft2(spec))
+        chans.append(x / (x.std() + 1e-9) * 45.0 + 120.0)
+    return np.clip(np.stack(chans, -1), 0, 255).astype(np.uint8)
+
+
 def make_frame(family, h, w, rng):
     """One BGR uint8 frame of the given family."""
     import cv2
@@ -52,6 +69,8 @@ def make_frame(family, h, w, rng):
         return rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
     if family == "pink":
         return _pink(rng, h, w)
+    if family == "natural":
+        return _natural(rng, h, w)
     if family == "blur":
         x = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
         return cv2.GaussianBlur(x, (31, 31), 8)

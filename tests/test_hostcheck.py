@@ -182,3 +182,35 @@ def test_constant_division_is_exact(tmp_path):
     for which in "0123":
         out = subprocess.run([exe, which, "97"], capture_output=True, text=True)
         assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout
+
+
+@pytest.mark.parametrize("sub_bits", [0, 1024])
+def test_jpeg_decoder_functions_match_cv2_imdecode(hc, sub_bits):
+    """csrc/px_jpegdec.h (header parser, Huffman state machine, IDCT, fancy up-sampling, colour conversion -- the functions the
+    device decoder jpegdec.cu inlines) on the CPU against cv2.imdecode: sequentially (sub_bits = 0) and as a simulation of the
+    kernel's self-synchronising parallel schedule with 1024-bit subsequences.  Bit-exact, odd sizes included."""
+    rng = np.random.RandomState(21)
+    cases = [((405, 720), [cv2.IMWRITE_JPEG_QUALITY, 85]), ((97, 83), [cv2.IMWRITE_JPEG_QUALITY, 85]),
+             ((64, 48), [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_OPTIMIZE, 1]),
+             ((131, 77), [cv2.IMWRITE_JPEG_QUALITY, 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]),
+             ((131, 77), [cv2.IMWRITE_JPEG_QUALITY, 60, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422]),
+             ((1, 1), [cv2.IMWRITE_JPEG_QUALITY, 85])]
+    for (h, w), params in cases:
+        for fam in ("pink", "gradient", "natural"):
+            img = synth.make_frame(fam, h, w, rng)
+            ok, enc = cv2.imencode(".jpg", img, params)
+            ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+            out = np.zeros_like(ref)
+            rounds = ctypes.c_int(0)
+            buf = np.ascontiguousarray(enc)
+            rc = hc.hc_jpeg_decode(ptr(buf), ctypes.c_long(buf.size), ptr(out), sub_bits, ctypes.byref(rounds))
+            assert rc == 0 and np.array_equal(out, ref), (h, w, params, fam, rc)
+    # unsupported / invalid streams are recognised by the parser
+    img = synth.make_frame("pink", 64, 64, rng)
+    info = (ctypes.c_int * 7)()
+    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    assert hc.hc_jpeg_info(ptr(np.ascontiguousarray(prog)), ctypes.c_long(prog.size), info) == -2
+    ok, rst = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_RST_INTERVAL, 2])
+    assert hc.hc_jpeg_info(ptr(np.ascontiguousarray(rst)), ctypes.c_long(rst.size), info) == -2
+    junk = np.frombuffer(b"\x89PNG\r\n\x1a\n" + bytes(64), np.uint8)
+    assert hc.hc_jpeg_info(ptr(junk), ctypes.c_long(junk.size), info) == -1

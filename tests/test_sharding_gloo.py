@@ -40,6 +40,17 @@ def _worker(rank, world, port, out):
     assert sorted(allrec["stream_id"].tolist()) == list(range(11))
     for r in allrec:
         assert int(r["verdict"]) == int(r["stream_id"]) % 3 and abs(r["vote_input"] - r["stream_id"] / 10.0) < 1e-12
+    # preallocated send buffer (what the vote kernel writes into on the GPU): no copy, local slot ids -> global ids
+    send, out_buf = sh.make_buffers(6, "cpu")
+    rec2 = np.zeros(len(idx), RECORD_DTYPE)
+    rec2["stream_id"] = slots
+    rec2["verdict"] = stream_ids[idx] % 3
+    send[:rec2.nbytes] = torch.from_numpy(rec2.view(np.uint8).copy())
+    g2 = sh.gather_records(send, 6, out=out_buf)
+    assert g2.data_ptr() == out_buf.data_ptr()
+    glob = sh.globalize(g2, 6)
+    assert sorted(glob["stream_id"].tolist()) == list(range(11))
+    assert all(int(r["verdict"]) == int(r["stream_id"]) % 3 for r in glob)
     crops = [8, 1, 1, 1, 5, 2, 2, 3]
     mine = sh.shard_frames_round_robin(len(crops), crops)
     load = sum(crops[i] for i in mine)
