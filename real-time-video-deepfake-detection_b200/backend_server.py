@@ -4,7 +4,14 @@ fields, served by a small werkzeug WSGI app (Flask is not in this image; ``app.t
 
 Face boxes are inputs on this path: ``POST /analyze`` accepts an optional multipart field ``faces`` holding a
 JSON list ``[[x, y, w, h], ...]``; without it (and without ``face_detector`` installed) the request is
-analysed in ``frame_only`` mode.  Image decoding stays on the host (cv2.imdecode), as in the reference.
+analysed in ``frame_only`` mode.
+
+Ingest (reference backend_server.py:140-142, ``cv2.imdecode``): a baseline JPEG upload -- the extension's wire format,
+``canvas.toDataURL('image/jpeg', 0.85)`` -- is decoded ON THE DEVICE (``DeepfakeDetector.decode_frame`` ->
+``dfd_decode_jpeg_batch``, bit-exact with OpenCV), so the frame never exists in host memory and the face crop is taken
+from the device copy.  Uploads in any other format (PNG, progressive JPEG, ...) keep the reference's own ingest call,
+``cv2.imdecode`` on the host: that is the caller's side of the boundary, not a fallback of the compute path -- every
+signal, the classifier and the vote still run in libdfd.
 """
 import json
 import logging
@@ -15,6 +22,7 @@ import torch
 from werkzeug.test import Client
 from werkzeug.wrappers import Request, Response
 
+from . import _lib
 from .deepfake_detection import DeepfakeDetector, _model_state
 
 logger = logging.getLogger(__name__)
@@ -71,22 +79,34 @@ def analyze_frame(request):
         import cv2
         if "frame" not in request.files:
             return _json({"error": "No frame provided"}, 400)
-        data = np.frombuffer(request.files["frame"].read(), np.uint8)
-        frame = cv2.imdecode(data, cv2.IMREAD_COLOR) if data.size else None
+        raw = request.files["frame"].read()
+        det = _get_detector()
+        frame = None
+        if len(raw) > 3 and raw[:2] == b"\xff\xd8":                              # JPEG: decode on the device
+            try:
+                frame = det.decode_frame(raw)
+            except _lib.DfdError:
+                frame = None                                                     # not a baseline stream: reference ingest below
+        if frame is None:
+            data = np.frombuffer(raw, np.uint8)
+            frame = cv2.imdecode(data, cv2.IMREAD_COLOR) if data.size else None
         if frame is None:
             return _json({"error": "Invalid image format"}, 400)
-        det = _get_detector()
         ff = det.analyze_frame_forensics(frame)                                  # frame_count read BEFORE increment (:148,156)
         ff_prob = ff["fake_probability"]
         if "faces" in request.form:
             faces = [tuple(int(v) for v in b) for b in json.loads(request.form["faces"])]
         else:
-            faces = face_detector(frame) if face_detector is not None else []
+            faces = (face_detector(frame.cpu().numpy() if torch.is_tensor(frame) else frame)
+                     if face_detector is not None else [])
         det.frame_count += 1
         tr = det.temporal_tracker
         if len(faces) > 0:
             x, y, w, h = faces[0]
-            fake_prob, _, _ = det.analyze_face(frame[y:y + h, x:x + w])
+            if torch.is_tensor(frame):
+                fake_prob, _, _ = det.analyze_face_box(frame, (x, y, w, h))
+            else:
+                fake_prob, _, _ = det.analyze_face(frame[y:y + h, x:x + w])
             if fake_prob is not None:
                 tr.update(fake_prob)
                 ms = (time.time() - start) * 1000

@@ -220,6 +220,38 @@ class DeepfakeDetector:
             print(f"Face analysis error: {e}")
             return None, None, None
 
+    def analyze_face_box(self, frame_dev, box):
+        """``analyze_face(frame[y:y+h, x:x+w])`` for a frame that is already on the device (an (H, W, 3) uint8 CUDA tensor,
+        e.g. from ``decode_frame``): the crop never visits the host.  Same return convention as ``analyze_face``."""
+        try:
+            _ensure_weights(self._eng)
+            x, y, w, h = (int(v) for v in box)
+            H, W = int(frame_dev.shape[0]), int(frame_dev.shape[1])
+            bx = np.array([[x, y, w, h]], np.int32)
+            xin = self._eng.face_prep_batch(frame_dev.contiguous().unsqueeze(0), bx, [0], self.dtype)
+            logits = self._eng.effnet_forward(xin)
+            # heuristics see the crop numpy slicing would give (clamped to the frame), like face_region.shape in the reference
+            cw, ch = max(min(x + w, W) - max(x, 0), 0), max(min(y + h, H) - max(y, 0), 0)
+            p = self._eng.face_probability(logits, np.array([[0, 0, cw, ch]], np.int32))
+            p = np.float64(p.cpu().numpy()[0])
+            if np.isnan(p):
+                raise ValueError(f"face box {box} is empty inside the {W}x{H} frame or exceeds the engine's max_crop")
+            return p, p, None
+        except Exception as e:
+            print(f"Face analysis error: {e}")
+            return None, None, None
+
+    def decode_frame(self, image_bytes):
+        """``cv2.imdecode(np.frombuffer(image_bytes, np.uint8), cv2.IMREAD_COLOR)`` (backend_server.py:140-142) on the
+        DEVICE for baseline JPEG uploads (the extension's wire format): returns an (H, W, 3) uint8 BGR CUDA tensor, bit-exact
+        with OpenCV.  Raises DfdError for streams the device decoder does not cover (the caller decides what to do)."""
+        H, W = self._eng.jpeg_info(image_bytes)[:2]
+        packed, offsets = self._eng.pack_jpegs([image_bytes])
+        frames, status = self._eng.decode_jpeg_batch(packed, offsets, H, W)
+        if int(status.cpu()[0]) != 0:
+            raise _lib.DfdError("corrupt JPEG stream (entropy-coded data incomplete)")
+        return frames[0]
+
     # -- whole frame ---------------------------------------------------------------------------
     def predict(self, frame, faces=None):
         """(frame, trigger_forensic, forensic_frame, result_data) as deepfake_detection.py:588-686; the frame is

@@ -34,10 +34,15 @@ class FrameForensicAnalyzer:
             self._eng.reset(self._slot)
 
     def _run(self, frame, full):
-        frame = np.asarray(frame)
-        if frame.ndim != 3 or frame.shape[2] != 3 or frame.dtype != np.uint8:
-            raise ValueError("frame must be an (H, W, 3) uint8 BGR image")   # cv2.resize would raise too
-        ft = torch.from_numpy(np.ascontiguousarray(frame)).to(self._eng.device).unsqueeze(0)
+        if torch.is_tensor(frame) and frame.is_cuda:      # a frame already resident on the device (device JPEG ingest)
+            if frame.dim() != 3 or frame.shape[2] != 3 or frame.dtype != torch.uint8:
+                raise ValueError("frame must be an (H, W, 3) uint8 BGR image")
+            ft = frame.contiguous().unsqueeze(0)
+        else:
+            frame = np.asarray(frame)
+            if frame.ndim != 3 or frame.shape[2] != 3 or frame.dtype != np.uint8:
+                raise ValueError("frame must be an (H, W, 3) uint8 BGR image")   # cv2.resize would raise too
+            ft = torch.from_numpy(np.ascontiguousarray(frame)).to(self._eng.device).unsqueeze(0)
         res = self._eng.forensic_to_numpy(self._eng.forensics_batch(ft, [self._slot], [1 if full else 0]))[0]
         self.frame_count = int(res["frame_number"])
         self.prev_frame_gray = "device"

@@ -222,3 +222,36 @@ def test_http_contract(weights):
     client.post("/reset")
     assert client.get("/stats").get_json()["frame_count"] == 0
     assert client.get("/nope").status_code == 404
+
+
+def test_http_jpeg_upload_is_decoded_on_the_device(weights):
+    """/analyze with the extension's wire format (JPEG quality 85, 720 x 405): the upload is decoded on the device and the
+    response equals what the reference computes from cv2.imdecode of the same bytes (forensic probability exactly, face
+    probability within 1e-4); a progressive JPEG takes the reference's host ingest and gives the same contract."""
+    from dfd_b200 import backend_server as bs
+    from oracle import forensics as ofor
+    client = bs.app.test_client()
+    client.post("/reset")
+    rng = np.random.RandomState(14)
+    frame = synth.make_frame("natural", 405, 720, rng)
+    ok, enc = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, 85])
+    decoded = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+    box = [150, 60, 260, 300]
+    time.sleep(0.15)
+    r = client.post("/analyze", data={"frame": (io.BytesIO(enc.tobytes()), "f.jpg"), "faces": json.dumps([box])},
+                    content_type="multipart/form-data")
+    j = r.get_json()
+    assert r.status_code == 200 and j["analysis_mode"] == "face+frame"
+    exp = ofor.OracleForensicAnalyzer().analyze(decoded)
+    assert j["frame_forensic_probability"] == exp["fake_probability"]
+    p = float(torch.sigmoid(oeff.forward(ofp.prepare(decoded, box), weights)).item())
+    assert abs(j["face_probability"] - p) <= 1e-4
+    # the decode itself: bit-exact with cv2
+    det = bs._get_detector()
+    dev = det.decode_frame(enc.tobytes())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), decoded)
+    ok, prog = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    time.sleep(0.15)
+    r = client.post("/analyze", data={"frame": (io.BytesIO(prog.tobytes()), "p.jpg")}, content_type="multipart/form-data")
+    assert r.status_code == 200 and r.get_json()["analysis_mode"] == "frame_only"
+    client.post("/reset")
