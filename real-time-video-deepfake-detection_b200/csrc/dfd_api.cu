@@ -189,6 +189,7 @@ int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
     if (const char* e = getenv("DFD_GATED_W_MAX")) { ctx->gated_w_max = atoi(e); if (ctx->gated_w_max > 10) ctx->gated_w_max = 10; }
     ctx->no_fold = getenv("DFD_NO_FOLD") != nullptr;
     ctx->fp32_simt = getenv("DFD_FP32_SIMT") != nullptr;
+    if (const char* e = getenv("DFD_L2_BUDGET_MB")) { ctx->l2_budget = atoi(e) << 20; ctx->no_subbatch = ctx->l2_budget <= 0; }
     if (getenv("DFD_SE_MODE")) ctx->se_mode = atoi(getenv("DFD_SE_MODE"));
     int rc = create_impl(ctx);
     if (rc) { g_create_err = ctx->err; dfd_destroy(ctx); *out = nullptr; return rc; }
@@ -399,6 +400,7 @@ int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value) {
     else if (n == "se_mode") ctx->se_mode = value;
     else if (n == "no_overlap") ctx->no_overlap = value != 0;
     else if (n == "fp32_simt") ctx->fp32_simt = value != 0;
+    else if (n == "no_subbatch") ctx->no_subbatch = value != 0;
     else { ctx->err = "dbg_set_option: unknown option " + n; return DFD_ERR_INVALID; }
     return DFD_OK;
 }

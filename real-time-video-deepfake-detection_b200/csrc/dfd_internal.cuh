@@ -91,6 +91,8 @@ struct dfd_ctx {
     float* d_wtf_hi = nullptr;            // fp32 accuracy mode on the tensor cores (gemm_tf32x3.cu): tf32 hi / lo planes of the
     float* d_wtf_lo = nullptr;            //   parameter blob (same offsets), W = hi + lo to ~2^-22
     float* d_stem_wtf = nullptr;          // stem [32][32] K-major operand, hi plane then lo plane
+    bool no_subbatch = true;              // fp32 mode: L2-resident expand -> depthwise sub-batches are OFF (measured slower, see effnet.cu);
+    int l2_budget = 64 << 20;             //   DFD_L2_BUDGET_MB=n / "no_subbatch" = 0 turns them on with n MB of expanded tensor per sub-batch
     bool fp32_simt = false;               // "fp32_simt" / DFD_FP32_SIMT=1: run the fp32 mode on the CUDA-core kernels (k_pw / k_dw / k_stem; A/B testing)
     DfdBuf act[3];                        // activation ping-pong + expanded buffer
     DfdBuf face_in;                       // prepared crops for analyze_batch

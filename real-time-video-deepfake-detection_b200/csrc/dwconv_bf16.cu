@@ -258,7 +258,7 @@ k_dw_tile_f32(const float* __restrict__ in, const float* __restrict__ W, const f
 
 template <int K, int S, int TW, int TH>
 static int launch_f32(dfd_ctx* ctx, const EffBlock& b, const float* in, const float* W, const float* bias, float* out, int m,
-                      int* n_parts, cudaStream_t st) {
+                      int* n_parts, cudaStream_t st, int img0) {
     constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
     const size_t smem = ((size_t)PH * PW * 32 + (size_t)K * K * 32 + (size_t)DW_WARPS * 32) * 4;
     { int rc = dfd_func_smem(ctx, k_dw_tile_f32<K, S, TW, TH>, smem); if (rc) return rc; }
@@ -266,24 +266,26 @@ static int launch_f32(dfd_ctx* ctx, const EffBlock& b, const float* in, const fl
     dim3 grid(tiles_x * tiles_y, (b.cexp + 31) / 32, m);
     *n_parts = tiles_x * tiles_y;
     if ((size_t)grid.x * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
-    k_dw_tile_f32<K, S, TW, TH><<<grid, DW_WARPS * 32, smem, st>>>(in, W, bias, out, ctx->d_pool, b.cexp, b.hin, b.hout, b.pad, tiles_x);
+    // img0: first image of a sub-batch (in / out already point at it): its squeeze partials go to the images' own slots
+    k_dw_tile_f32<K, S, TW, TH><<<grid, DW_WARPS * 32, smem, st>>>(in, W, bias, out, ctx->d_pool + (size_t)img0 * grid.x * b.cexp, b.cexp, b.hin,
+                                                                   b.hout, b.pad, tiles_x);
     DFD_LAUNCH_CHECK("k_dw_tile_f32", st);
     return DFD_OK;
 }
 
 int dfd_dw_f32(dfd_ctx* ctx, const EffBlock& b, const float* in, const float* W, const float* bias, float* out, int m,
-               int* n_parts, cudaStream_t st) {
-    if (b.k == 3 && b.s == 1 && b.hout == 112) return launch_f32<3, 1, 16, 16>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 3 && b.s == 2 && b.hout == 56) return launch_f32<3, 2, 14, 8>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 56) return launch_f32<3, 1, 14, 8>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 5 && b.s == 2 && b.hout == 28) return launch_f32<5, 2, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 28) return launch_f32<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 3 && b.s == 2 && b.hout == 14) return launch_f32<3, 2, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 14) return launch_f32<3, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 14) return launch_f32<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 5 && b.s == 2 && b.hout == 7) return launch_f32<5, 2, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 5 && b.s == 1 && b.hout == 7) return launch_f32<5, 1, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
-    if (b.k == 3 && b.s == 1 && b.hout == 7) return launch_f32<3, 1, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st);
+               int* n_parts, cudaStream_t st, int img0) {
+    if (b.k == 3 && b.s == 1 && b.hout == 112) return launch_f32<3, 1, 16, 16>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 3 && b.s == 2 && b.hout == 56) return launch_f32<3, 2, 14, 8>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 3 && b.s == 1 && b.hout == 56) return launch_f32<3, 1, 14, 8>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 5 && b.s == 2 && b.hout == 28) return launch_f32<5, 2, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 5 && b.s == 1 && b.hout == 28) return launch_f32<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 3 && b.s == 2 && b.hout == 14) return launch_f32<3, 2, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 3 && b.s == 1 && b.hout == 14) return launch_f32<3, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 5 && b.s == 1 && b.hout == 14) return launch_f32<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 5 && b.s == 2 && b.hout == 7) return launch_f32<5, 2, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 5 && b.s == 1 && b.hout == 7) return launch_f32<5, 1, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
+    if (b.k == 3 && b.s == 1 && b.hout == 7) return launch_f32<3, 1, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
     ctx->err = "dw_f32: no tile configuration for this layer";
     return DFD_ERR_INVALID;
 }

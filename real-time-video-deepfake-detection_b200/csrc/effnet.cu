@@ -38,7 +38,7 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
                     const float* bias, const float* residual, float* C, int M, int N, int K, int act, cudaStream_t st);
 void dfd_tf32_split_host(const float* w, size_t n, float* hi, float* lo);
 int dfd_dw_f32(dfd_ctx* ctx, const EffBlock& b, const float* in, const float* W, const float* bias, float* out, int m,
-               int* n_parts, cudaStream_t st);
+               int* n_parts, cudaStream_t st, int img0);
 
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
 template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
@@ -919,6 +919,33 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
                                                 &n_parts, st))) return rc;
             }
         } else {
+            // fp32 accuracy mode: expand + depthwise run as two kernels, so the expanded tensor (6x the block input, fp32) would
+            // make a round trip through HBM: 1.23 GB written and read back for block 1 at batch 256.  It is produced and consumed
+            // in SUB-BATCHES whose expanded tensor fits the 126 MB L2 (same buffer every time): the depthwise kernel then reads it
+            // from L2 and the dirty lines are overwritten before they are ever evicted.  MEASURED AND OFF BY DEFAULT: 6.33 ms per
+            // 256 crops without, 6.72 / 6.95 / 7.20 ms with 96 / 64 / 48 MB sub-batches (b1.expand 0.38 -> 0.62 ms over 20 launches):
+            // neither kernel is HBM-bound (epilogue ALU / shared-memory issue), so the shorter launches only add tails.
+            int sub = m;
+            if (tc32 && b.cexp != b.cin && ctx->tap_name != nm && !ctx->no_subbatch) {
+                const size_t per_img = (size_t)b.hin * b.hin * b.cexp * sizeof(T);
+                const size_t fit = (size_t)ctx->l2_budget / per_img;
+                if (fit < (size_t)m) sub = fit < 8 ? 8 : (int)fit;
+                if (sub > m) sub = m;
+            }
+            if (sub < m) {
+                T* dwo = e + (size_t)sub * b.hin * b.hin * b.cexp;          // depthwise output of the whole batch behind ONE sub-batch of expanded data
+                if (((size_t)sub * b.hin * b.hin + (size_t)Mout) * b.cexp * sizeof(T) > ctx->act[2].bytes) { ctx->err = "internal: expanded buffer too small"; return DFD_ERR_CAPACITY; }
+                for (int m0 = 0; m0 < m; m0 += sub) {
+                    const int mc = m - m0 < sub ? m - m0 : sub;
+                    ctx->label = L_EXP[i];
+                    if ((rc = pw(x + (size_t)m0 * b.hin * b.hin * b.cin, f.we, f.be, nullptr, 0, nullptr, e, mc * b.hin * b.hin, b.cexp, b.cin, 1))) return rc;
+                    ctx->label = L_DW[i];
+                    if ((rc = dfd_dw_f32(ctx, b, (const float*)e, Wf + f.wd, Wf + f.bd, (float*)(dwo + (size_t)m0 * b.hout * b.hout * b.cexp), mc,
+                                         &n_parts, st, m0))) return rc;
+                }
+                dw_out = dwo;
+                goto dw_done;
+            }
             if (b.cexp != b.cin) {
                 ctx->label = L_EXP[i];
                 if ((rc = pw(x, f.we, f.be, nullptr, 0, nullptr, e, Min, b.cexp, b.cin, 1))) return rc;
@@ -935,11 +962,12 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
             if constexpr (BF) {
                 if ((rc = dfd_dw_bf16(ctx, b, (const __nv_bfloat16*)dw_in, Wf + f.wd, Wf + f.bd, (__nv_bfloat16*)dw_out, m, &n_parts, st))) return rc;
             } else if (tc32) {
-                if ((rc = dfd_dw_f32(ctx, b, (const float*)dw_in, Wf + f.wd, Wf + f.bd, (float*)dw_out, m, &n_parts, st))) return rc;
+                if ((rc = dfd_dw_f32(ctx, b, (const float*)dw_in, Wf + f.wd, Wf + f.bd, (float*)dw_out, m, &n_parts, st, 0))) return rc;
             } else {
                 if ((rc = launch_dw<T, VEC>(ctx, b, dw_in, Wf + f.wd, Wf + f.bd, dw_out, m, &n_parts, st))) return rc;
             }
         }
+    dw_done:
         snprintf(nm, sizeof nm, "b%d.dw", i);
         if ((rc = tap<T>(ctx, nm, dw_out, (size_t)Mout * b.cexp, st))) return rc;
         ctx->label = L_SE[i];
