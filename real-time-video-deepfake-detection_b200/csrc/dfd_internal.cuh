@@ -234,6 +234,33 @@ __device__ __forceinline__ float swish_f32(float x) {
     e = fmaf(e * tl, 0.693147182464599609375f, e);
     return __fdividef(x, 1.0f + e);
 }
+// The same on two values with packed fp32 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): 6 packed + 2 scalar + 4 MUFU
+// instructions per PAIR instead of ~13 per value -- the epilogues of the fp32 expand convs and the depthwise kernel are
+// instruction-issue-bound.  u = -(lo part of the exponent); 2^(t - u) = 2^t (1 - u ln 2).
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t swish_f32x2(uint64_t x) {
+    const uint64_t L2E = f2_pack(1.44269502162933349609375f, 1.44269502162933349609375f);
+    uint64_t t = f2_mul(x, f2_pack(-1.44269502162933349609375f, -1.44269502162933349609375f));
+    uint64_t u = f2_fma(x, L2E, t);                                       // x * log2e + t, exact: minus the rounding error of t
+    u = f2_fma(x, f2_pack(1.92596299112661746e-8f, 1.92596299112661746e-8f), u);
+    float t0, t1, e0, e1;
+    f2_unpack(t, t0, t1);
+    t0 = fminf(t0, 126.0f); t1 = fminf(t1, 126.0f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+    uint64_t e = f2_pack(e0, e1);
+    e = f2_fma(f2_mul(e, u), f2_pack(-0.693147182464599609375f, -0.693147182464599609375f), e);
+    const uint64_t d = f2_add(e, f2_pack(1.0f, 1.0f));
+    float d0, d1, r0, r1;
+    f2_unpack(d, d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    return f2_mul(x, f2_pack(r0, r1));
+}
 #endif
 
 // forensics.cu

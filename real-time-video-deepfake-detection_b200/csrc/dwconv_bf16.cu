@@ -171,121 +171,3 @@ int dfd_dw_bf16(dfd_ctx* ctx, const EffBlock& b, const __nv_bfloat16* in, const 
     ctx->err = "dw_bf16: no tile configuration for this layer";
     return DFD_ERR_INVALID;
 }
-
-// ---------------------------------------------------------------------------------------------
-// fp32 accuracy mode: the same tiled design on fp32 activations.  CTA = TH x TW output pixels x 32 channels of one image
-// (a pixel's 32 channels are one 128-byte shared-memory row), lane = channel, warp = output row, plain fp32 FMAs in the
-// reference's tap order (ky, kx ascending, like the fp32 oracle's conv), swish_f32 (~3 ulp; not the approximate tanh of the bf16
-// path, which is 2^-11: the fp32 gate is 1e-4 on the probability).  Squeeze partials: fixed order, no atomics.
-template <int K, int S, int TW, int TH>
-__global__ void __launch_bounds__(DW_WARPS * 32)
-k_dw_tile_f32(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
-              float* __restrict__ out, float* __restrict__ pool, int C, int hin, int hout, int pad, int tiles_x) {
-    constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
-    constexpr int CC = 32;
-    extern __shared__ __align__(16) uint32_t smem_dw[];
-    float* patch = (float*)smem_dw;                          // [PH][PW][32]
-    float* sw = patch + PH * PW * CC;                        // [K*K][32]
-    float* spool = sw + K * K * CC;                          // [DW_WARPS][32]
-    const int tile = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
-    const int ty = tile / tiles_x, tx = tile % tiles_x;
-    const int oy0 = ty * TH, ox0 = tx * TW;
-    const int c0 = chunk * CC;
-    const int iy0 = oy0 * S - pad, ix0 = ox0 * S - pad;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    const uint32_t patch_s = (uint32_t)__cvta_generic_to_shared(patch);
-    const float* img = in + (size_t)b * hin * hin * C;
-    for (int idx = tid; idx < PH * PW * 8; idx += DW_WARPS * 32) {
-        const int pix = idx >> 3, part = idx & 7;
-        const int py = pix / PW, px = pix - py * PW;
-        const int iy = iy0 + py, ix = ix0 + px, c = c0 + part * 4;
-        const bool ok = iy >= 0 && iy < hin && ix >= 0 && ix < hin && c < C;      // C % 4 == 0: a 16-byte chunk is valid or not as a whole
-        const float* src = ok ? img + ((size_t)iy * hin + ix) * C + c : in;
-        cp_async16(patch_s + (uint32_t)((pix * CC + part * 4) * 4), src, ok ? 16 : 0);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int i = tid; i < K * K * CC; i += DW_WARPS * 32) {
-        const int c = c0 + (i % CC);
-        sw[i] = c < C ? W[(size_t)(i / CC) * C + c] : 0.f;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
-    const int ch = c0 + lane;
-    const bool ch_ok = ch < C;
-    const float bv = ch_ok ? bias[ch] : 0.f;
-    float ps = 0.f;
-    for (int r = warp; r < TH; r += DW_WARPS) {
-        const int oy = oy0 + r;
-        if (oy >= hout) break;
-        float acc[TW];
-#pragma unroll
-        for (int i = 0; i < TW; i++) acc[i] = bv;
-#pragma unroll
-        for (int ky = 0; ky < K; ky++) {
-            float w[K];
-#pragma unroll
-            for (int kx = 0; kx < K; kx++) w[kx] = sw[(ky * K + kx) * CC + lane];
-            const float* prow = patch + (size_t)((r * S + ky) * PW) * CC + lane;
-#pragma unroll
-            for (int ix = 0; ix < PW; ix++) {
-                const float x = prow[ix * CC];
-#pragma unroll
-                for (int kx = 0; kx < K; kx++)
-                    if ((ix - kx) % S == 0 && (ix - kx) >= 0 && (ix - kx) / S < TW) acc[(ix - kx) / S] = fmaf(x, w[kx], acc[(ix - kx) / S]);
-            }
-        }
-        float* orow = out + (((size_t)b * hout + oy) * hout + ox0) * C + ch;
-#pragma unroll
-        for (int i = 0; i < TW; i++) {
-            if (ox0 + i < hout && ch_ok) {
-                const float y = swish_f32(acc[i]);
-                ps += y;
-                orow[(size_t)i * C] = y;
-            }
-        }
-    }
-    spool[warp * CC + lane] = ps;
-    __syncthreads();
-    if (tid < CC && c0 + tid < C) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < DW_WARPS; wv++) sacc += spool[wv * CC + tid];
-        pool[((size_t)b * gridDim.x + tile) * C + c0 + tid] = sacc;
-    }
-}
-
-template <int K, int S, int TW, int TH>
-static int launch_f32(dfd_ctx* ctx, const EffBlock& b, const float* in, const float* W, const float* bias, float* out, int m,
-                      int* n_parts, cudaStream_t st, int img0) {
-    constexpr int PH = (TH - 1) * S + K, PW = (TW - 1) * S + K;
-    const size_t smem = ((size_t)PH * PW * 32 + (size_t)K * K * 32 + (size_t)DW_WARPS * 32) * 4;
-    { int rc = dfd_func_smem(ctx, k_dw_tile_f32<K, S, TW, TH>, smem); if (rc) return rc; }
-    const int tiles_x = (b.hout + TW - 1) / TW, tiles_y = (b.hout + TH - 1) / TH;
-    dim3 grid(tiles_x * tiles_y, (b.cexp + 31) / 32, m);
-    *n_parts = tiles_x * tiles_y;
-    if ((size_t)grid.x * b.cexp > DFD_POOL_FLOATS) { ctx->err = "internal: squeeze partial buffer too small"; return DFD_ERR_CAPACITY; }
-    // img0: first image of a sub-batch (in / out already point at it): its squeeze partials go to the images' own slots
-    k_dw_tile_f32<K, S, TW, TH><<<grid, DW_WARPS * 32, smem, st>>>(in, W, bias, out, ctx->d_pool + (size_t)img0 * grid.x * b.cexp, b.cexp, b.hin,
-                                                                   b.hout, b.pad, tiles_x);
-    DFD_LAUNCH_CHECK("k_dw_tile_f32", st);
-    return DFD_OK;
-}
-
-int dfd_dw_f32(dfd_ctx* ctx, const EffBlock& b, const float* in, const float* W, const float* bias, float* out, int m,
-               int* n_parts, cudaStream_t st, int img0) {
-    if (b.k == 3 && b.s == 1 && b.hout == 112) return launch_f32<3, 1, 16, 16>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 3 && b.s == 2 && b.hout == 56) return launch_f32<3, 2, 14, 8>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 3 && b.s == 1 && b.hout == 56) return launch_f32<3, 1, 14, 8>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 5 && b.s == 2 && b.hout == 28) return launch_f32<5, 2, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 5 && b.s == 1 && b.hout == 28) return launch_f32<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 3 && b.s == 2 && b.hout == 14) return launch_f32<3, 2, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 3 && b.s == 1 && b.hout == 14) return launch_f32<3, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 5 && b.s == 1 && b.hout == 14) return launch_f32<5, 1, 14, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 5 && b.s == 2 && b.hout == 7) return launch_f32<5, 2, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 5 && b.s == 1 && b.hout == 7) return launch_f32<5, 1, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    if (b.k == 3 && b.s == 1 && b.hout == 7) return launch_f32<3, 1, 7, 7>(ctx, b, in, W, bias, out, m, n_parts, st, img0);
-    ctx->err = "dw_f32: no tile configuration for this layer";
-    return DFD_ERR_INVALID;
-}

@@ -527,7 +527,7 @@ int dfd_tmap_encode(dfd_ctx* ctx, CUtensorMap* m, int dtype_f32, const void* bas
     cuuint32_t b[4], e[4] = {1, 1, 1, 1};
     for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; }
     for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
-    const CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle sw = swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = g_encode(m, dtype_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base, d, s, b, e,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled (rank " + std::to_string(rank) + ") failed (" + std::to_string((int)r) + ")"; return DFD_ERR_CUDA; }

@@ -422,7 +422,10 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                             if (last) {
                                 const float4 bq = *(const float4*)(sbias + n_base + col);
                                 v0 += bq.x; v1 += bq.y; v2 += bq.z; v3 += bq.w;
-                                if (ACT) { v0 = swish_exact(v0); v1 = swish_exact(v1); v2 = swish_exact(v2); v3 = swish_exact(v3); }
+                                if (ACT) {
+                                    const uint64_t s01 = swish_f32x2(f2_pack(v0, v1)), s23 = swish_f32x2(f2_pack(v2, v3));
+                                    f2_unpack(s01, v0, v1); f2_unpack(s23, v2, v3);
+                                }
                                 if (RES && rrow && n_base + col + 4 <= p.N) { v0 += rcur[h].x; v1 += rcur[h].y; v2 += rcur[h].z; v3 += rcur[h].w; }
                             }
                             sts128(addr, make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3)));
@@ -507,13 +510,17 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     if (col < p.n_pad) {
                         const int n = n_base + col;
                         const float4 bq = *(const float4*)(sbias + n);
-                        const float cp = p.beta_plain;
-                        float v0 = fmaf(__uint_as_float(r[h * 4]), cp, __uint_as_float(r[h * 4])) + bq.x;
-                        float v1 = fmaf(__uint_as_float(r[h * 4 + 1]), cp, __uint_as_float(r[h * 4 + 1])) + bq.y;
-                        float v2 = fmaf(__uint_as_float(r[h * 4 + 2]), cp, __uint_as_float(r[h * 4 + 2])) + bq.z;
-                        float v3 = fmaf(__uint_as_float(r[h * 4 + 3]), cp, __uint_as_float(r[h * 4 + 3])) + bq.w;
-                        if (ACT) { v0 = swish_exact(v0); v1 = swish_exact(v1); v2 = swish_exact(v2); v3 = swish_exact(v3); }
-                        if (RES && rrow && n + 4 <= p.N) { v0 += rcur[h].x; v1 += rcur[h].y; v2 += rcur[h].z; v3 += rcur[h].w; }
+                        // packed fp32 pairs: acc + acc * beta (beta is below fp32's resolution of 1 + beta: it must multiply the
+                        // accumulator, not be added to one), + bias, swish_f32x2, + residual
+                        const uint64_t cp2 = f2_pack(p.beta_plain, p.beta_plain);
+                        const uint64_t r01 = f2_pack(__uint_as_float(r[h * 4]), __uint_as_float(r[h * 4 + 1]));
+                        const uint64_t r23 = f2_pack(__uint_as_float(r[h * 4 + 2]), __uint_as_float(r[h * 4 + 3]));
+                        uint64_t a01 = f2_add(f2_fma(r01, cp2, r01), f2_pack(bq.x, bq.y));
+                        uint64_t a23 = f2_add(f2_fma(r23, cp2, r23), f2_pack(bq.z, bq.w));
+                        if (ACT) { a01 = swish_f32x2(a01); a23 = swish_f32x2(a23); }
+                        if (RES && rrow && n + 4 <= p.N) { a01 = f2_add(a01, f2_pack(rcur[h].x, rcur[h].y)); a23 = f2_add(a23, f2_pack(rcur[h].z, rcur[h].w)); }
+                        float v0, v1, v2, v3;
+                        f2_unpack(a01, v0, v1); f2_unpack(a23, v2, v3);
                         const uint4 o = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
                         if (DENSE) { if (col < p.N) sts128(buf + (uint32_t)(row * (p.N * 4) + h * 16), o); }
                         else sts128(buf + (uint32_t)(row * 128 + ((h ^ (row & 7)) << 4)), o);

@@ -508,7 +508,7 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
     else DFD_CUDA(cudaEventCreateWithFlags(&ctx->jpg_ev, cudaEventDisableTiming));
     // ---- host: headers only ----
     long long words = 0, subs = 0;
-    int chunks = 0, max_ecs = 0;
+    int chunks = 0, max_ecs = 0, max_blocks = 0;
     const long long total_bytes = offsets_host[n] - offsets_host[0];
     for (int i = 0; i < n; i++) {
         const long long b0 = offsets_host[i], b1 = offsets_host[i + 1];
@@ -535,10 +535,11 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
         subs += ((long long)m.ecs_bytes * 8 + JPG_SUB_BITS - 1) / JPG_SUB_BITS + 1;
         chunks += (m.ecs_bytes + JU_CHUNK - 1) / JU_CHUNK + 1;
         if (m.ecs_bytes > max_ecs) max_ecs = m.ecs_bytes;
+        if (h->total_blocks > max_blocks) max_blocks = h->total_blocks;
     }
-    // workspaces (worst case 4:4:4 with 16-pixel MCU padding: 3 components of ceil16(H) x ceil16(W))
-    const long long bw = (W + 15) / 16 * 2, bh = (H + 15) / 16 * 2;
-    const long long blocks_stride = 3 * bw * bh;
+    // workspaces: per frame, the largest block count of the batch (4:2:0 needs half of 4:4:4; the coefficient array is zeroed
+    // on every call, so its size is time)
+    const long long blocks_stride = (max_blocks + 1) & ~1;
     const long long plane_stride = blocks_stride * 64;
     int rc;
     if ((rc = dfd_ensure(ctx, ctx->jpg_raw, (size_t)total_bytes + 16))) return rc;
