@@ -12,18 +12,21 @@
 // which restores ~22 bits per product ("3xTF32").  That alone is NOT fp32 accuracy: the tensor core adds into its fp32
 // accumulator with ROUND-TOWARD-ZERO, one truncation per MMA instruction (K = 8), so a single accumulator drifts
 // systematically by ~1 ulp per instruction -- measured here: relative error 4e-8 x K, i.e. 4.5e-5 at K = 1152, and
-// |dp| = 4.7e-4 on the whole network (the fp32 CUDA-core path: 9e-6).  Layers with K > 64 therefore accumulate in CHUNKS of
-// four k-blocks (K = 128), and within a chunk the small correction products (A_lo.W_hi + A_hi.W_lo) and the main product
-// (A_hi.W_hi) go to TWO different TMEM accumulators of the ring, so the main accumulator sees 16 truncations per chunk
-// instead of 12 x K / 32 per tile.  The epilogue warps -- idle during the k-loop anyway -- drain every accumulator as it
-// completes and add it, with round-to-nearest FADDs, into a running tile in shared memory (the store-staging buffer in
-// its final layout).  The truncation of a chunk is relative to the chunk's own small magnitude and follows the chunk's
-// sign, so across chunks it averages out instead of accumulating (Ootomo & Yokota's observation for Ampere mma.sync,
-// restated for TMEM accumulators).  What remains is, to 70 %, a pure SCALE factor: truncation toward zero shrinks an
-// accumulator by an expected 2.5e-8 * n^0.87 after n accumulations (tools/tf32_bias.py, profiles/tf32_bias_r02.txt).  The
-// epilogue multiplies every drained main-term chunk by 1 + that expectation, which turns round-toward-zero into an
-// unbiased rounding.  Measured at K = 1152: max relative error 4.5e-5 (one accumulator) -> 2.5e-6 (chunks) -> rms 1.5e-7
-// with a residual scale bias of 3e-9; whole network: max |dp| 4.7e-4 -> 6e-6 (fp32 CUDA-core path: 9e-6).
+// |dp| = 4.7e-4 on the whole network (the fp32 CUDA-core path: 9e-6).  Three measures:
+//  (1) the small correction products (A_lo.W_hi + A_hi.W_lo) and the main product (A_hi.W_hi) go to TWO different TMEM
+//      accumulators of the ring -- added to a large accumulator under round-toward-zero, a tiny addend of the opposite sign
+//      costs a whole ulp -- and the epilogue adds the pair;
+//  (2) layers with K > 160 accumulate in CHUNKS of four k-blocks (K = 128): every chunk starts a fresh accumulator pair, and
+//      the epilogue warps -- idle during the k-loop anyway -- drain every accumulator as it completes and add it, with
+//      round-to-nearest FADDs, into a running tile in shared memory (the store-staging buffer in its final layout).  The
+//      truncation of a chunk is relative to the chunk's own small magnitude and follows the chunk's sign, so across chunks it
+//      averages out instead of accumulating (Ootomo & Yokota's observation for Ampere mma.sync, restated for TMEM);
+//  (3) what remains is, to 70 %, a pure SCALE factor: truncation toward zero shrinks a main-term accumulator by an expected
+//      2.51e-8 * n^0.87 after n accumulations (tools/tf32_bias.py, profiles/tf32_bias_r02.txt: 8.4e-8 / 1.5e-7 / 2.8e-7 at
+//      n = 4 / 8 / 16), and the epilogue multiplies every drained main accumulator by 1 + that expectation, which turns
+//      round-toward-zero into an unbiased rounding.  The same law holds for the single pair of the shallow (K <= 160) layers.
+// Measured: rms relative error 0.6e-7 .. 1.9e-7 for every layer shape with a residual scale bias below 1.3e-8 (one accumulator
+// at K = 1152: 4.5e-5); whole network max |dp| 4.7e-4 -> 8e-6 (fp32 CUDA-core path: 9e-6).
 // The weights are split once on the host (W_hi / W_lo planes).  The activations are split ON THE FLY, tile by tile, in
 // shared memory, so HBM holds plain fp32 tensors:
 //
@@ -60,9 +63,10 @@ struct TGemmParams {
     int n_pad, n_blocks, num_tiles, stages, act, a_mode, hw, b_resident, n_acc, epi_db, dense_c;
     int ch;                    // k-blocks per accumulation chunk
     float beta_instr;          // expected relative shrink of a main-term accumulator after n MMA accumulations (round toward zero) = beta_instr * n^0.87, compensated in the epilogue
-    float beta_plain;          // same, total, for the single-accumulator (K <= 64) layers
-    int chunked;               // 1: every chunk uses TWO ring accumulators (correction terms, main term) that the epilogue adds into
-                               //    a running tile with round-to-nearest; 0 (K <= 64): one accumulator per tile, plain epilogue
+    float beta_plain;          // the same expectation for the one main-term accumulator of a plain (K <= 160) layer
+    int chunked;               // every chunk uses TWO ring accumulators (correction terms, main term).  1: several chunks per tile, the
+                               //    epilogue adds them into a running tile with round-to-nearest; 0 (K <= 160): one chunk per tile,
+                               //    plain ping-pong epilogue (main * (1 + beta) + corrections)
     const float* bias;
     const float* residual;
     const float* A;            // A_STEM: NHWC input [B,224,224,3]
@@ -96,6 +100,12 @@ __device__ __forceinline__ void tf32_split4(const float4 v, uint4& hi, uint4& lo
 }
 __device__ __forceinline__ float swish_exact(float x) { return swish_f32(x); }
 __device__ __forceinline__ bool jb_none(int grp, int nblk32) { return grp >= nblk32; }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
 
 template <bool RES, bool ACT, bool DENSE>
 __global__ void __launch_bounds__(TGEMM_THREADS, 1)
@@ -190,13 +200,13 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 uint32_t d_main = 0, d_corr = 0;
                 for (int kb = 0; kb < num_kb; kb++) {
-                    const int kc = p.chunked ? kb % p.ch : kb;
-                    if (kc == 0) {                                 // a new chunk: fresh accumulator(s) of the ring
+                    const int kc = kb % p.ch;                      // (plain layers: ch = num_kb, one chunk per tile)
+                    if (kc == 0) {                                 // a new chunk: a fresh PAIR of accumulators of the ring
                         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
-                        if (p.chunked) mbar_wait(tempty0 + 8 * (acc + 1), acc_phase ^ 1);
+                        mbar_wait(tempty0 + 8 * (acc + 1), acc_phase ^ 1);
                         tc_fence_after();
                         d_corr = tmem_base + (uint32_t)(acc * p.n_pad);
-                        d_main = p.chunked ? d_corr + (uint32_t)p.n_pad : d_corr;
+                        d_main = d_corr + (uint32_t)p.n_pad;
                     }
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
@@ -206,19 +216,20 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const uint64_t b_hi = make_smem_desc(sb), b_lo = make_smem_desc(sb + b_plane_bytes);
                     const int krem = p.K - kb * TBLOCK_K;
                     const int ksteps = krem >= TBLOCK_K ? TBLOCK_K / 8 : (krem + 7) / 8;
-                    // correction terms (into their own accumulator when chunked), then the dominant hi.hi product
+                    // correction terms into their own accumulator (added to a large accumulator, a tiny addend of the opposite sign
+                    // costs a whole ulp under round-toward-zero), then the dominant hi.hi product
                     for (int k = 0; k < ksteps; k++)
                         tc_mma_tf32(d_corr, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (kc | k) != 0);
                     for (int k = 0; k < ksteps; k++)
                         tc_mma_tf32(d_corr, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc, 1u);
                     for (int k = 0; k < ksteps; k++)
-                        tc_mma_tf32(d_main, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, p.chunked ? (uint32_t)((kc | k) != 0) : 1u);
+                        tc_mma_tf32(d_main, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (uint32_t)((kc | k) != 0));
                     tc_commit(empty0 + 8 * stage);                 // frees the smem stage when the MMAs retire
-                    const bool chunk_end = kb == num_kb - 1 || (p.chunked && kc == p.ch - 1);
-                    if (chunk_end) {                               // publish the accumulator(s), move on in the ring
+                    const bool chunk_end = kb == num_kb - 1 || kc == p.ch - 1;
+                    if (chunk_end) {                               // publish the pair, move on in the ring
                         tc_commit(tfull0 + 8 * acc);
-                        if (p.chunked) tc_commit(tfull0 + 8 * (acc + 1));
-                        acc += p.chunked ? 2 : 1;
+                        tc_commit(tfull0 + 8 * (acc + 1));
+                        acc += 2;
                         if (acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -473,11 +484,14 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const int m = m_blk * TBLOCK_M + row;
             const bool row_ok = m < p.M;
             const int n_base = n_blk * p.n_pad;
-            const int acc = it % p.n_acc;                          // n_acc is even: an accumulator always belongs to the same set
+            const int npairs = p.n_acc >> 1;
+            const int acc = 2 * (it % npairs);                     // corrections in accumulator acc, main term in acc + 1
             const float* rrow = (RES && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
-            mbar_wait(tfull0 + 8 * acc, (uint32_t)(it / p.n_acc) & 1u);
+            mbar_wait(tfull0 + 8 * acc, (uint32_t)(it / npairs) & 1u);
+            mbar_wait(tfull0 + 8 * (acc + 1), (uint32_t)(it / npairs) & 1u);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
+            const uint32_t taddr_c = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
+            const uint32_t taddr = taddr_c + (uint32_t)p.n_pad;
             for (int jb = 0; jb < nblk32; jb++, blk_count++) {
                 const uint32_t buf = my_staging + (p.epi_db ? (blk_count & 1u) * TSTAGING_BLOCK_BYTES : 0u);
                 // one buffer: its previous store must have been read before anyone writes -> wait + barrier here; two buffers:
@@ -499,10 +513,24 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     }
                 }
                 tc_ld_wait();
-                if (jb + 1 >= nblk32) {                            // last TMEM read of this tile: hand the accumulator back before the math
+                {   // main * (1 + beta) + corrections, 16 columns of the correction accumulator at a time (register budget)
+                    const float cp = p.beta_plain;
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        uint32_t qc[16];
+                        tc_ld16(taddr_c + jb * 32 + hh * 16, qc);
+                        tc_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float mv = __uint_as_float(r[hh * 16 + j]);
+                            r[hh * 16 + j] = __float_as_uint(fmaf(mv, cp, mv) + __uint_as_float(qc[j]));
+                        }
+                    }
+                }
+                if (jb + 1 >= nblk32) {                            // last TMEM read of this tile: hand the accumulators back before the math
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                    if (lane == 0) { mbar_arrive(tempty0 + 8 * acc); mbar_arrive(tempty0 + 8 * (acc + 1)); }
                 }
 #pragma unroll
                 for (int h = 0; h < 8; h++) {
@@ -510,13 +538,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     if (col < p.n_pad) {
                         const int n = n_base + col;
                         const float4 bq = *(const float4*)(sbias + n);
-                        // packed fp32 pairs: acc + acc * beta (beta is below fp32's resolution of 1 + beta: it must multiply the
-                        // accumulator, not be added to one), + bias, swish_f32x2, + residual
-                        const uint64_t cp2 = f2_pack(p.beta_plain, p.beta_plain);
+                        // packed fp32 pairs: + bias, swish_f32x2, + residual
                         const uint64_t r01 = f2_pack(__uint_as_float(r[h * 4]), __uint_as_float(r[h * 4 + 1]));
                         const uint64_t r23 = f2_pack(__uint_as_float(r[h * 4 + 2]), __uint_as_float(r[h * 4 + 3]));
-                        uint64_t a01 = f2_add(f2_fma(r01, cp2, r01), f2_pack(bq.x, bq.y));
-                        uint64_t a23 = f2_add(f2_fma(r23, cp2, r23), f2_pack(bq.z, bq.w));
+                        uint64_t a01 = f2_add(r01, f2_pack(bq.x, bq.y));
+                        uint64_t a23 = f2_add(r23, f2_pack(bq.z, bq.w));
                         if (ACT) { a01 = swish_f32x2(a01); a23 = swish_f32x2(a23); }
                         if (RES && rrow && n + 4 <= p.N) { a01 = f2_add(a01, f2_pack(rcur[h].x, rcur[h].y)); a23 = f2_add(a23, f2_pack(rcur[h].z, rcur[h].w)); }
                         float v0, v1, v2, v3;
@@ -609,7 +635,10 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     static const int force_ch = getenv("DFD_TF32_CHUNK") ? atoi(getenv("DFD_TF32_CHUNK")) : 0;
     p.ch = 4;                                                // K = 128 per chunk: 16 main-term accumulations per accumulator
     if (force_ch > 0) p.ch = force_ch;
-    const bool chunked = num_kb > 2;
+    if (num_kb <= 5) p.ch = num_kb;                          // plain layers: one chunk (= one accumulator pair) per tile
+    // K <= 160 (five k-blocks): one accumulator per tile and the ping-pong epilogue -- the shallow layers are huge-M and
+    // epilogue-bound (b2.project: 196 us plain, 310 us chunked), their truncation bias is small and compensated as a whole
+    const bool chunked = num_kb > 5;
     p.chunked = chunked ? 1 : 0;
     // Expected-value compensation of the tensor core's round-toward-zero accumulation (measured with tools/tf32_bias.py: the
     // GEMM's error is, to 70 %, a pure scale factor 1 - beta; profiles/tf32_bias_r02.txt).  Chunked layers: beta per main-term
@@ -617,8 +646,7 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     static const float beta_env = getenv("DFD_TF32_BETA") ? (float)atof(getenv("DFD_TF32_BETA")) : -1.f;
     // measured shrink of a main-term accumulator: 8.4e-8 / 1.5e-7 / 2.8e-7 after 4 / 8 / 16 accumulations = 2.51e-8 * n^0.87
     p.beta_instr = beta_env >= 0.f ? beta_env : 2.51e-8f;
-    p.beta_plain = K <= 16 ? 3.1e-8f : K <= 24 ? 4.8e-8f : K <= 32 ? 5.9e-8f : 1.2e-7f;
-    if (beta_env >= 0.f) p.beta_plain *= beta_env / 2.51e-8f;
+    p.beta_plain = p.beta_instr * powf((float)((K + 7) / 8), 0.87f);     // the main-term accumulator of a plain layer: same law
     const int nblk32 = (n_pad + 31) / 32;
     int staging_bytes = chunked ? nblk32 * TSTAGING_BLOCK_BYTES : 4 * TSTAGING_BLOCK_BYTES;
     p.epi_db = 1;
