@@ -150,6 +150,9 @@ ROUTES = {("GET", "/health"): health_check, ("POST", "/reset"): reset_detector,
 class App:
     """Minimal WSGI application with the slice of Flask's surface the reference's tests use."""
 
+    def __init__(self):
+        self.config = {}            # Flask's app.config (the reference's tests set TESTING)
+
     def __call__(self, environ, start_response):
         request = Request(environ)
         if request.method == "OPTIONS":

@@ -17,6 +17,7 @@ from . import _lib, runtime
 from .frame_analysis import FrameForensicAnalyzer
 
 _model_state = {"sd": None, "loaded": False}
+DEVICE = "cuda:0" if torch.cuda.is_available() else "cpu"      # deepfake_detection.py:21 (module attribute, a string)
 
 
 def load_model_weights(state_dict_or_path):
