@@ -132,6 +132,39 @@ int dfd_effnet_forward(dfd_ctx* ctx, const void* in_nhwc, int m, int dtype, floa
  * When m equals the box count of the context's last dfd_face_prep_batch call, boxes that call rejected get NaN. */
 int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, void* stream);
 
+/* Test-time augmentation, analyze_face_with_tta (deepfake_detection.py:408-443): n_pred predictions per face -- the
+ * preprocessed (CLAHE'd) crop itself and n_pred - 1 augmented copies of it: cv2.flip(.., 1) when `flip`,
+ * cv2.convertScaleAbs(alpha = brightness), cv2.warpAffine with cv2.getRotationMatrix2D((w/2, h/2), angle, 1.0) -- each then
+ * resized / normalised like dfd_face_prep_batch's crops.  All pixel work is on the device and bit-exact with OpenCV; the
+ * caller draws the random parameters (the reference uses Python's global `random`: see dfd_b200/tta.py, which consumes it in
+ * the reference's order) and supplies, per augmentation, the INVERSE of the 2 x 3 rotation matrix (the inversion
+ * cv2.warpAffine performs before its loops; a dozen double operations, done on the host so that cos / sin come from the same
+ * libm as the reference's).  augs: DEVICE array of m * (n_pred - 1) records, box-major.  out: m * n_pred crops, crop
+ * i * n_pred + j = prediction j of box i (j = 0 un-augmented).  Requires m * n_pred <= max_batch and n_pred <= DFD_TTA_MAX_PRED;
+ * the matrices must be built from the box sizes AFTER clamping to the frame (what face_region.shape is in the reference). */
+#define DFD_TTA_MAX_PRED 16
+typedef struct {
+    int32_t flip;                 /* 1 = cv2.flip(aug, 1)                              deepfake_detection.py:422-423 */
+    float brightness;             /* float32(random.uniform(0.9, 1.1))                 :426-427 */
+    double im[6];                 /* inverse of getRotationMatrix2D((w/2, h/2), angle) :430-433 */
+} dfd_tta_aug;
+int dfd_face_prep_tta(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride, int row_pitch,
+                      const int32_t* boxes, const int32_t* frame_idx, int m, int n_pred, const dfd_tta_aug* augs,
+                      void* out_nhwc, int dtype, void* stream);
+/* np.mean of the n_pred sigmoids of each box (float64, NumPy's summation order) + apply_calibration + apply_heuristics
+ * (deepfake_detection.py:441, 445-455, 489-502): logits[m * n_pred] -> prob[m]. */
+int dfd_face_probability_tta(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, int n_pred, double* prob,
+                             void* stream);
+
+/* apply_calibration (deepfake_detection.py:445-455; weights/calibrator.pkl, not shipped): the probability map applied
+ * between the classifier and the heuristics by dfd_face_probability(_tta) and dfd_analyze_batch.
+ *   DFD_CALIB_NONE              identity (the reference without calibrator.pkl)
+ *   DFD_CALIB_LOGISTIC          n = 1: expit(xs[0] * p + ys[0])  (Platt scaling / sklearn LogisticRegression on the raw probability)
+ *   DFD_CALIB_PIECEWISE_LINEAR  n knots (xs strictly increasing): np.interp(p, xs, ys)  (sklearn IsotonicRegression)
+ * xs / ys are HOST arrays, copied before the call returns. */
+typedef enum { DFD_CALIB_NONE = 0, DFD_CALIB_LOGISTIC = 1, DFD_CALIB_PIECEWISE_LINEAR = 2 } dfd_calibrator_kind;
+int dfd_set_calibrator(dfd_ctx* ctx, int kind, int n, const double* xs_host, const double* ys_host, void* stream);
+
 /* TemporalTracker.update for n streams (deepfake_detection.py:120-196).  vote_input[i] NaN = update(None).
  * np_flags (nullable, device u8[n]): 1 where the reference's value would be a numpy scalar (the face
  * probability returned by np.clip, deepfake_detection.py:502) rather than a Python float; it selects how
@@ -164,6 +197,28 @@ int dfd_decode_jpeg_batch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_t
 /* HOST-only header peek (no context): info = {H, W, components, luma h sampling, luma v sampling}; returns 0 if the stream is
  * decodable by dfd_decode_jpeg_batch, DFD_ERR_UNSUPPORTED / DFD_ERR_INVALID otherwise (info is filled when SOF was seen). */
 int dfd_jpeg_info(const uint8_t* bytes_host, size_t n_bytes, int32_t* info);
+
+/* Result annotation: draw_detection_overlay / _draw_frame_analysis_overlay (deepfake_detection.py:559-586, 688-726) on the
+ * DEVICE copy of one frame, in place, bit-exact with the OpenCV calls the reference makes.  cmds_host[n_cmds] (HOST, applied in
+ * order like successive OpenCV calls; n_cmds <= DFD_DRAW_MAX_CMDS):
+ *   DFD_DRAW_OUTLINE  cv2.rectangle(img, (x0,y0), (x1,y1), color, thickness >= 1)
+ *   DFD_DRAW_FILL     cv2.rectangle(.., thickness = -1)
+ *   DFD_DRAW_BLEND    overlay = img.copy(); cv2.rectangle(overlay, (x0,y0), (x1,y1), color, -1);
+ *                     cv2.addWeighted(overlay, alpha, img, beta, 0, img)
+ *   DFD_DRAW_MASK     cv2.putText: masks_host[mask_off .. + mask_w*mask_h) is the string's stroke mask (nonzero = ink), its
+ *                     top-left corner at (x0, y0); ink pixels take `color`.  The caller rasterises the string with OpenCV's
+ *                     Hershey font (dfd_b200/overlay.py): glyph outlines are font data, every frame pixel is written here.
+ * color is B, G, R.  Coordinates may lie outside the frame (clipped like OpenCV).  The host arrays are free on return. */
+#define DFD_DRAW_MAX_CMDS 64
+typedef enum { DFD_DRAW_OUTLINE = 1, DFD_DRAW_FILL = 2, DFD_DRAW_BLEND = 3, DFD_DRAW_MASK = 4 } dfd_draw_op;
+typedef struct {
+    int32_t op, x0, y0, x1, y1, thickness;
+    uint8_t color[4];             /* B, G, R, unused */
+    float alpha, beta;            /* DFD_DRAW_BLEND only */
+    int32_t mask_off, mask_w, mask_h, reserved;
+} dfd_draw_cmd;
+int dfd_draw_overlay(dfd_ctx* ctx, uint8_t* frame, int H, int W, int row_pitch, const dfd_draw_cmd* cmds_host, int n_cmds,
+                     const uint8_t* masks_host, size_t mask_bytes, void* stream);
 
 /* DeepfakeDetector.reset / FrameForensicAnalyzer.reset / TemporalTracker.reset
  * (deepfake_detection.py:344-355, 270-289; frame_analysis.py:391-395).  stream_id < 0 resets all. */

@@ -61,3 +61,25 @@ def heuristics(p, crop_h, crop_w):
     (np.float64 result)."""
     adj = 0.10 if (crop_h < 80 or crop_w < 80) else 0.0
     return np.clip(p + adj, 0, 1)
+
+
+def tta_augment(face_bgr, flip, brightness, angle):
+    """One augmentation of ``analyze_face_with_tta`` (deepfake_detection.py:417-434) with the random draws made explicit."""
+    aug = face_bgr.copy()
+    if flip:
+        aug = cv2.flip(aug, 1)
+    aug = cv2.convertScaleAbs(aug, alpha=brightness, beta=0)
+    h, w = aug.shape[:2]
+    M = cv2.getRotationMatrix2D((w / 2, h / 2), angle, 1.0)
+    return cv2.warpAffine(aug, M, (w, h))
+
+
+def tta_faces(face_bgr, params):
+    """[preprocessed, augmented...]: the images ``_single_prediction`` sees under TTA (deepfake_detection.py:520-526, 408-438):
+    CLAHE first, augmentations of the CLAHE'd crop."""
+    pre = clahe_lab(face_bgr)
+    return [pre] + [tta_augment(pre, *p) for p in params]
+
+
+def to_input_noclahe(face_bgr_u8):
+    return to_input(resize160(face_bgr_u8))

@@ -48,6 +48,10 @@ SYMBOLS = {
     "dfd_face_prep_batch": (_I, [_P, _P, _I, _I, _I, _S, _I, _P, _P, _I, _P, _I, _P]),
     "dfd_effnet_forward": (_I, [_P, _P, _I, _I, _P, _P]),
     "dfd_face_probability": (_I, [_P, _P, _P, _I, _P, _P]),
+    "dfd_face_prep_tta": (_I, [_P, _P, _I, _I, _I, _S, _I, _P, _P, _I, _I, _P, _P, _I, _P]),
+    "dfd_face_probability_tta": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "dfd_set_calibrator": (_I, [_P, _I, _I, _P, _P, _P]),
+    "dfd_draw_overlay": (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _S, _P]),
     "dfd_vote_update": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "dfd_analyze_batch": (_I, [_P, _P, _I, _I, _I, _S, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "dfd_decode_jpeg_batch": (_I, [_P, _P, _P, _I, _I, _I, _P, _S, _I, _P, _P]),

@@ -147,6 +147,17 @@ ROUTES = {("GET", "/health"): health_check, ("POST", "/reset"): reset_detector,
           ("POST", "/analyze"): analyze_frame, ("GET", "/stats"): get_stats}
 
 
+class _TestClient(Client):
+    """werkzeug's test client with Flask's context-manager form (``with app.test_client() as c:``); responses are werkzeug
+    TestResponse objects (``status_code``, ``data``, ``get_json()``, ``json``) like Flask's."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class App:
     """Minimal WSGI application with the slice of Flask's surface the reference's tests use."""
 
@@ -167,7 +178,7 @@ class App:
         return resp(environ, start_response)
 
     def test_client(self):
-        return Client(self, Response)
+        return _TestClient(self)
 
     def run(self, host="0.0.0.0", port=5000, debug=False, threaded=True):
         from werkzeug.serving import run_simple

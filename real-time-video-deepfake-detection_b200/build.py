@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["dfd_api.cu", "forensics.cu", "faceprep.cu", "effnet.cu", "vote.cu", "gemm_tcgen05.cu", "gemm_tf32x3.cu", "dwconv_bf16.cu", "dwconv_f32.cu", "mbconv_fused.cu", "jpegdec.cu"]
+SOURCES = ["dfd_api.cu", "forensics.cu", "faceprep.cu", "effnet.cu", "vote.cu", "gemm_tcgen05.cu", "gemm_tf32x3.cu", "dwconv_bf16.cu", "dwconv_f32.cu", "mbconv_fused.cu", "jpegdec.cu", "overlay.cu"]
 OUT = os.path.join(HERE, "libdfd.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]

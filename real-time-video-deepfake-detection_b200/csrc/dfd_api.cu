@@ -45,6 +45,21 @@ void dfd_trace(dfd_ctx* ctx, const char* kernel, cudaStream_t st) {
     fflush(stderr);
 }
 
+#include <map>
+#include <mutex>
+int dfd_func_smem_raise(dfd_ctx* ctx, const void* fn, size_t bytes, bool full_carveout) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> limit;          // (device, function) -> bytes set so far
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = limit[{ctx->cfg.device, fn}];
+    if (bytes > cur) {
+        DFD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        if (full_carveout) DFD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        cur = bytes;
+    }
+    return DFD_OK;
+}
+
 extern "C" {
 
 int dfd_profile_start(dfd_ctx* ctx, void* stream) {
@@ -212,7 +227,9 @@ void dfd_destroy(dfd_ctx* ctx) {
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     dfd_gemm_free(ctx);
     dfd_jpeg_free(ctx);
-    for (DfdBuf* b : {&ctx->jpg_raw, &ctx->jpg_words, &ctx->jpg_sub, &ctx->jpg_coef, &ctx->jpg_dc, &ctx->jpg_planes, &ctx->jpg_hdr})
+    if (ctx->draw_host) cudaFreeHost(ctx->draw_host);
+    for (DfdBuf* b : {&ctx->jpg_raw, &ctx->jpg_words, &ctx->jpg_sub, &ctx->jpg_coef, &ctx->jpg_dc, &ctx->jpg_planes, &ctx->jpg_hdr, &ctx->tta_base,
+                      &ctx->calib, &ctx->draw_buf})
         if (b->p) cudaFree(b->p);
     delete ctx;
 }
@@ -254,7 +271,54 @@ int dfd_face_probability(dfd_ctx* ctx, const float* logits, const int32_t* boxes
     if (!ctx) return DFD_ERR_INVALID;
     DfdDeviceGuard dev_guard(ctx->cfg.device);
     DFD_REQUIRE(logits && boxes && prob && m > 0, DFD_ERR_INVALID, "face_probability: bad argument");
-    return dfd_faceprob_launch(ctx, logits, boxes, m, prob, (cudaStream_t)stream);
+    return dfd_faceprob_launch(ctx, logits, boxes, m, 1, prob, (cudaStream_t)stream);
+}
+
+int dfd_face_prep_tta(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride, int row_pitch,
+                      const int32_t* boxes, const int32_t* frame_idx, int m, int n_pred, const dfd_tta_aug* augs,
+                      void* out_nhwc, int dtype, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
+    DFD_REQUIRE(frames && boxes && frame_idx && out_nhwc, DFD_ERR_INVALID, "face_prep_tta: null pointer");
+    return dfd_faceprep_tta_launch(ctx, frames, n_frames, H, W, frame_stride, row_pitch, boxes, frame_idx, m, n_pred, augs, out_nhwc,
+                                   dtype, (cudaStream_t)stream);
+}
+
+int dfd_face_probability_tta(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, int n_pred, double* prob,
+                             void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
+    DFD_REQUIRE(logits && boxes && prob && m > 0 && n_pred >= 1 && n_pred <= DFD_TTA_MAX_PRED, DFD_ERR_INVALID,
+                "face_probability_tta: bad argument");
+    return dfd_faceprob_launch(ctx, logits, boxes, m, n_pred, prob, (cudaStream_t)stream);
+}
+
+int dfd_draw_overlay(dfd_ctx* ctx, uint8_t* frame, int H, int W, int row_pitch, const dfd_draw_cmd* cmds_host, int n_cmds,
+                     const uint8_t* masks_host, size_t mask_bytes, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
+    DFD_REQUIRE(frame && (n_cmds == 0 || cmds_host) && (mask_bytes == 0 || masks_host), DFD_ERR_INVALID, "draw_overlay: null pointer");
+    return dfd_overlay_launch(ctx, frame, H, W, row_pitch, cmds_host, n_cmds, masks_host, mask_bytes, (cudaStream_t)stream);
+}
+
+int dfd_set_calibrator(dfd_ctx* ctx, int kind, int n, const double* xs_host, const double* ys_host, void* stream) {
+    if (!ctx) return DFD_ERR_INVALID;
+    DfdDeviceGuard dev_guard(ctx->cfg.device);
+    DFD_REQUIRE(kind >= DFD_CALIB_NONE && kind <= DFD_CALIB_PIECEWISE_LINEAR, DFD_ERR_INVALID, "set_calibrator: unknown kind");
+    if (kind == DFD_CALIB_NONE) { ctx->calib_kind = 0; ctx->calib_n = 0; return DFD_OK; }
+    DFD_REQUIRE(xs_host && ys_host && n >= 1 && n <= (1 << 20), DFD_ERR_INVALID, "set_calibrator: bad table");
+    DFD_REQUIRE(kind != DFD_CALIB_LOGISTIC || n == 1, DFD_ERR_INVALID, "set_calibrator: the logistic kind takes one (coef, intercept) pair");
+    for (int i = 1; i < n; i++)
+        DFD_REQUIRE(xs_host[i] > xs_host[i - 1], DFD_ERR_INVALID, "set_calibrator: xs must be strictly increasing");
+    cudaStream_t st = (cudaStream_t)stream;
+    DFD_CUDA(cudaStreamSynchronize(st));                        // a running k_faceprob may still read the old table
+    int rc = dfd_ensure(ctx, ctx->calib, (size_t)2 * n * sizeof(double));
+    if (rc) return rc;
+    DFD_CUDA(cudaMemcpyAsync(ctx->calib.p, xs_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    DFD_CUDA(cudaMemcpyAsync((double*)ctx->calib.p + n, ys_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    DFD_CUDA(cudaStreamSynchronize(st));                        // the host arrays belong to the caller
+    ctx->calib_kind = kind; ctx->calib_n = n;
+    return DFD_OK;
 }
 
 int dfd_vote_update(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
@@ -292,7 +356,7 @@ int dfd_analyze_batch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int W, 
         if ((rc = dfd_ensure(ctx, ctx->face_in, (size_t)m * 224 * 224 * 3 * esz))) return rc;
         if ((rc = dfd_faceprep_launch(ctx, frames, n, H, W, frame_stride, row_pitch, boxes, box_frame, m, ctx->face_in.p, dtype, st))) return rc;
         if ((rc = dfd_effnet_launch(ctx, ctx->face_in.p, m, dtype, ctx->d_logits, st))) return rc;
-        if ((rc = dfd_faceprob_launch(ctx, ctx->d_logits, ctx->d_boxes_ok, m, fprob, st))) return rc;   // heuristics see the clamped crop, as face_bgr.shape does
+        if ((rc = dfd_faceprob_launch(ctx, ctx->d_logits, ctx->d_boxes_ok, m, 1, fprob, st))) return rc;   // heuristics see the clamped crop, as face_bgr.shape does
     }
     if (overlap) DFD_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     return dfd_select_vote_launch(ctx, n, m, box_frame, fprob, fres, stream_ids, records, st);

@@ -82,6 +82,13 @@ struct dfd_ctx {
     int32_t* d_fidx_ok = nullptr;         // [m]
     uint8_t* d_box_bad = nullptr;         // [m] 1 = box rejected (empty after clamping / larger than max_crop): probability NaN
     int box_flags_m = 0;                  // number of boxes the flags describe (last face-prep call)
+    DfdBuf tta_base;                      // [m][max_crop*max_crop*3] CLAHE'd crops, the base images of the test-time augmentations (allocated on first use)
+    int calib_kind = 0;                   // probability calibrator (dfd_set_calibrator): 0 none, 1 logistic, 2 piecewise linear
+    int calib_n = 0;
+    DfdBuf calib;                         // [2][calib_n] doubles: xs then ys (kind 2) or {coef, intercept} (kind 1)
+    DfdBuf draw_buf;                      // overlay.cu: command list + text masks of one dfd_draw_overlay call
+    void* draw_host = nullptr;            //   pinned staging copy
+    size_t draw_host_bytes = 0;
     // classifier
     bool has_weights = false;
     float* d_wf32 = nullptr;              // packed folded fp32 parameters
@@ -181,15 +188,18 @@ void dfd_flight_mark(dfd_ctx* ctx, const char* kernel, cudaStream_t st);
 
 int dfd_ensure(dfd_ctx* ctx, DfdBuf& b, size_t bytes);
 
-// Raises the kernel's dynamic shared-memory limit on this context's device to at least `bytes` (once per context and size).
+// Raises the kernel's dynamic shared-memory limit on this context's device to at least `bytes`.  The attribute belongs to the
+// (device, function) pair and cudaFuncSetAttribute REPLACES it, so the largest value any context of this process asked for is
+// kept in a process-wide table (dfd_api.cu): a second context with smaller workspaces must never lower the limit under a
+// context that needs more (two Engines with different max_crop on one GPU).  ctx->func_smem caches what this context knows.
+int dfd_func_smem_raise(dfd_ctx* ctx, const void* fn, size_t bytes, bool full_carveout);
 template <typename F>
 static inline int dfd_func_smem(dfd_ctx* ctx, F* fn, size_t bytes, bool full_carveout = false) {
     size_t& have = ctx->func_smem[(const void*)fn];
     if (bytes <= have) return DFD_OK;
-    DFD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    if (full_carveout) DFD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    have = bytes;
-    return DFD_OK;
+    int rc = dfd_func_smem_raise(ctx, (const void*)fn, bytes, full_carveout);
+    if (rc == DFD_OK) have = bytes;
+    return rc;
 }
 
 // Makes the context's device current for the duration of a C entry point (a process may hold one context per GPU).
@@ -270,6 +280,12 @@ int dfd_forensics_launch(dfd_ctx* ctx, const uint8_t* frames, int n, int H, int 
 int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
                         int row_pitch, const int32_t* boxes, const int32_t* frame_idx, int m, void* out, int dtype,
                         cudaStream_t st);
+int dfd_faceprep_tta_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
+                            int row_pitch, const int32_t* boxes, const int32_t* frame_idx, int m, int n_pred,
+                            const dfd_tta_aug* augs, void* out, int dtype, cudaStream_t st);
+// overlay.cu
+int dfd_overlay_launch(dfd_ctx* ctx, uint8_t* frame, int H, int W, int row_pitch, const dfd_draw_cmd* cmds_host, int n_cmds,
+                       const uint8_t* masks_host, size_t mask_bytes, cudaStream_t st);
 // jpegdec.cu
 int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_t* offsets_host, int n, int H, int W,
                            uint8_t* frames_out, size_t frame_stride, int row_pitch, int32_t* status_dev, cudaStream_t st);
@@ -279,7 +295,7 @@ int dfd_effnet_launch(dfd_ctx* ctx, const void* in, int m, int dtype, float* log
 int dfd_effnet_upload(dfd_ctx* ctx, const float* blob, size_t n);
 size_t dfd_effnet_blob_floats();
 // vote.cu
-int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, cudaStream_t st);
+int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, int n_pred, double* prob, cudaStream_t st);
 int dfd_vote_launch(dfd_ctx* ctx, const int32_t* stream_ids, const double* vote_input, const uint8_t* np_flags, int n,
                     dfd_vote_record* rec, cudaStream_t st);
 int dfd_select_vote_launch(dfd_ctx* ctx, int n, int m, const int32_t* box_frame, const double* face_prob,

@@ -15,6 +15,7 @@
 #include "px_resize.h"
 #include "px_clahe.h"
 #include "px_numpy.h"
+#include "px_warp.h"
 
 #define PIL_STRIDE (2 + DFD_PIL_KMAX)
 
@@ -87,6 +88,25 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ f
     dfd_clahe_lut_warp(h, g.clip, g.lut_scale, luts + ((size_t)m * 64 + ty * 8 + tx) * 256, lane);
 }
 
+// Pillow's horizontal resampling pass of one RGB row (in shared memory) to 160 pixels: a lane resamples one output pixel
+// (3 channels share the tap positions and weights); k = this box's coefficient table, kstride ints per output pixel.
+__device__ __forceinline__ void pil_hpass_row(const uint8_t* row, uint8_t* out, const int* ktab, int kstride, int lane) {
+    for (int xx = lane; xx < 160; xx += 32) {
+        const int* k = ktab + xx * kstride;
+        const int xmin = k[0], cnt = k[1];
+        int a0 = 1 << (DFD_PIL_PRECISION - 1), a1 = a0, a2 = a0;
+        const uint8_t* rp = row + xmin * 3;
+        for (int t = 0; t < cnt; t++) {
+            const int w = k[2 + t];
+            a0 += rp[0] * w; a1 += rp[1] * w; a2 += rp[2] * w;
+            rp += 3;
+        }
+        out[xx * 3] = (uint8_t)dfd_pil_clip8(a0);
+        out[xx * 3 + 1] = (uint8_t)dfd_pil_clip8(a1);
+        out[xx * 3 + 2] = (uint8_t)dfd_pil_clip8(a2);
+    }
+}
+
 // CTA = HP_ROWS consecutive crop rows of one box (32: staging the 34 KB of tables costs more than 16 rows of pixels), warp = one row at a time: BGR -> LAB -> CLAHE(L) -> LAB2BGR -> RGB row
 // in shared memory, then Pillow's horizontal resampling pass of that row to 160 pixels.  The colour tables and the
 // box's 64 CLAHE LUTs are staged in shared memory once per CTA (11 table gathers + 4 LUT gathers per pixel).
@@ -96,7 +116,8 @@ __global__ void __launch_bounds__(256) k_clahe_hpass(const uint8_t* __restrict__
                                                      const int32_t* __restrict__ boxes, const int32_t* __restrict__ frame_idx,
                                                      const DfdColorTables* __restrict__ tab, const uint8_t* __restrict__ luts,
                                                      const int* __restrict__ pil, uint8_t* __restrict__ hpass, int max_crop,
-                                                     uint8_t* __restrict__ dbg_clahe, int dbg_box, int rows_per_cta) {
+                                                     uint8_t* __restrict__ clahe_out, size_t clahe_stride, int clahe_box,
+                                                     int slot_mul, int rows_per_cta) {
     extern __shared__ __align__(16) uint8_t hp_smem[];
     DfdColorTables* s_tab = (DfdColorTables*)hp_smem;                               // sizeof is a multiple of 16
     uint8_t* s_lut = hp_smem + sizeof(DfdColorTables);                              // [64][256]
@@ -150,31 +171,65 @@ __global__ void __launch_bounds__(256) k_clahe_hpass(const uint8_t* __restrict__
             __syncwarp();                                    // every lane has read its pixel before anyone overwrites the buffer
             if (x < bw) {
                 row[x * 3] = (uint8_t)orr; row[x * 3 + 1] = (uint8_t)og; row[x * 3 + 2] = (uint8_t)ob;   // RGB order (:376)
-                if (dbg_clahe && m == dbg_box) {
-                    uint8_t* d = dbg_clahe + ((size_t)y * bw + x) * 3;
+                // the CLAHE'd crop itself (tight w*h*3 BGR): box `clahe_box` alone (diagnostics) or, with clahe_box < 0, every box
+                // at its own clahe_stride slot (the base image of the test-time augmentations)
+                if (clahe_out && (clahe_box < 0 || m == clahe_box)) {
+                    uint8_t* d = clahe_out + (clahe_box < 0 ? (size_t)m * clahe_stride : 0) + ((size_t)y * bw + x) * 3;
                     d[0] = (uint8_t)ob; d[1] = (uint8_t)og; d[2] = (uint8_t)orr;
                 }
             }
         }
         __syncwarp();
-        if (hpass) {
-            uint8_t* out = hpass + (((size_t)m * max_crop + y) * 160) * 3;
-            // a lane resamples one output pixel (3 channels share the tap positions and weights)
-            for (int xx = lane; xx < 160; xx += 32) {
-                const int* k = staged ? s_pc + xx * pcs : pg + xx * PIL_STRIDE;
-                const int xmin = k[0], cnt = k[1];
-                int a0 = 1 << (DFD_PIL_PRECISION - 1), a1 = a0, a2 = a0;
-                const uint8_t* rp = row + xmin * 3;
-                for (int t = 0; t < cnt; t++) {
-                    const int w = k[2 + t];
-                    a0 += rp[0] * w; a1 += rp[1] * w; a2 += rp[2] * w;
-                    rp += 3;
-                }
-                out[xx * 3] = (uint8_t)dfd_pil_clip8(a0);
-                out[xx * 3 + 1] = (uint8_t)dfd_pil_clip8(a1);
-                out[xx * 3 + 2] = (uint8_t)dfd_pil_clip8(a2);
-            }
+        if (hpass) pil_hpass_row(row, hpass + (((size_t)m * slot_mul * max_crop + y) * 160) * 3, staged ? s_pc : pg, staged ? pcs : PIL_STRIDE, lane);
+        __syncwarp();
+    }
+}
+
+// Test-time augmentation (deepfake_detection.py:417-434): CTA = rows_per_cta rows of ONE augmented copy of one box, warp = one
+// row at a time.  The augmented image is never materialised: a lane computes its pixel of the row -- cv2.warpAffine's
+// fixed-point source position, four taps fetched from the CLAHE'd base crop (written by k_clahe_hpass, L2-resident) through
+// the flip and the brightness table (px_warp.h) -- into the shared-memory row buffer in RGB order, and the row goes straight
+// through Pillow's horizontal pass into h-pass slot i * n_pred + 1 + a; k_vpass_up_norm finishes it like any other crop.
+struct DfdTtaAug { int32_t flip; float brightness; double im[6]; };
+static_assert(sizeof(DfdTtaAug) == sizeof(dfd_tta_aug), "dfd_tta_aug layout");
+__global__ void __launch_bounds__(256) k_tta_hpass(const uint8_t* __restrict__ base, size_t base_stride,
+                                                   const int32_t* __restrict__ boxes, const DfdTtaAug* __restrict__ augs,
+                                                   const int* __restrict__ pil, uint8_t* __restrict__ hpass, int max_crop,
+                                                   int n_pred, int rows_per_cta) {
+    extern __shared__ __align__(16) uint8_t hp_smem[];
+    uint8_t* s_lut = hp_smem;                                                       // [256] brightness table
+    int* s_pc = (int*)(hp_smem + 256);                                              // [160][2 + ksize]
+    uint8_t* s_rows = (uint8_t*)(s_pc + 160 * (2 + DFD_PIL_KMAX_STAGED));           // [8 warps][row_stride]
+    const int n_aug = n_pred - 1;
+    const int i = blockIdx.y / n_aug, a = blockIdx.y - i * n_aug, y0 = blockIdx.x * rows_per_cta;
+    const int bw = boxes[i * 4 + 2], bh = boxes[i * 4 + 3];
+    if (y0 >= bh) return;
+    const DfdTtaAug A = augs[(size_t)i * n_aug + a];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    s_lut[threadIdx.x] = (uint8_t)dfd_scale_abs_u8(threadIdx.x, A.brightness);
+    const int* pg = pil + ((size_t)i * 2 + 0) * 160 * PIL_STRIDE;
+    const int ks_real = dfd_pil_ksize(bw, 160);
+    const bool staged = ks_real <= DFD_PIL_KMAX_STAGED;
+    const int pcs = 2 + (staged ? ks_real : 0);
+    if (staged) {
+        for (int t = threadIdx.x; t < 160 * pcs; t += 256) {
+            const int xx = t / pcs, j = t - xx * pcs;
+            s_pc[t] = pg[xx * PIL_STRIDE + j];
         }
+    }
+    __syncthreads();
+    const int row_stride = (max_crop * 3 + 8 + 15) & ~15;
+    uint8_t* row = s_rows + (size_t)warp * row_stride;
+    const uint8_t* src = base + (size_t)i * base_stride;
+    const size_t slot = (size_t)i * n_pred + 1 + a;
+    for (int y = y0 + warp; y < y0 + rows_per_cta && y < bh; y += 8) {
+        for (int x = lane; x < bw; x += 32) {
+            int ob, og, orr;
+            dfd_tta_pixel(src, bw * 3, bw, bh, A.flip, s_lut, A.im, x, y, &ob, &og, &orr);
+            row[x * 3] = (uint8_t)orr; row[x * 3 + 1] = (uint8_t)og; row[x * 3 + 2] = (uint8_t)ob;     // RGB order (:376)
+        }
+        __syncwarp();
+        pil_hpass_row(row, hpass + ((slot * max_crop + y) * 160) * 3, staged ? s_pc : pg, staged ? pcs : PIL_STRIDE, lane);
         __syncwarp();
     }
 }
@@ -198,14 +253,14 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* o, const fl
 template <typename OutT>
 __global__ void __launch_bounds__(512) k_vpass_up_norm(const int32_t* __restrict__ boxes, const int* __restrict__ pil,
                                                        const uint8_t* __restrict__ hpass, int max_crop,
-                                                       uint8_t* __restrict__ face160, OutT* __restrict__ out) {
+                                                       uint8_t* __restrict__ face160, OutT* __restrict__ out, int rep) {
     __shared__ __align__(16) uint8_t s160[44][480];
-    const int m = blockIdx.y, band = blockIdx.x;           // 4 bands of 56 output rows
+    const int m = blockIdx.y, band = blockIdx.x;           // 4 bands of 56 output rows; crop m belongs to box m / rep (TTA copies)
     int r_first, r_last, t0, t1; float l0, l1;
     dfd_torch_bilinear_coef(band * 56, 160, 224, &r_first, &t1, &l0, &l1);
     dfd_torch_bilinear_coef(band * 56 + 55, 160, 224, &t0, &r_last, &l0, &l1);
     const int nrows = r_last - r_first + 1;                // <= 42
-    const int* pc = pil + ((size_t)m * 2 + 1) * 160 * PIL_STRIDE;
+    const int* pc = pil + ((size_t)(m / rep) * 2 + 1) * 160 * PIL_STRIDE;
     const uint8_t* hp = hpass + (size_t)m * max_crop * 480;
     // a thread resamples 4 consecutive bytes of an output row: one 32-bit load of the h-pass image per tap
     for (int o = threadIdx.x; o < nrows * 120; o += 512) {
@@ -303,13 +358,24 @@ __global__ void k_box_sanitize(const int32_t* __restrict__ boxes, const int32_t*
     bad[i] = is_bad ? 1 : 0;
 }
 
-int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
-                        int row_pitch, const int32_t* boxes_in, const int32_t* frame_idx_in, int m, void* out, int dtype,
-                        cudaStream_t st) {
-    DFD_REQUIRE(m > 0 && m <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "face_prep: box count exceeds max_batch");
+// n_pred = 1: plain face prep.  n_pred > 1 (test-time augmentation): crop q = i * n_pred + j of `out` is prediction j of box i
+// (j = 0 the un-augmented crop, j >= 1 augmentation augs[i * (n_pred - 1) + j - 1]).
+static int faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
+                           int row_pitch, const int32_t* boxes_in, const int32_t* frame_idx_in, int m, int n_pred,
+                           const dfd_tta_aug* augs, void* out, int dtype, cudaStream_t st) {
+    DFD_REQUIRE(m > 0 && n_pred >= 1 && (long long)m * n_pred <= ctx->cfg.max_batch, DFD_ERR_CAPACITY,
+                "face_prep: box count (x predictions per box) exceeds max_batch");
     DFD_REQUIRE(dtype == DFD_F32 || dtype == DFD_BF16, DFD_ERR_INVALID, "face_prep: bad dtype");
     DFD_REQUIRE(n_frames > 0 && H >= 1 && W >= 1 && row_pitch >= 3 * W, DFD_ERR_INVALID, "face_prep: bad frame geometry");
+    DFD_REQUIRE(n_pred == 1 || augs != nullptr, DFD_ERR_INVALID, "face_prep_tta: augmentation parameters missing");
     const int mc = ctx->cfg.max_crop;
+    const size_t base_stride = (size_t)mc * mc * 3;
+    uint8_t* base = nullptr;
+    if (n_pred > 1) {
+        int rc = dfd_ensure(ctx, ctx->tta_base, (size_t)m * base_stride);
+        if (rc) return rc;
+        base = (uint8_t*)ctx->tta_base.p;
+    }
     k_box_sanitize<<<(m + 127) / 128, 128, 0, st>>>(boxes_in, frame_idx_in, m, n_frames, H, W, mc, ctx->d_boxes_ok, ctx->d_fidx_ok,
                                                     ctx->d_box_bad);
     DFD_LAUNCH_CHECK("k_box_sanitize", st);
@@ -326,15 +392,35 @@ int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H
     const int hp_rows = m >= 16 ? HP_ROWS : 8;
     k_clahe_hpass<<<dim3((mc + hp_rows - 1) / hp_rows, m), 256, hp_smem, st>>>(frames, frame_stride, row_pitch, boxes, frame_idx,
                                                                                ctx->d_tables, ctx->d_luts, ctx->d_pil, ctx->d_hpass, mc,
-                                                                               nullptr, -1, hp_rows);
+                                                                               base, base_stride, -1, n_pred, hp_rows);
     DFD_LAUNCH_CHECK("k_clahe_hpass", st);
+    if (n_pred > 1) {
+        const size_t tta_smem = 256 + 160 * (2 + DFD_PIL_KMAX_STAGED) * sizeof(int) + (size_t)8 * ((mc * 3 + 8 + 15) & ~15);
+        { int rc = dfd_func_smem(ctx, k_tta_hpass, tta_smem); if (rc) return rc; }
+        k_tta_hpass<<<dim3((mc + hp_rows - 1) / hp_rows, m * (n_pred - 1)), 256, tta_smem, st>>>(
+            base, base_stride, boxes, (const DfdTtaAug*)augs, ctx->d_pil, ctx->d_hpass, mc, n_pred, hp_rows);
+        DFD_LAUNCH_CHECK("k_tta_hpass", st);
+    }
     if (dtype == DFD_F32)
-        k_vpass_up_norm<float><<<dim3(4, m), 512, 0, st>>>(boxes, ctx->d_pil, ctx->d_hpass, mc, ctx->d_face160, (float*)out);
+        k_vpass_up_norm<float><<<dim3(4, m * n_pred), 512, 0, st>>>(boxes, ctx->d_pil, ctx->d_hpass, mc, ctx->d_face160, (float*)out, n_pred);
     else
-        k_vpass_up_norm<__nv_bfloat16><<<dim3(4, m), 512, 0, st>>>(boxes, ctx->d_pil, ctx->d_hpass, mc, ctx->d_face160,
-                                                                   (__nv_bfloat16*)out);
+        k_vpass_up_norm<__nv_bfloat16><<<dim3(4, m * n_pred), 512, 0, st>>>(boxes, ctx->d_pil, ctx->d_hpass, mc, ctx->d_face160,
+                                                                            (__nv_bfloat16*)out, n_pred);
     DFD_LAUNCH_CHECK("k_vpass_up_norm", st);
     return DFD_OK;
+}
+
+int dfd_faceprep_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
+                        int row_pitch, const int32_t* boxes_in, const int32_t* frame_idx_in, int m, void* out, int dtype,
+                        cudaStream_t st) {
+    return faceprep_launch(ctx, frames, n_frames, H, W, frame_stride, row_pitch, boxes_in, frame_idx_in, m, 1, nullptr, out, dtype, st);
+}
+
+int dfd_faceprep_tta_launch(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, size_t frame_stride,
+                            int row_pitch, const int32_t* boxes_in, const int32_t* frame_idx_in, int m, int n_pred,
+                            const dfd_tta_aug* augs, void* out, int dtype, cudaStream_t st) {
+    DFD_REQUIRE(n_pred >= 1 && n_pred <= DFD_TTA_MAX_PRED, DFD_ERR_INVALID, "face_prep_tta: n_pred outside 1..DFD_TTA_MAX_PRED");
+    return faceprep_launch(ctx, frames, n_frames, H, W, frame_stride, row_pitch, boxes_in, frame_idx_in, m, n_pred, augs, out, dtype, st);
 }
 
 int dfd_dbg_clahe_launch(dfd_ctx* ctx, const uint8_t* frames, size_t frame_stride, int row_pitch, const int32_t* boxes,
@@ -346,7 +432,7 @@ int dfd_dbg_clahe_launch(dfd_ctx* ctx, const uint8_t* frames, size_t frame_strid
     // (the sanitised boxes of that call are used as well: see k_box_sanitize)
     (void)boxes; (void)frame_idx;
     k_clahe_hpass<<<dim3((mc + HP_ROWS - 1) / HP_ROWS, i + 1), 256, hp_smem, st>>>(frames, frame_stride, row_pitch, ctx->d_boxes_ok, ctx->d_fidx_ok,
-                                                                                   ctx->d_tables, ctx->d_luts, ctx->d_pil, nullptr, mc, out, i, HP_ROWS);
+                                                                                   ctx->d_tables, ctx->d_luts, ctx->d_pil, nullptr, mc, out, 0, i, 1, HP_ROWS);
     DFD_LAUNCH_CHECK("k_clahe_hpass", st);
     return DFD_OK;
 }

@@ -180,15 +180,71 @@ k_select_vote(int n, int m, const int32_t* __restrict__ box_frame, const double*
     if (lane == 0) rec[i] = r;
 }
 
-// sigmoid + apply_heuristics (deepfake_detection.py:398,489-502)
-__global__ void k_faceprob(int m, const float* __restrict__ logits, const int32_t* __restrict__ boxes,
-                           const uint8_t* __restrict__ bad, double* __restrict__ prob) {
+// np.mean of a list of n Python floats (analyze_face_with_tta, deepfake_detection.py:441): float64 pairwise summation --
+// n < 8 a plain running sum, otherwise eight accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and the tail
+// added sequentially (n <= DFD_TTA_MAX_PRED < 128: no recursion) -- divided by n.
+__device__ double np_mean_f64(const double* a, int n) {
+    double res;
+    if (n < 8) {
+        res = 0.0;
+        for (int i = 0; i < n; i++) res = __dadd_rn(res, a[i]);
+    } else {
+        double r[8];
+        for (int j = 0; j < 8; j++) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __dadd_rn(res, a[i]);
+    }
+    return __ddiv_rn(res, (double)n);
+}
+
+// apply_calibration (deepfake_detection.py:445-455): calibrator.predict_proba([[p]])[0][1] for the two calibrator families
+// a pickled scikit-learn object reduces to -- a logistic (Platt) map expit(coef * p + intercept), or a monotone
+// piecewise-linear table (isotonic regression; np.interp semantics: clamped at the ends, slope * (p - x_j) + y_j inside).
+__device__ double calibrate(double p, int kind, int n, const double* __restrict__ tab) {
+    if (kind == DFD_CALIB_LOGISTIC) {
+        const double z = __dadd_rn(__dmul_rn(tab[0], p), tab[1]);
+        // scipy.special.expit: 1 / (1 + exp(-z)) for z >= 0, exp(z) / (1 + exp(z)) below
+        if (z >= 0) return 1.0 / (1.0 + exp(-z));
+        const double e = exp(z);
+        return e / (1.0 + e);
+    }
+    if (kind == DFD_CALIB_PIECEWISE_LINEAR) {
+        const double* xs = tab; const double* ys = tab + n;
+        if (!(p > xs[0])) return ys[0];
+        if (!(p < xs[n - 1])) return ys[n - 1];
+        int lo = 0, hi = n - 1;                                  // xs[lo] <= p < xs[hi]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (xs[mid] <= p) lo = mid; else hi = mid; }
+        const double slope = __ddiv_rn(__dsub_rn(ys[lo + 1], ys[lo]), __dsub_rn(xs[lo + 1], xs[lo]));
+        return __dadd_rn(__dmul_rn(slope, __dsub_rn(p, xs[lo])), ys[lo]);
+    }
+    return p;
+}
+
+// sigmoid (+ mean over the n_pred test-time predictions of a box) + apply_calibration + apply_heuristics
+// (deepfake_detection.py:398, 441, 445-455, 489-502); logits[i * n_pred + j] = prediction j of box i
+__global__ void k_faceprob(int m, int n_pred, const float* __restrict__ logits, const int32_t* __restrict__ boxes,
+                           const uint8_t* __restrict__ bad, int calib_kind, int calib_n, const double* __restrict__ calib,
+                           double* __restrict__ prob) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     if (bad && bad[i]) { prob[i] = __longlong_as_double(0x7ff8000000000000LL); return; }   // rejected box: "no face"
-    float z = logits[i];
-    float s = 1.0f / (1.0f + expf(-z));                              // torch.sigmoid in float32
-    double p = (double)s;                                            // .item() -> Python float
+    double p;
+    if (n_pred == 1) {
+        float z = logits[i];
+        float s = 1.0f / (1.0f + expf(-z));                          // torch.sigmoid in float32
+        p = (double)s;                                               // .item() -> Python float
+    } else {
+        double preds[DFD_TTA_MAX_PRED];
+        for (int j = 0; j < n_pred; j++) {
+            float z = logits[(size_t)i * n_pred + j];
+            preds[j] = (double)(1.0f / (1.0f + expf(-z)));
+        }
+        p = np_mean_f64(preds, n_pred);
+    }
+    p = calibrate(p, calib_kind, calib_n, calib);
     int w = boxes[i * 4 + 2], h = boxes[i * 4 + 3];
     double adj = (h < 80 || w < 80) ? 0.10 : 0.0;
     p = p + adj;
@@ -216,10 +272,10 @@ static VoteCfg make_cfg(const dfd_ctx* ctx) {
     return c;
 }
 
-int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, double* prob, cudaStream_t st) {
+int dfd_faceprob_launch(dfd_ctx* ctx, const float* logits, const int32_t* boxes, int m, int n_pred, double* prob, cudaStream_t st) {
     // boxes the last face-prep call rejected (k_box_sanitize) get NaN; the flags describe exactly its m boxes
     const uint8_t* bad = ctx->box_flags_m == m ? ctx->d_box_bad : nullptr;
-    k_faceprob<<<(m + 127) / 128, 128, 0, st>>>(m, logits, boxes, bad, prob);
+    k_faceprob<<<(m + 127) / 128, 128, 0, st>>>(m, n_pred, logits, boxes, bad, ctx->calib_kind, ctx->calib_n, (const double*)ctx->calib.p, prob);
     DFD_LAUNCH_CHECK("k_faceprob", st);
     return DFD_OK;
 }

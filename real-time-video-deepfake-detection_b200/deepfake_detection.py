@@ -3,9 +3,17 @@
 result shapes.  All numerics run in libdfd's CUDA kernels; these classes move one frame at a time across
 the C-ABI (the batched multi-stream entry is ``dfd_b200.engine.Engine.analyze_batch``).
 
+Test-time augmentation (``use_tta``, deepfake_detection.py:408-443) runs on the device: the random draws come from Python's
+global ``random`` in the reference's order (``dfd_b200.tta``), flip / brightness / rotation / resize / classifier / mean are
+libdfd kernels.  A calibrator (``weights/calibrator.pkl`` or ``set_calibrator``) that is a scikit-learn
+``LogisticRegression`` is applied on the device as well; any other object with ``predict_proba`` is called on the host
+exactly as the reference does (it is opaque user code).
+
 Out of scope: face detection (boxes are inputs -- pass ``faces=[(x,y,w,h),...]`` or
-install ``detector.face_detector``), MTCNN re-detection, TTA / calibrator / GradCAM, overlay drawing.
+install ``detector.face_detector``), MTCNN re-detection, GradCAM.
 """
+import os
+import pickle
 import time
 import warnings
 from collections import deque
@@ -13,7 +21,7 @@ from collections import deque
 import numpy as np
 import torch
 
-from . import _lib, runtime
+from . import _lib, overlay as _overlay, runtime, tta as _tta
 from .frame_analysis import FrameForensicAnalyzer
 
 _model_state = {"sd": None, "loaded": False}
@@ -162,9 +170,15 @@ class DeepfakeDetector:
         self.full_forensic_interval = 3
         self.last_frame_forensic_result = None
         self.calibrator = None
-        if use_tta and num_tta_augmentations > 1:
-            warnings.warn("test-time augmentation is out of scope for the B200 path (random, disabled in both shipped "
-                          "reference detectors); running single predictions", stacklevel=2)
+        self._device_calibrator = False
+        calibrator_path = os.path.join(os.path.dirname(__file__), "weights", "calibrator.pkl")     # deepfake_detection.py:333-342
+        if os.path.exists(calibrator_path):
+            try:
+                with open(calibrator_path, "rb") as f:
+                    self.set_calibrator(pickle.load(f))
+                print("✓ Probability calibrator loaded")
+            except Exception:
+                print("⚠️ Could not load calibrator")
 
     def reset(self):
         self.temporal_tracker.reset()
@@ -193,12 +207,54 @@ class DeepfakeDetector:
         return result
 
     # -- Layer 1: face model ----------------------------------------------------------------
+    def set_calibrator(self, calibrator):
+        """Install ``self.calibrator`` (deepfake_detection.py:333-342).  A fitted scikit-learn ``LogisticRegression`` on the
+        single raw-probability feature (Platt scaling) becomes a device-side map (``dfd_set_calibrator``); ``None`` removes it;
+        any other object is kept and called on the host through ``predict_proba`` as the reference does."""
+        self.calibrator = calibrator
+        self._device_calibrator = False
+        self._eng.set_calibrator("none")
+        if calibrator is None:
+            return
+        coef, icpt = getattr(calibrator, "coef_", None), getattr(calibrator, "intercept_", None)
+        if (type(calibrator).__name__ == "LogisticRegression" and coef is not None and np.shape(coef) == (1, 1)
+                and np.shape(icpt) == (1,)):
+            self._eng.set_calibrator("logistic", [float(coef[0][0])], [float(icpt[0])])
+            self._device_calibrator = True
+
     def apply_calibration(self, raw_prob):
-        return raw_prob
+        """deepfake_detection.py:445-455 (host form, for callers that use it directly)."""
+        if self.calibrator is None:
+            return raw_prob
+        try:
+            return self.calibrator.predict_proba([[raw_prob]])[0][1]
+        except Exception:
+            return raw_prob
 
     def apply_heuristics(self, fake_prob, face_region):
         h, w = face_region.shape[:2]
         return np.clip(fake_prob + (0.10 if (h < 80 or w < 80) else 0.0), 0, 1)
+
+    def _face_probability(self, frames, box, cw, ch):
+        """prep (+ TTA) -> classifier -> sigmoid / mean / calibration / heuristics for ONE box of frames[0]; cw x ch is the
+        crop numpy slicing would give.  np.float64 like the reference's np.clip result, NaN if the box was rejected."""
+        n_pred = self.num_tta_augmentations if self.use_tta else 1
+        bx = np.asarray([box], np.int32)
+        if n_pred > 1:
+            params = [_tta.draw_params(n_pred)]                    # consumes `random` exactly like deepfake_detection.py:418-430
+            xin = self._eng.face_prep_tta(frames, bx, [0], params, self.dtype)
+        else:
+            xin = self._eng.face_prep_batch(frames, bx, [0], self.dtype)
+        logits = self._eng.effnet_forward(xin)
+        host_calib = self.calibrator is not None and not self._device_calibrator
+        # an opaque host calibrator sits between the mean and the heuristics: take the raw mean from the device (a >= 80 px
+        # dummy size switches the heuristic off), call the object, apply the reference's heuristic line on the host
+        size = np.array([[0, 0, 80, 80]] if host_calib else [[0, 0, cw, ch]], np.int32)
+        p = self._eng.face_probability_tta(logits, size, n_pred) if n_pred > 1 else self._eng.face_probability(logits, size)
+        p = np.float64(p.cpu().numpy()[0])
+        if host_calib and not np.isnan(p):
+            p = np.clip(self.apply_calibration(float(p)) + (0.10 if (ch < 80 or cw < 80) else 0.0), 0, 1)
+        return p
 
     def analyze_face(self, face_region):
         """(p, p, None) for a BGR face crop, or (None, None, None) on failure (deepfake_detection.py:517-550)."""
@@ -209,11 +265,7 @@ class DeepfakeDetector:
             _ensure_weights(self._eng)
             h, w = face.shape[:2]
             ft = torch.from_numpy(np.ascontiguousarray(face)).to(self._eng.device).unsqueeze(0)
-            box = np.array([[0, 0, w, h]], np.int32)
-            x = self._eng.face_prep_batch(ft, box, [0], self.dtype)
-            logits = self._eng.effnet_forward(x)
-            p = self._eng.face_probability(logits, box)
-            p = np.float64(p.cpu().numpy()[0])              # np.float64, like np.clip in apply_heuristics
+            p = self._face_probability(ft, [0, 0, w, h], w, h)
             if np.isnan(p):                                 # box rejected on the device (k_box_sanitize)
                 raise ValueError(f"face crop {w}x{h} exceeds the engine's max_crop ({self._eng.cfg.max_crop})")
             return p, p, None
@@ -228,13 +280,9 @@ class DeepfakeDetector:
             _ensure_weights(self._eng)
             x, y, w, h = (int(v) for v in box)
             H, W = int(frame_dev.shape[0]), int(frame_dev.shape[1])
-            bx = np.array([[x, y, w, h]], np.int32)
-            xin = self._eng.face_prep_batch(frame_dev.contiguous().unsqueeze(0), bx, [0], self.dtype)
-            logits = self._eng.effnet_forward(xin)
-            # heuristics see the crop numpy slicing would give (clamped to the frame), like face_region.shape in the reference
+            # heuristics / rotation centre see the crop numpy slicing would give (clamped to the frame), like face_region.shape
             cw, ch = max(min(x + w, W) - max(x, 0), 0), max(min(y + h, H) - max(y, 0), 0)
-            p = self._eng.face_probability(logits, np.array([[0, 0, cw, ch]], np.int32))
-            p = np.float64(p.cpu().numpy()[0])
+            p = self._face_probability(frame_dev.contiguous().unsqueeze(0), [x, y, w, h], cw, ch)
             if np.isnan(p):
                 raise ValueError(f"face box {box} is empty inside the {W}x{H} frame or exceeds the engine's max_crop")
             return p, p, None
@@ -253,35 +301,97 @@ class DeepfakeDetector:
             raise _lib.DfdError("corrupt JPEG stream (entropy-coded data incomplete)")
         return frames[0]
 
+    # -- result annotation (deepfake_detection.py:552-586, 688-726) ----------------------------------
+    def get_box_color(self, confidence_level):
+        return _overlay.get_box_color(confidence_level)
+
+    def _as_device_frame(self, frame):
+        if torch.is_tensor(frame) and frame.is_cuda:
+            return frame if frame.is_contiguous() else frame.contiguous()
+        return torch.from_numpy(np.ascontiguousarray(frame)).to(self._eng.device)
+
+    def _finish_drawing(self, frame, fdev):
+        """The reference draws into the caller's array and returns it: copy the annotated device frame back into it."""
+        if torch.is_tensor(frame) and frame.is_cuda:
+            if fdev is not frame:
+                frame.copy_(fdev)
+            return frame
+        out = fdev.cpu().numpy()
+        if isinstance(frame, np.ndarray) and frame.flags.writeable and frame.shape == out.shape:
+            frame[...] = out
+            return frame
+        return out
+
+    def draw_detection_overlay(self, frame, x, y, w, h, fake_prob, confidence_level):
+        """Box, verdict label and vote counts drawn on the device copy of the frame (bit-exact with the reference's OpenCV
+        calls); accepts a numpy frame (annotated in place and returned, like the reference) or a CUDA tensor."""
+        fdev = self._as_device_frame(frame)
+        cl = _overlay.CommandList(fdev.shape[0], fdev.shape[1])
+        _overlay.detection_overlay(cl, int(x), int(y), int(w), int(h), fake_prob, confidence_level,
+                                   self.temporal_tracker.get_voting_stats())
+        self._eng.draw_overlay(fdev, cl)
+        return self._finish_drawing(frame, fdev)
+
+    def _draw_frame_analysis_overlay(self, frame, fake_prob, confidence_level, forensic_result):
+        fdev = self._as_device_frame(frame)
+        cl = _overlay.CommandList(fdev.shape[0], fdev.shape[1])
+        _overlay.frame_analysis_overlay(cl, fake_prob, confidence_level, forensic_result)
+        self._eng.draw_overlay(fdev, cl)
+        return self._finish_drawing(frame, fdev)
+
     # -- whole frame ---------------------------------------------------------------------------
-    def predict(self, frame, faces=None):
-        """(frame, trigger_forensic, forensic_frame, result_data) as deepfake_detection.py:588-686; the frame is
-        returned unannotated (overlay drawing is out of scope).  ``faces`` = [(x, y, w, h), ...]."""
+    def predict(self, frame, faces=None, draw=True):
+        """(frame, trigger_forensic, forensic_frame, result_data) as deepfake_detection.py:588-686.  ``faces`` =
+        [(x, y, w, h), ...] (face detection is the caller's).  The frame is uploaded once; forensics, every face crop and the
+        annotation (``draw=True``, the reference's behaviour: the overlay of face k is part of the pixels face k + 1 is cropped
+        from, :611-634) work on the device copy, and the annotated frame is written back into the caller's array."""
         self.frame_count += 1
-        frame_forensic = self.analyze_frame_forensics(frame)
+        is_np = not (torch.is_tensor(frame) and frame.is_cuda)
+        if is_np:
+            f = np.asarray(frame)
+            if f.ndim != 3 or f.shape[2] != 3 or f.dtype != np.uint8:
+                raise ValueError("frame must be an (H, W, 3) uint8 BGR image")
+        fdev = self._as_device_frame(frame)
+        H, W = int(fdev.shape[0]), int(fdev.shape[1])
+        frame_forensic = self.analyze_frame_forensics(fdev)
         if faces is None:
-            faces = self.face_detector(frame) if self.face_detector is not None else []
+            faces = self.face_detector(frame if is_np else fdev.cpu().numpy()) if self.face_detector is not None else []
         trigger, forensic_frame, face_results = False, None, []
         confidence_level = "UNCERTAIN"
+        drawn = False
         if len(faces) > 0:
             for (x, y, w, h) in faces:
-                fake_prob, _, _ = self.analyze_face(frame[y:y + h, x:x + w])
+                fake_prob, _, _ = self.analyze_face_box(fdev, (x, y, w, h))
                 if fake_prob is None:
                     continue
                 self.temporal_tracker.update(fake_prob)
                 confidence_level = self.temporal_tracker.get_confidence_level()
                 if self.temporal_tracker.should_trigger_forensic_analysis():
-                    trigger, forensic_frame = True, frame.copy()
+                    trigger, forensic_frame = True, fdev.cpu().numpy()
+                if draw:
+                    cl = _overlay.CommandList(H, W)
+                    _overlay.detection_overlay(cl, int(x), int(y), int(w), int(h), fake_prob, confidence_level,
+                                               self.temporal_tracker.get_voting_stats())
+                    self._eng.draw_overlay(fdev, cl)
+                    drawn = True
                 face_results.append({"face_prob": float(fake_prob), "combined_prob": float(fake_prob),
                                      "bbox": {"x": int(x), "y": int(y), "w": int(w), "h": int(h)}})
             if not face_results:
                 # the reference raises NameError here (confidence_level unbound, SURVEY.md §0); report the tracker state
                 confidence_level = self.temporal_tracker.get_confidence_level()
         else:
-            self.temporal_tracker.update(frame_forensic["fake_probability"])
+            frame_fake_prob = frame_forensic["fake_probability"]
+            self.temporal_tracker.update(frame_fake_prob)
             confidence_level = self.temporal_tracker.get_confidence_level()
             if self.temporal_tracker.should_trigger_forensic_analysis():
-                trigger, forensic_frame = True, frame.copy()
+                trigger, forensic_frame = True, fdev.cpu().numpy()
+            if draw:
+                cl = _overlay.CommandList(H, W)
+                _overlay.frame_analysis_overlay(cl, frame_fake_prob, confidence_level, frame_forensic)
+                self._eng.draw_overlay(fdev, cl)
+                drawn = True
+        if drawn:
+            frame = self._finish_drawing(frame, fdev)
         result_data = {
             "frame_count": self.frame_count,
             "faces_detected": len(faces),

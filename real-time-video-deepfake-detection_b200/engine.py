@@ -143,6 +143,64 @@ class Engine:
                     "dfd_face_probability")
         return prob
 
+    # -- test-time augmentation / calibration --------------------------------------------
+    def face_prep_tta(self, frames, boxes, frame_idx, params, dtype="fp32"):
+        """analyze_face_with_tta's inputs (deepfake_detection.py:408-438) for m boxes: ``params[i]`` = the n_pred - 1
+        (flip, brightness, angle) triples of box i (``tta.draw_params``).  Returns (m * n_pred, 224, 224, 3): crop
+        i * n_pred + j is prediction j of box i (j = 0 un-augmented).  ``boxes`` is a HOST array: the rotation matrices are
+        built here from the box sizes after clamping to the frame (the reference's ``face_region.shape``)."""
+        from . import tta as _tta
+        n, H, W, _ = frames.shape
+        code, tdt = DTYPES[dtype]
+        bh = np.asarray(boxes, np.int64).reshape(-1, 4)
+        m = bh.shape[0]
+        n_pred = len(params[0]) + 1
+        assert len(params) == m and all(len(p) == n_pred - 1 for p in params)
+        recs = []
+        for (x, y, w, h), prm in zip(bh, params):
+            cw = max(min(x + w, W) - max(x, 0), 0)
+            ch = max(min(y + h, H) - max(y, 0), 0)
+            recs.append(_tta.pack(prm, int(cw), int(ch)))
+        aug = np.concatenate(recs) if n_pred > 1 else np.zeros(0, _tta.AUG_DTYPE)
+        aug_dev = torch.from_numpy(aug.view(np.uint8).copy()).to(self.device) if aug.size else None
+        bx = self._dev(bh.astype(np.int32), torch.int32)
+        fi = self._dev(frame_idx, torch.int32)
+        out = torch.empty((m * n_pred, 224, 224, 3), dtype=tdt, device=self.device)
+        rc = self.lib.dfd_face_prep_tta(self.h, _ptr(frames), n, H, W, frames.stride(0), frames.stride(1), _ptr(bx), _ptr(fi),
+                                        m, n_pred, _ptr(aug_dev), _ptr(out), code, self._stream())
+        self._check(rc, "dfd_face_prep_tta")
+        return out
+
+    def face_probability_tta(self, logits, boxes, n_pred):
+        bx = self._dev(boxes, torch.int32)
+        m = bx.shape[0]
+        assert logits.shape[0] == m * n_pred
+        prob = torch.empty(m, dtype=torch.float64, device=self.device)
+        self._check(self.lib.dfd_face_probability_tta(self.h, _ptr(logits), _ptr(bx), m, n_pred, _ptr(prob), self._stream()),
+                    "dfd_face_probability_tta")
+        return prob
+
+    def set_calibrator(self, kind="none", xs=(), ys=()):
+        """apply_calibration on the device: kind "none" | "logistic" (xs = [coef], ys = [intercept]) | "piecewise_linear"."""
+        code = {"none": 0, "logistic": 1, "piecewise_linear": 2}[kind]
+        xa = np.ascontiguousarray(xs, np.float64)
+        ya = np.ascontiguousarray(ys, np.float64)
+        assert xa.shape == ya.shape
+        self._check(self.lib.dfd_set_calibrator(self.h, code, int(xa.size), xa.ctypes.data_as(C.c_void_p),
+                                                ya.ctypes.data_as(C.c_void_p), self._stream()), "dfd_set_calibrator")
+
+    # -- result annotation ------------------------------------------------------------------
+    def draw_overlay(self, frame_dev, command_list):
+        """Composite an ``overlay.CommandList`` on an (H, W, 3) uint8 CUDA frame, in place (dfd_draw_overlay)."""
+        assert frame_dev.dtype == torch.uint8 and frame_dev.is_cuda and frame_dev.dim() == 3 and frame_dev.stride(2) == 1 \
+            and frame_dev.stride(1) == 3
+        cmds, masks = command_list.pack()
+        H, W = int(frame_dev.shape[0]), int(frame_dev.shape[1])
+        rc = self.lib.dfd_draw_overlay(self.h, _ptr(frame_dev), H, W, frame_dev.stride(0), cmds.ctypes.data_as(C.c_void_p),
+                                       int(cmds.size), masks.ctypes.data_as(C.c_void_p), int(masks.size), self._stream())
+        self._check(rc, "dfd_draw_overlay")
+        return frame_dev
+
     # -- vote -------------------------------------------------------------------------
     def vote_update(self, stream_ids, vote_input, np_flags=None):
         sid = self._dev(stream_ids, torch.int32)

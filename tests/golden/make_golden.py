@@ -153,6 +153,62 @@ def gen_clahe(dd):
     return out
 
 
+TTA_CASES = [(300, 300, 51, 3, 7), (97, 83, 52, 3, 8), (50, 71, 53, 5, 9), (400, 96, 54, 2, 10), (223, 410, 55, 4, 11),
+             (64, 64, 56, 3, 12)]
+
+
+def gen_tta(dd):
+    """What the unmodified analyze_face (use_tta=True) hands to _single_prediction, under random.seed(py_seed)."""
+    import random
+    out = []
+    for h, w, seed, n_pred, py_seed in TTA_CASES:
+        with contextlib.redirect_stdout(io.StringIO()):
+            det = dd.DeepfakeDetector(use_tta=True, num_tta_augmentations=n_pred, detection_threshold=0.55)
+        rng = np.random.RandomState(seed)
+        fam = synth.FAMILIES[seed % 3]
+        crop = synth.make_frame(fam, h, w, rng)
+        seen = []
+        det._single_prediction = lambda face: (seen.append(sha(face)), 0.25 + 0.125 * len(seen))[1]
+        random.seed(py_seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            p, _, _ = det.analyze_face(crop)
+        random.seed(py_seed)
+        params = []
+        for _ in range(n_pred - 1):       # the reference's draw order (deepfake_detection.py:422-430)
+            params.append([random.random() > 0.5, random.uniform(0.9, 1.1), random.uniform(-3, 3)])
+        out.append({"h": h, "w": w, "seed": seed, "family": fam, "n_pred": n_pred, "py_seed": py_seed, "in_sha1": sha(crop),
+                    "params": params, "face_sha1": seen, "mean_of_stub_predictions": float(p)})
+    return out
+
+
+OVERLAY_CASES = [
+    # h, w, seed, box, fake_prob, verdict, votes (fake, real, total)
+    (360, 640, 61, (200, 100, 150, 160), 0.8312, "FAKE", (7, 3, 10)),
+    (360, 640, 62, (5, 12, 90, 90), 0.1249, "REAL", (0, 4, 4)),
+    (480, 640, 63, (500, 400, 200, 120), 0.505, "UNCERTAIN", (0, 0, 0)),
+    (720, 1280, 64, (-20, 300, 100, 100), 0.995, "FAKE", (10, 0, 10)),
+    (240, 320, 65, (100, 20, 40, 50), 0.0, "REAL", (1, 9, 10)),
+]
+
+
+def gen_overlay(dd):
+    """draw_detection_overlay / _draw_frame_analysis_overlay of the unmodified reference on seeded frames."""
+    out = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        det = dd.DeepfakeDetector(use_tta=False, num_tta_augmentations=1, detection_threshold=0.55)
+    for h, w, seed, box, p, verdict, votes in OVERLAY_CASES:
+        rng = np.random.RandomState(seed)
+        frame = synth.make_frame("pink", h, w, rng)
+        det.temporal_tracker.get_voting_stats = lambda v=votes: {"fake_count": v[0], "real_count": v[1], "total_frames": v[2]}
+        a = det.draw_detection_overlay(frame.copy(), *box, p, verdict)
+        fres = {"scores": {"frequency": 0.25, "noise": 0.5, "ela": 0.15, "edge": 0.65, "color": 0.1, "temporal": 0.0}}
+        b = det._draw_frame_analysis_overlay(frame.copy(), p, verdict, fres)
+        out.append({"h": h, "w": w, "seed": seed, "box": list(box), "fake_prob": p, "verdict": verdict, "votes": list(votes),
+                    "in_sha1": sha(frame), "detection_sha1": sha(a), "frame_sha1": sha(b),
+                    "detection_changed": int((a != frame).any(axis=2).sum()), "frame_changed": int((b != frame).any(axis=2).sum())})
+    return out
+
+
 def main():
     fa, dd = import_reference()
     import cv2
@@ -160,7 +216,7 @@ def main():
     meta = {"cv2": cv2.__version__, "numpy": np.__version__, "PIL": PIL.__version__,
             "generator": "tests/golden/make_golden.py", "reference": REF}
     for name, data in (("forensics", gen_forensics(fa, dd)), ("tracker", gen_tracker(dd)),
-                       ("clahe", gen_clahe(dd))):
+                       ("clahe", gen_clahe(dd)), ("tta", gen_tta(dd)), ("overlay", gen_overlay(dd))):
         with open(os.path.join(HERE, f"{name}.json"), "w") as f:
             json.dump({"meta": meta, "cases": data}, f, indent=0)
         print(name, "ok")

@@ -323,3 +323,20 @@ int hc_jpeg_decode(const uint8_t* data, long n, uint8_t* out, int sub_bits, int*
     return 0;
 }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Test-time augmentation (csrc/px_warp.h): flip -> convertScaleAbs -> warpAffine of a whole w x h x 3 image.
+#include "px_warp.h"
+extern "C" {
+void hc_tta_augment(const uint8_t* src, int h, int w, int flip, float alpha, const double* im, uint8_t* dst) {
+    uint8_t lut[256];
+    for (int v = 0; v < 256; v++) lut[v] = (uint8_t)dfd_scale_abs_u8(v, alpha);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int o0, o1, o2;
+            dfd_tta_pixel(src, w * 3, w, h, flip, lut, im, x, y, &o0, &o1, &o2);
+            uint8_t* d = dst + ((size_t)y * w + x) * 3;
+            d[0] = (uint8_t)o0; d[1] = (uint8_t)o1; d[2] = (uint8_t)o2;
+        }
+}
+}

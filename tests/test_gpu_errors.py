@@ -138,3 +138,25 @@ def test_two_engines_on_two_devices_in_one_process():
     finally:
         for e in engines:
             e.close()
+
+
+def test_two_engines_with_different_workspaces_on_one_device():
+    """The dynamic shared-memory limit of a kernel belongs to the (device, function) pair: a second engine with a smaller
+    max_crop must not lower it under the first one (regression: 'invalid argument' at k_clahe_hpass)."""
+    from dfd_b200.engine import Engine
+    from oracle import faceprep
+    big = Engine(device=0, max_streams=2, max_batch=4, max_crop=2176)
+    small = Engine(device=0, max_streams=2, max_batch=4, max_crop=256)
+    try:
+        rng = np.random.RandomState(4)
+        frame = synth.make_frame("pink", 720, 1280, rng)
+        ft = torch.from_numpy(frame).cuda().unsqueeze(0)
+        box = np.array([[100, 100, 200, 180]], np.int32)
+        for e in (big, small, big, small, big):
+            out = e.face_prep_batch(ft, box, [0], "fp32")
+            torch.cuda.synchronize()
+            ref = faceprep.prepare(frame, box[0])[0].permute(1, 2, 0).numpy()
+            assert np.abs(out[0].cpu().numpy() - ref).max() < 2e-6
+    finally:
+        big.close()
+        small.close()
