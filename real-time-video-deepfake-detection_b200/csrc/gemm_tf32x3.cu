@@ -83,6 +83,17 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // x ~= hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi): |x - hi - lo| <= 2^-22 |x|
+#ifndef DFD_TF32_CVT
+// rna_tf32 with two full-rate integer instructions, (bits + 0x1000) & ~0x1fff: round to nearest, ties away from zero -- what
+// cvt.rna.tf32.f32 computes for every finite value below the overflow threshold (activations), and what the host uses for the
+// weight planes (tf32_rna_host).  cvt is a conversion-pipe instruction (16 / clk / SM): 64 of them per thread and k-block were
+// the staging warps' longest dependency chain.
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    const float d = x - hi;                                  // exact
+    lo = __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xffffe000u);   // rounded, not left to the tensor core's truncation: one more bit
+}
+#else
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
@@ -91,6 +102,7 @@ __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(d));      // rounded, not left to the tensor core's truncation: one more bit
     lo = __uint_as_float(h);
 }
+#endif
 __device__ __forceinline__ void tf32_split4(const float4 v, uint4& hi, uint4& lo) {
     float h, l;
     tf32_split(v.x, h, l); hi.x = __float_as_uint(h); lo.x = __float_as_uint(l);

@@ -11,7 +11,7 @@
 //   700 KB noise frame and a 10 KB flat frame in the same batch load the chip evenly:
 //     k_jh_blind    every thread decodes its subsequence from the state "a block starts here"; Huffman streams
 //                   resynchronise, so most END states are already right
-//     k_jh_round    x JH_ROUNDS: thread i re-decodes subsequence i from the END state of subsequence i-1 whenever that
+//     k_jh_round    x 4 (DFD_JH_ROUNDS): thread i re-decodes subsequence i from the END state of subsequence i-1 whenever that
 //                   changed (a frame whose previous round changed nothing exits at once).  When a whole round changes
 //                   nothing, by induction from subsequence 0 (whose start is known) every state is exact.
 //     k_jh_finish   CTA per frame, only for frames still changing after the flat rounds (pathological streams): rounds in a
@@ -32,7 +32,8 @@
 #define JPG_SUB_BITS 2048
 #define JPG_THREADS 512
 #define JH_THREADS 128
-#define JH_ROUNDS 12
+#define JH_ROUNDS 12                  // upper bound of the flat rounds (array sizing)
+#define JH_ROUNDS_DEFAULT 4           // measured on 256 x 720p: rounds + finish 2.75 ms at 12, 2.51 at 6, 2.43 at 3 (bench mix); natural frames 1.21 -> 1.16 ms at 4
 #define JU_CHUNK 2048                 // raw bytes per unstuffing chunk = 128 threads x 16 bytes
 
 struct JpgMeta {
@@ -325,6 +326,7 @@ struct JhArgs {
     const JpgMeta* meta; const DfdJpegHeader* hdr; const uint32_t* words; const uint32_t* nbits;
     unsigned long long* E; unsigned long long* used; int* cnt; int* blk0; int* changed;
     int16_t* coef; int32_t* dc; long long blocks_stride;
+    int last_round;                   // index of the last flat synchronisation round that was launched
 };
 
 // grid (subsequence groups, frames); mode 0: blind pass, 1: synchronisation round `round`, 2: write pass
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(JH_THREADS) k_jh_pass(const JhArgs a, int roun
 __global__ void __launch_bounds__(JPG_THREADS) k_jh_finish(const JhArgs a) {
     __shared__ JhTabs T;
     const int f = blockIdx.x, tid = threadIdx.x;
-    if (a.changed[f * JH_ROUNDS + JH_ROUNDS - 1] == 0) return;
+    if (a.changed[f * JH_ROUNDS + a.last_round] == 0) return;
     const JpgMeta M = a.meta[f];
     const DfdJpegHeader* h = a.hdr + f;
     jh_load_tabs(T, h, tid, JPG_THREADS);
@@ -506,6 +508,86 @@ k_jpeg_idct(const DfdJpegHeader* __restrict__ hdr, const int16_t* __restrict__ c
             hi |= (uint32_t)dfd_sat_u8(b[r * 8 + 4 + k] + 128) << (8 * k);
         }
         *(uint2*)(out + (size_t)r * pitch) = make_uint2(lo, hi);
+    }
+}
+
+// 4:2:0 (the wire format): thread = 8 horizontally adjacent pixels of TWO rows (2r, 2r + 1: they share chroma row r).
+// Per plane the thread needs chroma columns cx0 - 1 .. cx0 + 4 of rows r - 1, r, r + 1: one aligned 32-bit load + two edge
+// bytes per row (18 loads for 16 pixels; the 4-pixel kernel below issues 68), luma as two 8-byte loads, and the 2 x 24 output
+// bytes leave as 8-byte stores (consecutive lanes write consecutive 24-byte runs).  Same arithmetic as jdsample.c
+// h2v2_fancy_upsample: vertical 3:1 blend first, then horizontal 3:1 with the +8 / +7 rounding pair; clamping the neighbour
+// index at the plane's edges reproduces libjpeg's edge special cases exactly ((3t + t + 8) >> 4 == (4t + 8) >> 4).
+__global__ void __launch_bounds__(256)
+k_jpeg_color420(const DfdJpegHeader* __restrict__ hdr, const uint8_t* __restrict__ planes_all, long long plane_stride,
+                uint8_t* __restrict__ frames, size_t frame_stride, int row_pitch, int H, int W) {
+    const int f = blockIdx.z;
+    const DfdJpegHeader* h = hdr + f;
+    const int xg = blockIdx.x * 64 + (threadIdx.x & 63), x0 = xg * 8;
+    const int r = blockIdx.y * 4 + (threadIdx.x >> 6), y0 = r * 2;
+    if (y0 >= H || x0 >= W) return;
+    const uint8_t* P = planes_all + (size_t)f * plane_stride;
+    const int pitch0 = h->comp_bw[0] * 8, pitch1 = h->comp_bw[1] * 8;
+    const uint8_t* p1 = P + (size_t)h->comp_bw[0] * h->comp_bh[0] * 64;
+    const uint8_t* p2 = p1 + (size_t)h->comp_bw[1] * h->comp_bh[1] * 64;
+    const int cw = (W + 1) >> 1, chh = (H + 1) >> 1;
+    const int cx0 = xg * 4;
+    const int rm = max(r - 1, 0), rp = min(r + 1, chh - 1);
+    const bool interior = cx0 >= 1 && cx0 + 4 <= cw - 1;
+    int te[2][6], to[2][6];                                 // vertical blends for the even / odd output row, per plane
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) {
+        const uint8_t* base = pl ? p2 : p1;
+        int v[3][6];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint8_t* row = base + (size_t)(k == 0 ? rm : (k == 1 ? r : rp)) * pitch1;
+            if (interior) {
+                const uint32_t w = *(const uint32_t*)(row + cx0);          // cx0 % 4 == 0, pitch1 % 8 == 0: aligned
+                v[k][0] = row[cx0 - 1]; v[k][5] = row[cx0 + 4];
+                v[k][1] = w & 255u; v[k][2] = (w >> 8) & 255u; v[k][3] = (w >> 16) & 255u; v[k][4] = w >> 24;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 6; q++) v[k][q] = row[min(max(cx0 - 1 + q, 0), cw - 1)];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) { te[pl][q] = 3 * v[1][q] + v[0][q]; to[pl][q] = 3 * v[1][q] + v[2][q]; }
+    }
+    const bool al8 = (((uintptr_t)frames | frame_stride | (size_t)row_pitch) & 7) == 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int y = y0 + half;
+        if (y >= H) break;
+        const uint2 yw = *(const uint2*)(P + (size_t)y * pitch0 + x0);
+        uint8_t px[24];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int q = 1 + (i >> 1);
+            int cbv, crv;
+            if (half == 0) {
+                cbv = (i & 1) ? (te[0][q] * 3 + te[0][q + 1] + 7) >> 4 : (te[0][q] * 3 + te[0][q - 1] + 8) >> 4;
+                crv = (i & 1) ? (te[1][q] * 3 + te[1][q + 1] + 7) >> 4 : (te[1][q] * 3 + te[1][q - 1] + 8) >> 4;
+            } else {
+                cbv = (i & 1) ? (to[0][q] * 3 + to[0][q + 1] + 7) >> 4 : (to[0][q] * 3 + to[0][q - 1] + 8) >> 4;
+                crv = (i & 1) ? (to[1][q] * 3 + to[1][q + 1] + 7) >> 4 : (to[1][q] * 3 + to[1][q - 1] + 8) >> 4;
+            }
+            const int Y = (int)(((i < 4 ? yw.x : yw.y) >> (8 * (i & 3))) & 255u);
+            int rr, gg, bb;
+            dfd_jpeg_ycc2rgb(Y, cbv, crv, &rr, &gg, &bb);
+            px[3 * i] = (uint8_t)bb; px[3 * i + 1] = (uint8_t)gg; px[3 * i + 2] = (uint8_t)rr;
+        }
+        uint8_t* o = frames + (size_t)f * frame_stride + (size_t)y * row_pitch + (size_t)x0 * 3;
+        if (x0 + 8 <= W && al8) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                uint2 w;
+                w.x = px[8 * k] | (px[8 * k + 1] << 8) | (px[8 * k + 2] << 16) | ((uint32_t)px[8 * k + 3] << 24);
+                w.y = px[8 * k + 4] | (px[8 * k + 5] << 8) | (px[8 * k + 6] << 16) | ((uint32_t)px[8 * k + 7] << 24);
+                ((uint2*)o)[k] = w;
+            }
+        } else {
+            for (int i = 0; i < 8 && x0 + i < W; i++) { o[3 * i] = px[3 * i]; o[3 * i + 1] = px[3 * i + 1]; o[3 * i + 2] = px[3 * i + 2]; }
+        }
     }
 }
 
@@ -679,14 +761,17 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
     DFD_LAUNCH_CHECK("k_ju_scan", st);
     k_ju_scatter<<<dim3(gc, n), 128, 0, st>>>((const uint8_t*)ctx->jpg_raw.p, d_meta, d_hdr, d_chunk, (uint32_t*)ctx->jpg_words.p);
     DFD_LAUNCH_CHECK("k_ju_scatter", st);
+    static const int rounds_env = getenv("DFD_JH_ROUNDS") ? atoi(getenv("DFD_JH_ROUNDS")) : JH_ROUNDS_DEFAULT;
+    const int n_rounds = rounds_env < 1 ? 1 : (rounds_env > JH_ROUNDS ? JH_ROUNDS : rounds_env);
     JhArgs ja;
+    ja.last_round = n_rounds - 1;
     ja.meta = d_meta; ja.hdr = d_hdr; ja.words = (const uint32_t*)ctx->jpg_words.p; ja.nbits = d_nbits;
     ja.E = d_E; ja.used = d_used; ja.cnt = d_cnt; ja.blk0 = d_blk0; ja.changed = d_changed;
     ja.coef = (int16_t*)ctx->jpg_coef.p; ja.dc = (int32_t*)ctx->jpg_dc.p; ja.blocks_stride = blocks_stride;
     const unsigned gs = (unsigned)(((long long)max_ecs * 8 + JPG_SUB_BITS - 1) / JPG_SUB_BITS + JH_THREADS - 1) / JH_THREADS;
     k_jh_pass<0><<<dim3(gs, n), JH_THREADS, 0, st>>>(ja, 0);
     DFD_LAUNCH_CHECK("k_jh_blind", st);
-    for (int r = 0; r < JH_ROUNDS; r++) {
+    for (int r = 0; r < n_rounds; r++) {
         k_jh_pass<1><<<dim3(gs, n), JH_THREADS, 0, st>>>(ja, r);
         DFD_LAUNCH_CHECK("k_jh_round", st);
     }
@@ -701,8 +786,19 @@ int dfd_jpeg_decode_launch(dfd_ctx* ctx, const uint8_t* bytes_host, const int64_
     k_jpeg_idct<<<dim3((unsigned)((blocks_stride + 127) / 128), n), 128, 0, st>>>(d_hdr, (const int16_t*)ctx->jpg_coef.p, (const int32_t*)ctx->jpg_dc.p,
                                                                                   blocks_stride, (uint8_t*)ctx->jpg_planes.p, plane_stride);
     DFD_LAUNCH_CHECK("k_jpeg_idct", st);
-    k_jpeg_color<<<dim3((W + 255) / 256, (H + 3) / 4, n), 256, 0, st>>>(d_hdr, (const uint8_t*)ctx->jpg_planes.p, plane_stride, frames_out,
-                                                                        frame_stride, row_pitch, H, W);
+    // every frame of the batch 4:2:0 with more than two chroma columns (what browsers and cv2.imencode emit): the 16-pixel kernel
+    bool all420 = true;
+    for (int i = 0; i < n; i++) {
+        const DfdJpegHeader& h = J->h_hdr_pinned[i];
+        all420 = all420 && h.ncomp == 3 && h.hs[0] == 2 && h.vs[0] == 2 && h.hs[1] == 1 && h.vs[1] == 1 && h.hs[2] == 1 && h.vs[2] == 1 && W > 4;
+    }
+    static const bool no420 = getenv("DFD_JPEG_NO420") != nullptr;
+    if (all420 && !no420)
+        k_jpeg_color420<<<dim3((W + 511) / 512, (H + 7) / 8, n), 256, 0, st>>>(d_hdr, (const uint8_t*)ctx->jpg_planes.p, plane_stride, frames_out,
+                                                                               frame_stride, row_pitch, H, W);
+    else
+        k_jpeg_color<<<dim3((W + 255) / 256, (H + 3) / 4, n), 256, 0, st>>>(d_hdr, (const uint8_t*)ctx->jpg_planes.p, plane_stride, frames_out,
+                                                                            frame_stride, row_pitch, H, W);
     DFD_LAUNCH_CHECK("k_jpeg_color", st);
     return DFD_OK;
 }
