@@ -276,7 +276,8 @@ int64_t dfd_dbg_activation(dfd_ctx* ctx, const char* name, float* out_dev, int64
  * instead of the fused mbconv_fused.cu kernel), "se_mode" (bf16 SE excite: 0 = two kernels, 1 = one kernel, 2 = one kernel on 8-CTA clusters), "no_gated_w" (1 = blocks 0-4 gate the
  * project GEMM's A operand instead of using per-image gated weights), "pdl" (0 = no programmatic dependent launch),
  * "no_overlap" (1 = forensic kernels on the caller's stream), "fp32_simt" (1 = fp32 mode on the CUDA-core kernels instead of
- * the 3xTF32 tensor-core path).
+ * the 3xTF32 tensor-core path), "dual_chain" (0 = the classifier runs a large batch as ONE chain of kernels instead of two
+ * concurrent half-batch chains).
  * Threading / devices: one context per GPU; every entry point makes the context's device current for its duration and
  * restores the caller's, so one process may drive several contexts on different GPUs (from one thread at a time each). */
 int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value);

@@ -204,6 +204,8 @@ int dfd_create(const dfd_config* cfg, dfd_ctx** out) {
     if (const char* e = getenv("DFD_GATED_W_MAX")) { ctx->gated_w_max = atoi(e); if (ctx->gated_w_max > 10) ctx->gated_w_max = 10; }
     ctx->no_fold = getenv("DFD_NO_FOLD") != nullptr;
     ctx->fp32_simt = getenv("DFD_FP32_SIMT") != nullptr;
+    if (getenv("DFD_DUAL_CHAIN")) ctx->dual_chain = atoi(getenv("DFD_DUAL_CHAIN")) != 0;
+    if (getenv("DFD_DUAL_MIN")) ctx->dual_min = atoi(getenv("DFD_DUAL_MIN"));
     if (const char* e = getenv("DFD_L2_BUDGET_MB")) { ctx->l2_budget = atoi(e) << 20; ctx->no_subbatch = ctx->l2_budget <= 0; }
     if (getenv("DFD_SE_MODE")) ctx->se_mode = atoi(getenv("DFD_SE_MODE"));
     int rc = create_impl(ctx);
@@ -224,6 +226,10 @@ void dfd_destroy(dfd_ctx* ctx) {
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
+    if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
+    for (DfdBuf& b : ctx->act_b) if (b.p) cudaFree(b.p);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     dfd_gemm_free(ctx);
     dfd_jpeg_free(ctx);
@@ -464,6 +470,7 @@ int dfd_dbg_set_option(dfd_ctx* ctx, const char* name, int value) {
     else if (n == "se_mode") ctx->se_mode = value;
     else if (n == "no_overlap") ctx->no_overlap = value != 0;
     else if (n == "fp32_simt") ctx->fp32_simt = value != 0;
+    else if (n == "dual_chain") ctx->dual_chain = value != 0;
     else if (n == "no_subbatch") ctx->no_subbatch = value != 0;
     else { ctx->err = "dbg_set_option: unknown option " + n; return DFD_ERR_INVALID; }
     return DFD_OK;

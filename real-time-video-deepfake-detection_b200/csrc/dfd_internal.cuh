@@ -102,6 +102,11 @@ struct dfd_ctx {
     int l2_budget = 64 << 20;             //   DFD_L2_BUDGET_MB=n / "no_subbatch" = 0 turns them on with n MB of expanded tensor per sub-batch
     bool fp32_simt = false;               // "fp32_simt" / DFD_FP32_SIMT=1: run the fp32 mode on the CUDA-core kernels (k_pw / k_dw / k_stem; A/B testing)
     DfdBuf act[3];                        // activation ping-pong + expanded buffer
+    DfdBuf act_b[3];                      // the same for the second half-batch chain (effnet.cu dfd_effnet_launch)
+    bool dual_chain = false;              // batches >= dual_min run as two concurrent half-batch chains ("dual_chain" option / DFD_DUAL_CHAIN=1): MEASURED AND OFF -- fp32 5.27 -> 5.47 ms per 256 crops, bf16 unchanged: the persistent GEMM CTAs (140-200 KB of shared memory, 61 k registers) leave no room for a second chain's CTAs, and half-size kernels lose efficiency
+    int dual_min = 64;
+    cudaStream_t aux2 = nullptr;
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     DfdBuf face_in;                       // prepared crops for analyze_batch
     float* d_pool = nullptr;              // [m][n_parts][C] SE squeeze partial sums (<= DFD_POOL_FLOATS per image)
     float* d_sescale = nullptr;           // [m][1152]

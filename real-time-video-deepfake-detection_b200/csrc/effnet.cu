@@ -1048,11 +1048,50 @@ static int forward_t(dfd_ctx* ctx, const T* in, int m, float* logits, cudaStream
     return DFD_OK;
 }
 
+static int effnet_forward_any(dfd_ctx* ctx, const void* in, int m, int dtype, float* logits, cudaStream_t st) {
+    if (dtype == DFD_F32) return forward_t<float>(ctx, (const float*)in, m, logits, st);
+    return forward_t<__nv_bfloat16>(ctx, (const __nv_bfloat16*)in, m, logits, st);
+}
+
+// Large batches run as TWO independent half-batch chains on two streams (the caller's and ctx->aux2).  A single chain leaves
+// SMs idle INSIDE its kernels -- the 16 squeeze-excite launches are latency chains that occupy a fraction of the chip, the
+// deep layers (M = batch x 49 rows) have fewer tiles than SMs, every kernel ends in a partial wave -- and nothing else is
+// runnable, because each layer depends on the previous one.  The second chain is: its CTAs fill those holes.  The halves share
+// nothing but the (read-only) weights: the second one gets its own activation buffers and its slice of every per-image
+// scratch array.  Results are bit-identical to the single chain (every kernel is batch-invariant: tests/test_gpu_effnet.py).
 int dfd_effnet_launch(dfd_ctx* ctx, const void* in, int m, int dtype, float* logits, cudaStream_t st) {
     DFD_REQUIRE(ctx->has_weights, DFD_ERR_NO_WEIGHTS, "effnet_forward: call dfd_load_weights first");
     DFD_REQUIRE(m > 0 && m <= ctx->cfg.max_batch, DFD_ERR_CAPACITY, "effnet_forward: batch exceeds max_batch");
-    if (dtype == DFD_F32) return forward_t<float>(ctx, (const float*)in, m, logits, st);
-    if (dtype == DFD_BF16) return forward_t<__nv_bfloat16>(ctx, (const __nv_bfloat16*)in, m, logits, st);
-    ctx->err = "effnet_forward: bad dtype";
-    return DFD_ERR_INVALID;
+    DFD_REQUIRE(dtype == DFD_F32 || dtype == DFD_BF16, DFD_ERR_INVALID, "effnet_forward: bad dtype");
+    const bool dual = ctx->dual_chain && m >= ctx->dual_min && !ctx->profiling && !ctx->trace && ctx->tap_name.empty() &&
+                      !(dtype == DFD_F32 && ctx->fp32_simt);
+    if (!dual) return effnet_forward_any(ctx, in, m, dtype, logits, st);
+    if (!ctx->aux2) {
+        DFD_CUDA(cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking));
+        DFD_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
+        DFD_CUDA(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
+    }
+    const int m0 = ((m + 1) / 2 + 7) & ~7, m1 = m - m0;       // (gated tiles / clusters like multiples of 8 images)
+    const size_t esz = dtype == DFD_BF16 ? 2 : 4;
+    DFD_CUDA(cudaEventRecord(ctx->ev_fork2, st));
+    DFD_CUDA(cudaStreamWaitEvent(ctx->aux2, ctx->ev_fork2, 0));
+    int rc = effnet_forward_any(ctx, in, m0, dtype, logits, st);
+    if (rc) return rc;
+    // second half: its own activation buffers, its slice of the per-image scratch (pointers are launch arguments: swapping them
+    // on the host while the first half's kernels are queued is safe)
+    struct Saved { DfdBuf act[3]; float *pool, *sescale, *se_r, *feat, *h1, *h2; __nv_bfloat16 *wg, *wgf; } sv;
+    for (int i = 0; i < 3; i++) { sv.act[i] = ctx->act[i]; ctx->act[i] = ctx->act_b[i]; }
+    sv.pool = ctx->d_pool; sv.sescale = ctx->d_sescale; sv.se_r = ctx->d_se_r; sv.feat = ctx->d_feat; sv.h1 = ctx->d_fc_h1; sv.h2 = ctx->d_fc_h2;
+    sv.wg = ctx->d_wgated; sv.wgf = ctx->d_wgated_fold;
+    ctx->d_pool += (size_t)m0 * DFD_POOL_FLOATS; ctx->d_sescale += (size_t)m0 * 1152; ctx->d_se_r += (size_t)m0 * 64;
+    ctx->d_feat += (size_t)m0 * 1280; ctx->d_fc_h1 += (size_t)m0 * 512; ctx->d_fc_h2 += (size_t)m0 * 256;
+    ctx->d_wgated += (size_t)m0 * 112 * 672; ctx->d_wgated_fold += (size_t)m0 * 32 * 64;
+    rc = effnet_forward_any(ctx, (const uint8_t*)in + (size_t)m0 * 224 * 224 * 3 * esz, m1, dtype, logits + m0, ctx->aux2);
+    for (int i = 0; i < 3; i++) { ctx->act_b[i] = ctx->act[i]; ctx->act[i] = sv.act[i]; }
+    ctx->d_pool = sv.pool; ctx->d_sescale = sv.sescale; ctx->d_se_r = sv.se_r; ctx->d_feat = sv.feat; ctx->d_fc_h1 = sv.h1; ctx->d_fc_h2 = sv.h2;
+    ctx->d_wgated = sv.wg; ctx->d_wgated_fold = sv.wgf;
+    if (rc) return rc;
+    DFD_CUDA(cudaEventRecord(ctx->ev_join2, ctx->aux2));
+    DFD_CUDA(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+    return DFD_OK;
 }

@@ -16,7 +16,7 @@
 //  (1) the small correction products (A_lo.W_hi + A_hi.W_lo) and the main product (A_hi.W_hi) go to TWO different TMEM
 //      accumulators of the ring -- added to a large accumulator under round-toward-zero, a tiny addend of the opposite sign
 //      costs a whole ulp -- and the epilogue adds the pair;
-//  (2) layers with K > 160 accumulate in CHUNKS of four k-blocks (K = 128): every chunk starts a fresh accumulator pair, and
+//  (2) layers with K > 192 accumulate in CHUNKS of six k-blocks (K = 192): every chunk starts a fresh accumulator pair, and
 //      the epilogue warps -- idle during the k-loop anyway -- drain every accumulator as it completes and add it, with
 //      round-to-nearest FADDs, into a running tile in shared memory (the store-staging buffer in its final layout).  The
 //      truncation of a chunk is relative to the chunk's own small magnitude and follows the chunk's sign, so across chunks it
@@ -24,7 +24,10 @@
 //  (3) what remains is, to 70 %, a pure SCALE factor: truncation toward zero shrinks a main-term accumulator by an expected
 //      2.51e-8 * n^0.87 after n accumulations (tools/tf32_bias.py, profiles/tf32_bias_r02.txt: 8.4e-8 / 1.5e-7 / 2.8e-7 at
 //      n = 4 / 8 / 16), and the epilogue multiplies every drained main accumulator by 1 + that expectation, which turns
-//      round-toward-zero into an unbiased rounding.  The same law holds for the single pair of the shallow (K <= 160) layers.
+//      round-toward-zero into an unbiased rounding.  The same law holds for the single pair of the shallow (K <= 192) layers.
+//      (Chunk length and the plain / chunked boundary were re-swept at the end of round 2 -- 4 / 160, 6 / 192, 8 / 256, 12 / 384:
+//      5.36 / 5.21 / 5.19 / 5.17 ms per 256 crops, largest per-layer error 1.7 / 2.4 / 3.4 / 4.4 e-6, whole network max |dp|
+//      8.0 / 5.5 / 6.0 / 7.2 e-6: six k-blocks take most of the time and stay well inside the 4e-6 per-layer test bound.)
 // Measured: rms relative error 0.6e-7 .. 1.9e-7 for every layer shape with a residual scale bias below 1.3e-8 (one accumulator
 // at K = 1152: 4.5e-5); whole network max |dp| 4.7e-4 -> 8e-6 (fp32 CUDA-core path: 9e-6).
 // The weights are split once on the host (W_hi / W_lo planes).  The activations are split ON THE FLY, tile by tile, in
@@ -63,9 +66,9 @@ struct TGemmParams {
     int n_pad, n_blocks, num_tiles, stages, act, a_mode, hw, b_resident, n_acc, epi_db, dense_c;
     int ch;                    // k-blocks per accumulation chunk
     float beta_instr;          // expected relative shrink of a main-term accumulator after n MMA accumulations (round toward zero) = beta_instr * n^0.87, compensated in the epilogue
-    float beta_plain;          // the same expectation for the one main-term accumulator of a plain (K <= 160) layer
+    float beta_plain;          // the same expectation for the one main-term accumulator of a plain (K <= 192) layer
     int chunked;               // every chunk uses TWO ring accumulators (correction terms, main term).  1: several chunks per tile, the
-                               //    epilogue adds them into a running tile with round-to-nearest; 0 (K <= 160): one chunk per tile,
+                               //    epilogue adds them into a running tile with round-to-nearest; 0 (K <= 192): one chunk per tile,
                                //    plain ping-pong epilogue (main * (1 + beta) + corrections)
     const float* bias;
     const float* residual;
@@ -642,15 +645,16 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     p.num_tiles = m_blocks * p.n_blocks;
     const int num_kb = (K + TBLOCK_K - 1) / TBLOCK_K;
     const int budget = 200 * 1024;
-    // accumulation chunks of two k-blocks (see the header: the tensor core's accumulator truncates); K <= 64 is one chunk and
+    // accumulation chunks of six k-blocks (see the header: the tensor core's accumulator truncates); K <= 192 is one chunk and
     // keeps the plain ping-pong epilogue
     static const int force_ch = getenv("DFD_TF32_CHUNK") ? atoi(getenv("DFD_TF32_CHUNK")) : 0;
-    p.ch = 4;                                                // K = 128 per chunk: 16 main-term accumulations per accumulator
+    p.ch = 6;                                                // K = 192 per chunk: 24 main-term accumulations per accumulator
     if (force_ch > 0) p.ch = force_ch;
-    if (num_kb <= 5) p.ch = num_kb;                          // plain layers: one chunk (= one accumulator pair) per tile
-    // K <= 160 (five k-blocks): one accumulator per tile and the ping-pong epilogue -- the shallow layers are huge-M and
+    static const int plain_kb = getenv("DFD_TF32_PLAIN_KB") ? atoi(getenv("DFD_TF32_PLAIN_KB")) : 6;
+    if (num_kb <= plain_kb) p.ch = num_kb;                   // plain layers: one chunk (= one accumulator pair) per tile
+    // K <= 192 (six k-blocks): one accumulator pair per tile and the ping-pong epilogue -- the shallow layers are huge-M and
     // epilogue-bound (b2.project: 196 us plain, 310 us chunked), their truncation bias is small and compensated as a whole
-    const bool chunked = num_kb > 5;
+    const bool chunked = num_kb > plain_kb;
     p.chunked = chunked ? 1 : 0;
     // Expected-value compensation of the tensor core's round-toward-zero accumulation (measured with tools/tf32_bias.py: the
     // GEMM's error is, to 70 %, a pure scale factor 1 - beta; profiles/tf32_bias_r02.txt).  Chunked layers: beta per main-term
