@@ -11,12 +11,18 @@ python tools/prof_effnet.py 256 1 fp32 > $OUT/prof_pre.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:"k_gemm_tf32x3|k_dw_tile_f32" -c 49 -o $OUT/ncu_fp32_r02 -f \
     python tools/prof_effnet.py 256 1 fp32 > $OUT/ncu_fp32.log 2>&1
 ncu -i $OUT/ncu_fp32_r02.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_extract.py > $OUT/ncu_fp32_r02_raw.csv
+python tools/ncu_traffic.py $OUT/ncu_fp32_r02_raw.csv > $OUT/traffic_r02.json
 ncu -i $OUT/ncu_fp32_r02.ncu-rep --page details --kernel-name regex:k_gemm_tf32x3 --launch-count 1 --launch-skip 4 > $OUT/ncu_tf32_b1expand_details_r02.txt 2>/dev/null
 ncu -i $OUT/ncu_fp32_r02.ncu-rep --page details --kernel-name regex:k_gemm_tf32x3 --launch-count 1 --launch-skip 25 > $OUT/ncu_tf32_b9project_details_r02.txt 2>/dev/null
 rm -f $OUT/ncu_fp32_r02.ncu-rep
 python tools/jpeg_probe.py > $OUT/jpeg_pre.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:"k_jh_|k_ju_|k_jpeg_" --launch-skip 154 -c 22 -o $OUT/ncu_jpeg_r02 -f \
+ncu --set full --clock-control none --import-source on -k regex:"k_jh_|k_ju_|k_jpeg_" --launch-skip 98 -c 14 -o $OUT/ncu_jpeg_r02 -f \
     python tools/jpeg_probe.py > $OUT/ncu_jpeg.log 2>&1
 ncu -i $OUT/ncu_jpeg_r02.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_extract.py > $OUT/ncu_jpeg_r02_raw.csv
 rm -f $OUT/ncu_jpeg_r02.ncu-rep
+python tools/tta_overlay_probe.py > $OUT/tta_overlay_probe_r02.txt 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:"k_tta_hpass|k_overlay|k_clahe_hpass|k_vpass" --launch-skip 6 -c 5 -o $OUT/ncu_tta_r02 -f \
+    python tools/tta_overlay_probe.py > $OUT/ncu_tta.log 2>&1
+ncu -i $OUT/ncu_tta_r02.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_extract.py > $OUT/ncu_tta_overlay_r02_raw.csv
+rm -f $OUT/ncu_tta_r02.ncu-rep
 ls -la $OUT | tail -20
