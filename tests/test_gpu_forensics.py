@@ -73,6 +73,12 @@ def test_forensics_720p_sequences(eng, family):
     _run_case(eng, family, 720, 1280, 14, seed=101 + synth.FAMILIES.index(family), stream=3)
 
 
+def test_forensics_temporal_deque_wraps(eng):
+    """44 frames of one stream: temporal_diffs is a deque(maxlen=30) (frame_analysis.py:36) -- the ring wraps after the 31st
+    frame and the CV / last-difference statistics must keep following the oracle's deque (small frames: the oracle is the cost)."""
+    _run_case(eng, "pink", 240, 320, 44, seed=77, stream=6)
+
+
 @pytest.mark.parametrize("shape", [(1080, 1920), (480, 640), (120, 160), (333, 517), (256, 256), (2160, 3840)])
 def test_forensics_resolutions(eng, shape):
     _run_case(eng, "pink", shape[0], shape[1], 4, seed=7, stream=5)
