@@ -64,6 +64,9 @@ enum { TA_PLAIN = 0, TA_SCALE = 1, TA_STEM = 2 };
 struct TGemmParams {
     int M, N, K;
     int n_pad, n_blocks, num_tiles, stages, act, a_mode, hw, b_resident, n_acc, epi_db, dense_c;
+    uint32_t stg_stride;       // plain epilogue: bytes per store-staging block (128 rows x 128 B; dense N <= 32 tiles: 128 rows x N x 4 B -- the
+                               //    difference buys the huge-M project layers another pipeline stage)
+    int pf;                    // A tiles prefetched into L2 this many k-blocks ahead of their TMA load (0 = off)
     uint32_t bias_off;         // byte offset of the bias table from the aligned base of dynamic shared memory
     int epi_groups;            // 2: warps 4-11 drain accumulators, warps 12-19 stage A (two groups on alternate k-blocks).  3 (shallow plain layers with a
                                //    wide N: the epilogue is the critical path and one staging group keeps up): warps 16-19 are a THIRD epilogue group
@@ -193,9 +196,22 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const bool load_a = p.a_mode != TA_STEM, load_b = !p.b_resident;
             const uint32_t tx = (load_a ? (uint32_t)TA_BYTES : 0u) + (load_b ? 2u * b_plane_bytes : 0u);
             if (tx != 0) {
+                // L2 prefetch cursor, p.pf k-blocks ahead of the loads (cp.async.bulk.prefetch.tensor needs no shared memory: the tile
+                // is pulled into L2 early and the real load pays L2 latency instead of DRAM latency).  MEASURED AND OFF (DFD_TF32_PF=n):
+                // 4 / 8 / 16 / 32 k-blocks ahead change the layer table by +0.1 / +0.7 / +1.9 / +3.9 % -- DRAM latency is not what
+                // the pipeline waits for; its own hand-over chain (TMA -> split -> MMA -> release, four barrier hops) is.
+                int pf_tile = blockIdx.x, pf_kb = 0;
+                auto pf_issue = [&]() {
+                    if (!load_a || pf_tile >= p.num_tiles) return;
+                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                                 ::"l"(&map_a), "r"(pf_kb * TBLOCK_K), "r"((pf_tile / p.n_blocks) * TBLOCK_M) : "memory");
+                    if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
+                };
+                for (int i = 0; i < p.pf; i++) pf_issue();
                 for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                     const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
                     for (int kb = 0; kb < num_kb; kb++) {
+                        if (p.pf > 0) pf_issue();
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + 2u * TA_BYTES;
                         mbar_expect_tx(raw0 + 8 * stage, tx);
@@ -501,7 +517,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const int q = warp & 3;                                    // TMEM lane quarter (= warp % 4)
         const int row = q * 32 + lane;
         const bool issuer = q == 0 && lane == 0;
-        const uint32_t my_staging = staging + (uint32_t)(p.epi_db ? 2 * set : set) * TSTAGING_BLOCK_BYTES;
+        const uint32_t my_staging = staging + (uint32_t)(p.epi_db ? 2 * set : set) * p.stg_stride;
         const int nblk32 = (p.n_pad + 31) >> 5;
         uint32_t blk_count = 0;
         int it = 0;
@@ -528,7 +544,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const uint32_t taddr_c = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
             const uint32_t taddr = taddr_c + (uint32_t)p.n_pad;
             for (int jb = 0; jb < nblk32; jb++, blk_count++) {
-                const uint32_t buf = my_staging + (p.epi_db ? (blk_count & 1u) * TSTAGING_BLOCK_BYTES : 0u);
+                const uint32_t buf = my_staging + (p.epi_db ? (blk_count & 1u) * p.stg_stride : 0u);
                 // one buffer: its previous store must have been read before anyone writes -> wait + barrier here; two buffers:
                 // the issuer confirms before the barrier that ENDS a block that the store issued one block earlier has been read
                 if (!p.epi_db) {
@@ -657,7 +673,8 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     p.dense_c = N <= 32 ? 1 : 0;
     // N tiling: equal UMMA-N blocks (multiples of 16, <= 128 so that a stage with both W planes stays <= 64 KB); with several
     // blocks the width is a multiple of 32 so that the 32-column TMA stores of one block never touch its neighbour's columns
-    const int nb = (N + 127) / 128;
+    static const int n_max = getenv("DFD_TF32_NMAX") ? atoi(getenv("DFD_TF32_NMAX")) : 128;
+    const int nb = (N + n_max - 1) / n_max;
     const int n_pad = nb == 1 ? (N + 15) / 16 * 16 : ((N + nb - 1) / nb + 31) / 32 * 32;
     p.n_pad = n_pad; p.n_blocks = (N + n_pad - 1) / n_pad;
     p.n_acc = tgemm_n_acc(n_pad);
@@ -701,7 +718,8 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     static const bool even_only = getenv("DFD_TF32_EVEN") != nullptr, cap_depth = getenv("DFD_TF32_CAP") != nullptr;
     int staging_bytes = 0, stage_bytes = 0, stages = 0;
     for (;;) {
-        staging_bytes = chunked ? nblk32 * TSTAGING_BLOCK_BYTES : 2 * p.epi_groups * TSTAGING_BLOCK_BYTES;
+        p.stg_stride = (!chunked && p.dense_c) ? (uint32_t)((TBLOCK_M * N * 4 + 1023) & ~1023) : (uint32_t)TSTAGING_BLOCK_BYTES;
+        staging_bytes = chunked ? nblk32 * TSTAGING_BLOCK_BYTES : 2 * p.epi_groups * (int)p.stg_stride;
         const int st_res = p.n_blocks == 1 ? (avail - staging_bytes - b_bytes) / (2 * TA_BYTES) : 0;
         const int st_str = (avail - staging_bytes) / (2 * TA_BYTES + 2 * n_pad * 128);
         p.b_resident = (st_res >= 2 && st_res >= st_str) ? 1 : 0;
@@ -716,6 +734,8 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     }
     DFD_REQUIRE(stages >= 2, DFD_ERR_INVALID, "gemm_tf32x3: tile does not fit shared memory");
     p.stages = stages;
+    static const int pf_env = getenv("DFD_TF32_PF") ? atoi(getenv("DFD_TF32_PF")) : 0;
+    p.pf = a_mode == TA_STEM ? 0 : pf_env;
     p.bias_off = (uint32_t)(stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes);
     const size_t smem = (size_t)p.bias_off + bias_bytes + 1024;
     TGemmKernel kern = tgemm_kernel(residual != nullptr, act != 0, p.dense_c != 0);
