@@ -726,7 +726,9 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
         stage_bytes = 2 * TA_BYTES + (p.b_resident ? 0 : 2 * n_pad * 128);
         stages = p.b_resident ? st_res : st_str;
         if (stages > 8) stages = 8;
-        if (a_mode == TA_STEM && stages > 2) stages = 2;     // the stem's gather is bound by its own loads: 4 stages measured 217 -> 295 us
+        // the stem is bound by its im2col gather, not by pipeline depth: 2 / 3 / 4 stages measured 218 / 218 / 219 us
+        static const int stem_st = getenv("DFD_TF32_STEM_STAGES") ? atoi(getenv("DFD_TF32_STEM_STAGES")) : 2;
+        if (a_mode == TA_STEM && stages > stem_st) stages = stem_st;
         if (even_only) stages &= ~1;
         if (cap_depth && stages > 2 * ((num_kb + 1) / 2) && stages > 2) { stages = 2 * ((num_kb + 1) / 2); if (stages < 2) stages = 2; }
         if (stages >= 2 || p.epi_groups == 2) break;
