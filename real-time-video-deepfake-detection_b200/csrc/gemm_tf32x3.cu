@@ -35,7 +35,7 @@
 //
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads (fp32, SWIZZLE_128B: 32 floats = one 128-byte row) of the raw
 //               A tile (128 x 32) and -- unless W is resident -- the W_hi / W_lo tiles (n_pad x 32 each) of the k-block.
-//   warps 12-19 two groups of 4 staging warps on alternate k-blocks: wait for the raw tile, multiply by the squeeze-excite
+//   warps 12-19 two groups of 4 staging warps on alternate k-blocks (a stage is served by whichever group its k-block falls to): wait for the raw tile, multiply by the squeeze-excite
 //               gates (A_SCALE: project convs, the gated tensor never exists in HBM), split: hi written in place, lo into
 //               the stage's second A buffer at the same swizzled offset (the pass is address-agnostic), fence.proxy.async.
 //               A_STEM: gather the im2col row of the 3x3 stride-2 stem (27 taps + zero pad = 32 floats) instead.
@@ -44,6 +44,10 @@
 //   warps 4-11  two epilogue groups in ping-pong: tcgen05.ld 32x32b.x32 -> + bias, swish_f32 (~3 ulp; NOT tanh.approx: that
 //               approximation is 2^-11), + fp32 residual -> 128-byte-swizzled staging -> TMA store of each 32-column
 //               block (or one bulk copy of the whole tile when N <= 32).
+//               Shallow, wide layers (the first expand convs; epi_groups = 3): warps 16-19 are a THIRD epilogue group and warps
+//               12-15 stage every k-block -- there the epilogue is the critical path and the second staging group only spins.
+// Shared memory: as many pipeline stages as fit (2-8, odd counts included; W resident only when that costs no stage) -- every
+// layer shape is bound by the latency of the TMA -> split -> MMA -> release chain, and ring depth is what hides it.
 // Same skeleton (barrier protocol, accumulator ring, PDL) as the bf16 kernel in gemm_tcgen05.cu; byte geometry is
 // identical (128-byte operand rows), only the element type, the MMA kind and the split pass differ.
 #include "dfd_internal.cuh"
@@ -280,7 +284,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         }
     } else if (warp >= 12 && !(p.epi_groups == 3 && warp >= 16)) {
         const int n_sg = p.epi_groups == 3 ? 1 : 2;            // staging groups
-        // ===== staging warps: two groups of 128 threads on alternate k-blocks (p.stages is even: stage parity == group) =====
+        // ===== staging warps: two groups of 128 threads on alternate k-blocks (one group when epi_groups == 3); stage = k-block counter % p.stages, any stage count =====
         const int g = (warp - 12) >> 2;
         const int t = threadIdx.x - (12 + 4 * g) * 32;         // 0..127
         if (p.a_mode == TA_STEM) {
