@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DFD_ABI_VERSION 1
+#define DFD_ABI_VERSION 2   /* 2: + dfd_face_prep_tta, dfd_face_probability_tta, dfd_set_calibrator, dfd_draw_overlay (additions only) */
 #define DFD_TILE 256          /* forensic analysis size, frame_analysis.py:28 */
 #define DFD_N_RAW 16          /* raw statistics per frame, order = oracle/forensics.py RAW_NAMES */
 #define DFD_N_SIGNALS 6       /* frequency, noise, ela, edge, color, temporal */

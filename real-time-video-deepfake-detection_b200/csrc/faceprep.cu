@@ -11,6 +11,8 @@
 //   k_clahe_lut         per (box, row of 8 CLAHE tiles), warp per tile: L histogram in smem -> clipped, redistributed LUT
 //   k_clahe_hpass       per (box, 16 crop rows), warp per row: LAB/CLAHE/LAB2BGR row into smem, Pillow horizontal pass
 //   k_vpass_up_norm     per (box, 56-row band): Pillow vertical pass into smem, bilinear 224, normalise
+//   k_tta_hpass         test-time augmentation (deepfake_detection.py:408-443): flip / convertScaleAbs / warpAffine of the CLAHE'd
+//                       crop computed per pixel of an augmented row (px_warp.h) and fed straight into the Pillow horizontal pass
 #include "dfd_internal.cuh"
 #include "px_resize.h"
 #include "px_clahe.h"

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_and_blob_layout_agree_with_the_library():
     lib = _lib.load()
-    assert lib.dfd_abi_version() == 1
+    assert lib.dfd_abi_version() == 2
     assert _lib.FORENSIC_BYTES == 192 and _lib.RECORD_BYTES == 72
     _, total = weights.blob_layout()
     assert total == lib.dfd_weights_blob_floats()
