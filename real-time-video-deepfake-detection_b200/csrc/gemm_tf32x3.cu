@@ -70,6 +70,9 @@ struct TGemmParams {
     int n_pad, n_blocks, num_tiles, stages, act, a_mode, hw, b_resident, n_acc, epi_db, dense_c;
     uint32_t stg_stride;       // plain epilogue: bytes per store-staging block (128 rows x 128 B; dense N <= 32 tiles: 128 rows x N x 4 B -- the
                                //    difference buys the huge-M project layers another pipeline stage)
+    int raw_hi;                // plain A (no gate, no im2col): the MMA reads the RAW fp32 tile as the hi operand (the tensor core uses the top 19 bits =
+                               //    hi truncated; lo = x - trunc(x) stays exact), so two of the three MMA groups start when the TMA lands instead of
+                               //    after the split pass, and the pass writes one plane instead of two
     int pf;                    // A tiles prefetched into L2 this many k-blocks ahead of their TMA load (0 = off)
     uint32_t bias_off;         // byte offset of the bias table from the aligned base of dynamic shared memory
     int epi_groups;            // 2: warps 4-11 drain accumulators, warps 12-19 stage A (two groups on alternate k-blocks).  3 (shallow plain layers with a
@@ -249,8 +252,6 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         d_corr = tmem_base + (uint32_t)(acc * p.n_pad);
                         d_main = d_corr + (uint32_t)p.n_pad;
                     }
-                    mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = p.b_resident ? b_region + (uint32_t)kb * 2u * b_plane_bytes : sa + 2u * TA_BYTES;
                     const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + TA_BYTES);
@@ -258,13 +259,29 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const int krem = p.K - kb * TBLOCK_K;
                     const int ksteps = krem >= TBLOCK_K ? TBLOCK_K / 8 : (krem + 7) / 8;
                     // correction terms into their own accumulator (added to a large accumulator, a tiny addend of the opposite sign
-                    // costs a whole ulp under round-toward-zero), then the dominant hi.hi product
-                    for (int k = 0; k < ksteps; k++)
-                        tc_mma_tf32(d_corr, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (kc | k) != 0);
-                    for (int k = 0; k < ksteps; k++)
-                        tc_mma_tf32(d_corr, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc, 1u);
-                    for (int k = 0; k < ksteps; k++)
-                        tc_mma_tf32(d_main, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (uint32_t)((kc | k) != 0));
+                    // costs a whole ulp under round-toward-zero), and the dominant hi.hi product into its own
+                    if (p.raw_hi) {
+                        // hi = the raw tile as the TMA wrote it: these two groups do not wait for the split pass
+                        mbar_wait(raw0 + 8 * stage, phase);
+                        tc_fence_after();
+                        for (int k = 0; k < ksteps; k++)
+                            tc_mma_tf32(d_corr, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                        for (int k = 0; k < ksteps; k++)
+                            tc_mma_tf32(d_main, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (uint32_t)((kc | k) != 0));
+                        mbar_wait(full0 + 8 * stage, phase);       // lo plane written
+                        tc_fence_after();
+                        for (int k = 0; k < ksteps; k++)
+                            tc_mma_tf32(d_corr, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, 1u);
+                    } else {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        for (int k = 0; k < ksteps; k++)
+                            tc_mma_tf32(d_corr, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                        for (int k = 0; k < ksteps; k++)
+                            tc_mma_tf32(d_corr, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc, 1u);
+                        for (int k = 0; k < ksteps; k++)
+                            tc_mma_tf32(d_main, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (uint32_t)((kc | k) != 0));
+                    }
                     tc_commit(empty0 + 8 * stage);                 // frees the smem stage when the MMAs retire
                     const bool chunk_end = kb == num_kb - 1 || kc == p.ch - 1;
                     if (chunk_end) {                               // publish the pair, move on in the ring
@@ -402,11 +419,21 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         const float4 gq = wg[rel * 8 + c];
                         f.x *= gq.x; f.y *= gq.y; f.z *= gq.z; f.w *= gq.w;     // fp32 product rounded once, like torch's x * gate
                     }
-                    uint4 hi, lo;
-                    tf32_split4(f, hi, lo);
                     const uint32_t off = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
-                    sts128(sa + off, hi);
-                    sts128(sa + TA_BYTES + off, lo);
+                    if (p.raw_hi) {
+                        // the raw tile stays as it is (the MMA reads its top 19 bits = hi truncated); lo = rna_tf32(x - trunc(x))
+                        uint4 lo;
+                        lo.x = (__float_as_uint(f.x - __uint_as_float(__float_as_uint(f.x) & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+                        lo.y = (__float_as_uint(f.y - __uint_as_float(__float_as_uint(f.y) & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+                        lo.z = (__float_as_uint(f.z - __uint_as_float(__float_as_uint(f.z) & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+                        lo.w = (__float_as_uint(f.w - __uint_as_float(__float_as_uint(f.w) & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+                        sts128(sa + TA_BYTES + off, lo);
+                    } else {
+                        uint4 hi, lo;
+                        tf32_split4(f, hi, lo);
+                        sts128(sa + off, hi);
+                        sts128(sa + TA_BYTES + off, lo);
+                    }
                 }
                 fence_async_smem();
                 __syncwarp();
@@ -742,6 +769,8 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     p.stages = stages;
     static const int pf_env = getenv("DFD_TF32_PF") ? atoi(getenv("DFD_TF32_PF")) : 0;
     p.pf = a_mode == TA_STEM ? 0 : pf_env;
+    static const bool raw_hi_off = getenv("DFD_TF32_RAWHI") && atoi(getenv("DFD_TF32_RAWHI")) == 0;
+    p.raw_hi = (a_mode == TA_PLAIN && !raw_hi_off) ? 1 : 0;
     p.bias_off = (uint32_t)(stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes);
     const size_t smem = (size_t)p.bias_off + bias_bytes + 1024;
     TGemmKernel kern = tgemm_kernel(residual != nullptr, act != 0, p.dense_c != 0);
