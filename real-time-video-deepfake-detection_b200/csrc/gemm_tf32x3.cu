@@ -135,12 +135,33 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr));
 }
 
+// Pipeline stage and mbarrier parities of the CTA's j-th k-block: stage = j % S, ring parity (j / S) & 1.
+// The "raw tile landed" barrier needs more care.  Two staging groups take alternate k-blocks and a group waits only for ITS
+// k-blocks; with an odd S a stage alternates between the groups, so on a per-stage barrier a group would skip every other
+// phase -- and a parity wait can only tell the current phase from the one before it (if TMA j + 1 lands before TMA j, the group
+// would fall through its wait for j + 3 and split stale data; the bf16 kernel saw this as a rare hang with 3 stages).  With an
+// odd S every stage therefore has TWO raw barriers, one per group (rsel = j & 1): barrier (stage, group) is used once every
+// 2 S k-blocks, by that group alone and in consecutive phases.  (Even S, or one staging group: a stage belongs to one group.)
+// Kept as running counters (the producer and the MMA issuer are single threads on the critical path: divisions by a run-time
+// stage count there cost a quarter of a microsecond per k-block, 6 % of the layer table).
+struct TStageCursor {
+    int stage, c2, two_s, S, split;          // c2 = j % (2 S)
+    uint32_t phase, rph;
+    __device__ __forceinline__ void init(int n_sg, int S_) { S = S_; two_s = 2 * S_; split = (n_sg == 2 && (S_ & 1)) ? 1 : 0; stage = 0; c2 = 0; phase = 0; rph = 0; }
+    __device__ __forceinline__ void advance() {
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++c2 == two_s) { c2 = 0; rph ^= 1u; }
+    }
+    __device__ __forceinline__ int rsel() const { return split ? (c2 & 1) : 0; }          // (2 S is even: c2 & 1 == j & 1)
+    __device__ __forceinline__ uint32_t rphase() const { return split ? rph : phase; }
+};
+
 template <bool RES, bool ACT, bool DENSE>
 __global__ void __launch_bounds__(TGEMM_THREADS, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh,
               const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_c, const TGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[5 * 8 + 1];     // full[8], empty[8], raw[8], tmem_full[8], tmem_empty[8], bfull
+    __shared__ __align__(8) uint64_t bars[6 * 8 + 1];     // full[8], empty[8], raw[8], tmem_full[8], tmem_empty[8], bfull, raw of group 1 [8]
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float sgate[8][4][TBLOCK_K];  // A_SCALE: per staging warp, the k-block's gates of the tile's <= 4 images
 
@@ -153,6 +174,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const uint32_t staging = b_region + (p.b_resident ? (uint32_t)num_kb * 2u * b_plane_bytes : 0u);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), raw0 = smem_u32(&bars[16]);
     const uint32_t tfull0 = smem_u32(&bars[24]), tempty0 = smem_u32(&bars[32]), bfull = smem_u32(&bars[40]);
+    const uint32_t raw1 = smem_u32(&bars[41]);               // (TStageCursor: odd stage counts)
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(p.n_acc - 1) * (uint32_t)p.n_pad + (((uint32_t)p.n_pad + 31u) & ~31u)) tmem_cols <<= 1;
 
@@ -170,7 +192,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_init(bfull, 1);
         for (int s = 0; s < p.stages; s++) {
             // full[s]: the 4 staging warps of the stage's group (+ the TMA thread's expect_tx for a non-resident stem W: never, W is 8 KB)
-            mbar_init(full0 + 8 * s, 4); mbar_init(empty0 + 8 * s, 1); mbar_init(raw0 + 8 * s, 1);
+            mbar_init(full0 + 8 * s, 4); mbar_init(empty0 + 8 * s, 1); mbar_init(raw0 + 8 * s, 1); mbar_init(raw1 + 8 * s, 1);
         }
         // tempty[a]: one epilogue group drains an accumulator (plain), or both do (chunked accumulation)
         for (int a = 0; a < 8; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, p.chunked ? 8 : 4); }
@@ -199,7 +221,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
+            TStageCursor cur;
+            cur.init(p.epi_groups == 3 ? 1 : 2, p.stages);
             const bool load_a = p.a_mode != TA_STEM, load_b = !p.b_resident;
             const uint32_t tx = (load_a ? (uint32_t)TA_BYTES : 0u) + (load_b ? 2u * b_plane_bytes : 0u);
             if (tx != 0) {
@@ -219,15 +242,17 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
                     for (int kb = 0; kb < num_kb; kb++) {
                         if (p.pf > 0) pf_issue();
+                        const int stage = cur.stage; const uint32_t phase = cur.phase;
+                        const uint32_t rawb = (cur.rsel() ? raw1 : raw0) + 8 * stage;
+                        cur.advance();
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + 2u * TA_BYTES;
-                        mbar_expect_tx(raw0 + 8 * stage, tx);
-                        if (load_a) tma_load_2d(sa, &map_a, kb * TBLOCK_K, m_blk * TBLOCK_M, raw0 + 8 * stage);
+                        mbar_expect_tx(rawb, tx);
+                        if (load_a) tma_load_2d(sa, &map_a, kb * TBLOCK_K, m_blk * TBLOCK_M, rawb);
                         if (load_b) {
-                            tma_load_2d(sb, &map_bh, kb * TBLOCK_K, n_blk * p.n_pad, raw0 + 8 * stage);
-                            tma_load_2d(sb + b_plane_bytes, &map_bl, kb * TBLOCK_K, n_blk * p.n_pad, raw0 + 8 * stage);
+                            tma_load_2d(sb, &map_bh, kb * TBLOCK_K, n_blk * p.n_pad, rawb);
+                            tma_load_2d(sb + b_plane_bytes, &map_bl, kb * TBLOCK_K, n_blk * p.n_pad, rawb);
                         }
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -237,7 +262,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         if (lane == 0) {
             // idesc: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TBLOCK_M >> 4) << 24);
-            int stage = 0; uint32_t phase = 0;
+            TStageCursor cur;
+            cur.init(p.epi_groups == 3 ? 1 : 2, p.stages);
             int acc = 0; uint32_t acc_phase = 0;
             int tile_it = 0;
             if (p.b_resident) mbar_wait(bfull, 0);
@@ -252,6 +278,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         d_corr = tmem_base + (uint32_t)(acc * p.n_pad);
                         d_main = d_corr + (uint32_t)p.n_pad;
                     }
+                    const int stage = cur.stage, rsel = cur.rsel(); const uint32_t phase = cur.phase, rphase = cur.rphase();
+                    cur.advance();
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = p.b_resident ? b_region + (uint32_t)kb * 2u * b_plane_bytes : sa + 2u * TA_BYTES;
                     const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + TA_BYTES);
@@ -262,7 +290,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     // costs a whole ulp under round-toward-zero), and the dominant hi.hi product into its own
                     if (p.raw_hi) {
                         // hi = the raw tile as the TMA wrote it: these two groups do not wait for the split pass
-                        mbar_wait(raw0 + 8 * stage, phase);
+                        mbar_wait((rsel ? raw1 : raw0) + 8 * stage, rphase);
                         tc_fence_after();
                         for (int k = 0; k < ksteps; k++)
                             tc_mma_tf32(d_corr, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc, (kc | k) != 0);
@@ -295,15 +323,17 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         acc += 2;
                         if (acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
                     }
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp >= 12 && !(p.epi_groups == 3 && warp >= 16)) {
         const int n_sg = p.epi_groups == 3 ? 1 : 2;            // staging groups
-        // ===== staging warps: two groups of 128 threads on alternate k-blocks (one group when epi_groups == 3); stage = k-block counter % p.stages, any stage count =====
+        // ===== staging warps: two groups of 128 threads on alternate k-blocks (one group when epi_groups == 3); stage / barrier assignment: TStageCursor =====
         const int g = (warp - 12) >> 2;
         const int t = threadIdx.x - (12 + 4 * g) * 32;         // 0..127
+        TStageCursor sc;                                      // positioned on this group's first k-block (j = g)
+        sc.init(n_sg, p.stages);
+        if (g == 1) sc.advance();
         if (p.a_mode == TA_STEM) {
             // stem im2col (one k-block per tile): row = output pixel; 3 kernel rows x 9 contiguous floats (3 px x 3 ch) -> 27 taps
             // + 5 zeros.  The 15 loads of the group's NEXT tile are in flight while it waits for the smem slot of the current one.
@@ -338,8 +368,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             for (; tile < p.num_tiles; it += 2) {
                 const int ntile = blockIdx.x + (it + 2) * (int)gridDim.x;
                 if (ntile < p.num_tiles) gather(ntile, nxt);
-                const int stage = it % p.stages;
-                const uint32_t phase = (uint32_t)(it / p.stages) & 1u;
+                const int stage = sc.stage; const uint32_t phase = sc.phase;       // (the stem has no TMA loads: no raw barrier)
+                sc.advance(); sc.advance();
                 const uint32_t sa = smem_base + stage * stage_bytes;
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
                 const int row = t;
@@ -392,15 +422,15 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             prefetch();
             for (int j = g; tile < p.num_tiles; j += n_sg) {
                 const int m0 = (tile / p.n_blocks) * TBLOCK_M;
-                const int stage = j % p.stages;
-                const uint32_t phase = (uint32_t)(j / p.stages) & 1u;
+                const int stage = sc.stage, rsel = sc.rsel(); const uint32_t rphase = sc.rphase();
+                sc.advance(); if (n_sg == 2) sc.advance();
                 const uint32_t sa = smem_base + stage * stage_bytes;
                 if (gated) { wg[gl_img * 8 + gl_c] = q; __syncwarp(); }
                 const int k = kb * TBLOCK_K + c * 4;
                 kb += n_sg;
                 norm();
                 prefetch();                                        // next k-block's gates fly during the wait and the pass
-                mbar_wait(raw0 + 8 * stage, phase);                // raw A (and W) tile landed
+                mbar_wait((rsel ? raw1 : raw0) + 8 * stage, rphase);       // raw A (and W) tile landed
                 const int img0 = gated ? m0 / p.hw : 0, rem0 = gated ? m0 - img0 * p.hw : 0;
                 const int last = p.M - 1 - m0;                     // rows beyond M are clamped to the last row (their data is zero fill)
                 uint4 v[8];
