@@ -799,8 +799,10 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     p.stages = stages;
     static const int pf_env = getenv("DFD_TF32_PF") ? atoi(getenv("DFD_TF32_PF")) : 0;
     p.pf = a_mode == TA_STEM ? 0 : pf_env;
-    static const bool raw_hi_off = getenv("DFD_TF32_RAWHI") && atoi(getenv("DFD_TF32_RAWHI")) == 0;
-    p.raw_hi = (a_mode == TA_PLAIN && !raw_hi_off) ? 1 : 0;
+    // OFF by default (DFD_TF32_RAWHI=1): 1.3 % faster (same-box A/B, 4.949 vs 5.012 ms per 256 crops), but the truncated hi leaves a
+    // lo twice as large and the whole network's max |dp| goes from 5.5e-6 to 1.2e-5 -- inside the 1e-4 gate, not worth the margin
+    static const bool raw_hi_on = getenv("DFD_TF32_RAWHI") && atoi(getenv("DFD_TF32_RAWHI")) != 0;
+    p.raw_hi = (a_mode == TA_PLAIN && raw_hi_on) ? 1 : 0;
     p.bias_off = (uint32_t)(stages * stage_bytes + (p.b_resident ? b_bytes : 0) + staging_bytes);
     const size_t smem = (size_t)p.bias_off + bias_bytes + 1024;
     TGemmKernel kern = tgemm_kernel(residual != nullptr, act != 0, p.dense_c != 0);
