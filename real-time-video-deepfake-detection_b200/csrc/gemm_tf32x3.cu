@@ -753,6 +753,10 @@ int dfd_gemm_tf32x3(dfd_ctx* ctx, int a_mode, const float* A, const float* se, i
     // epilogue-bound (b2.project: 196 us plain, 310 us chunked), their truncation bias is small and compensated as a whole
     const bool chunked = num_kb > plain_kb;
     p.chunked = chunked ? 1 : 0;
+    // plain layers: the two epilogue groups take alternate tiles and an accumulator pair must always be drained by the same group
+    // (the parity-wait notes at TStageCursor apply to the "accumulator full" barriers too), so their ring holds an EVEN number of
+    // pairs.  No EfficientNet-B0 shape is affected (n_pad = 80 layers are chunked: both groups drain every chunk there).
+    if (!chunked && p.n_acc == 6) p.n_acc = 4;
     // Expected-value compensation of the tensor core's round-toward-zero accumulation (measured with tools/tf32_bias.py: the
     // GEMM's error is, to 70 %, a pure scale factor 1 - beta; profiles/tf32_bias_r02.txt).  Chunked layers: beta per main-term
     // instruction of a chunk; single-accumulator layers (all 12 x K / 32 instructions in one accumulator): beta per layer depth.
